@@ -1,0 +1,156 @@
+/* wepp_b200.h — C ABI of the B200-native WEPP read-placement library (libwepp_b200.so).
+ *
+ * This is the drop-in boundary for the reference's placement hot path.  Citations are
+ * file:line relative to the TurakhiaLab/WEPP tree (commit 6177aced):
+ *
+ *   wepp_set_arena        <- the flattened condensed tree the reference's `arena` holds:
+ *                            std::vector<haplotype> nodes, src/WEPP/arena.cpp:3-56
+ *                            (haplotype::parent / ::muts, src/WEPP/haplotype.hpp:10-43)
+ *   wepp_set_reads        <- std::vector<raw_read>, src/WEPP/read.hpp:6-12, after masking
+ *                            (src/WEPP/arena.hpp:62-72)
+ *   wepp_set_mapped       <- haplotype::mapped, src/WEPP/haplotype.hpp:36 (read at
+ *                            src/WEPP/initial_filter.cpp:130)
+ *   wepp_place            <- wepp_filter::cartesian_map, src/WEPP/initial_filter.cpp:139-211
+ *                            (which calls single_read_tree, :41-135, for every read)
+ *   wepp_place_subset     <- single_read_tree on chosen reads under the current `mapped`
+ *                            mask, as wepp_filter::remove_read does, :298-302
+ *   wepp_rescore          <- haplotype::mutation_distance(const raw_read&),
+ *                            src/WEPP/haplotype.hpp:123-177, over a candidate set with the
+ *                            min / argmin idiom of src/WEPP/arena.cpp:614-625 and :846-857
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host buffer, the
+ * library owns all device memory; every function returns 0 on success and a negative
+ * WEPP_E_* code on failure, with a message available from wepp_last_error() (the
+ * reference itself reports errors with fprintf(stderr)+exit(1), e.g. src/WEPP/sam2pb.cpp:497-500).
+ * One handle drives one GPU and is used from one host thread at a time.  There is no CPU
+ * fallback: without a usable CUDA device wepp_create fails.
+ *
+ * Nucleotide codes are the reference's 4-bit one-hot / IUPAC ids
+ * (src/mutation_annotated_tree.cpp:19-74): A=1 C=2 G=4 T=8, unions for ambiguity, N=15.
+ * Tree mutations may carry any code 1..15 in mut_nuc; read alleles must be one of
+ * 1,2,4,8,15 (what sam2PB emits, src/WEPP/sam2pb.cpp:245-249) — anything else is
+ * rejected with WEPP_E_INVALID.
+ */
+#ifndef WEPP_B200_H
+#define WEPP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WEPP_NUM_RANGE_BINS 50      /* src/WEPP/config.hpp:13 */
+#define WEPP_MAX_CACHED_EPP 2048    /* src/WEPP/config.hpp:9  */
+
+#define WEPP_OK           0
+#define WEPP_E_INVALID   -1   /* bad argument / malformed input            */
+#define WEPP_E_CUDA      -2   /* CUDA runtime error (message has details)  */
+#define WEPP_E_STATE     -3   /* call order violated (e.g. place before set_reads) */
+#define WEPP_E_CAPACITY  -4   /* caller-provided buffer too small          */
+
+typedef struct wepp_handle wepp_handle;
+
+/* Life cycle.  `device` is a CUDA ordinal.  */
+int         wepp_create(int device, wepp_handle** out);
+void        wepp_destroy(wepp_handle* h);
+const char* wepp_last_error(void);
+int         wepp_abi_version(void);
+
+/* Tunables (optional, before wepp_set_arena): stripe width in bases used to bucket read
+ * windows (default 32) and reads per warp lane K in {2,4,8} (0 = choose per bucket). */
+int wepp_set_options(wepp_handle* h, int32_t stripe_width, int32_t reads_per_lane);
+
+/* The flattened tree.  Node v is the v-th haplotype in preorder (arena index):
+ * parent[0] = -1 and parent[v] < v.  Node v's mutations are
+ * mut_pos/mut_ref/mut_nuc[mut_off[v] .. mut_off[v+1]) with 1 <= pos <= genome_size and at
+ * most one mutation per position per node.  Builds the device-resident Euler-tour event
+ * stripes.  */
+int wepp_set_arena(wepp_handle* h, int32_t n_nodes, const int32_t* parent, const int64_t* mut_off,
+                   const int32_t* mut_pos, const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size);
+
+/* The collapsed reads.  Window [start,end] is 1-based and closed; read r's mutation list
+ * is rm_pos/rm_nuc[rm_off[r] .. rm_off[r+1]), sorted by position, inside the window.
+ * Packs the reads, groups them into window buckets and builds the per-bucket Euler lists. */
+int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const int32_t* end,
+                   const int32_t* degree, const int64_t* rm_off, const int32_t* rm_pos, const uint8_t* rm_nuc);
+
+/* haplotype::mapped for every node (NULL = none mapped).  */
+int wepp_set_mapped(wepp_handle* h, const uint8_t* mapped);
+
+/* cartesian_map over all reads.  Results stay on the device until fetched.
+ * epp_cap: reads whose multiplicity is <= epp_cap get their sorted EPP node list stored
+ * (reference: MAX_CACHED_EPP_SIZE); epp_capacity: total int32 slots reserved for them
+ * (lists that do not fit are dropped and reported as uncached).  */
+int wepp_place(wepp_handle* h, int32_t epp_cap, int64_t epp_capacity);
+
+/* single_read_tree for a subset of reads (indices into the set_reads order) under the
+ * current mapped mask; per-node accumulators are NOT touched.  Per-read results are
+ * written for those reads only.  */
+int wepp_place_subset(wepp_handle* h, int64_t n_sel, const int64_t* read_idx, int32_t epp_cap, int64_t epp_capacity);
+
+/* Fetch results of the last place call (any pointer may be NULL to skip it).
+ * max_parsimony[R], multiplicity[R]; score[N] (double), counts[N*50] (int32, row = node).
+ * EPP lists: epp_off[R+1] CSR into epp_nodes (sorted arena indices); reads that were not
+ * cached have an empty range; *n_epp receives the number of slots used.  */
+int wepp_get_read_results(wepp_handle* h, int32_t* max_parsimony, int32_t* multiplicity);
+int wepp_get_node_results(wepp_handle* h, double* score, int32_t* counts);
+int wepp_get_epp(wepp_handle* h, int64_t* epp_off, int32_t* epp_nodes, int64_t capacity, int64_t* n_epp);
+
+/* The whole reference call in one go with host buffers in and out
+ * (set_reads + set_mapped + place + get_*): what the cgo/ctypes/C++ binding calls.  */
+int wepp_cartesian_map(wepp_handle* h, int64_t n_reads, const int32_t* start, const int32_t* end,
+                       const int32_t* degree, const int64_t* rm_off, const int32_t* rm_pos, const uint8_t* rm_nuc,
+                       const uint8_t* mapped, int32_t* max_parsimony, int32_t* multiplicity, double* score,
+                       int32_t* counts);
+
+/* Candidate re-scoring (K4).  Candidates are arena indices; for every read the minimum
+ * mutation distance over the candidates and, optionally, the dense distance matrix
+ * dist[R*n_cand] and the argmin sets as CSR (am_off[R+1], am_idx = positions in the
+ * candidate list, in candidate order; capacity am_capacity).  */
+int wepp_rescore(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, int32_t* min_dist, int32_t* dist,
+                 int64_t* am_off, int32_t* am_idx, int64_t am_capacity);
+
+/* Device-resident views for callers that keep results on the GPU (NCCL all-reduce of the
+ * per-node arrays in the multi-GPU driver).  Pointers stay valid until the next
+ * set_arena / destroy.  */
+#define WEPP_BUF_SCORE      1   /* double[N]            */
+#define WEPP_BUF_COUNTS     2   /* int32[N*50]          */
+#define WEPP_BUF_MAX_PARS   3   /* int32[R], read order */
+#define WEPP_BUF_MULT       4   /* int32[R], read order */
+int wepp_device_buffer(wepp_handle* h, int32_t which, void** dev_ptr, int64_t* n_bytes);
+
+/* Introspection for benchmarks: numbers describing the last wepp_place.  */
+typedef struct wepp_stats {
+    int64_t n_nodes, n_events, n_euler_entries;     /* tree */
+    int64_t n_reads, n_buckets, n_lists, n_tiles;   /* read bucketing */
+    int64_t list_entries_total;                     /* sum of per-list entries */
+    int64_t scanned_entries;                        /* sum over tiles of list length (one pass) */
+    int64_t scanned_read_entries;                   /* sum over reads of their list length */
+    int64_t algorithmic_bytes;                      /* DESIGN.md §roofline definition, per place */
+    int64_t kernel_launches;                        /* kernels launched by the last place */
+    float   ms_place_total;                         /* CUDA events, whole place */
+    float   ms_scan_kernel;                         /* the dominant placement kernel */
+    float   ms_node_kernels;                        /* expand + prefix scans */
+    int32_t reads_per_tile;
+    int32_t stripe_width;
+} wepp_stats;
+int wepp_get_stats(wepp_handle* h, wepp_stats* out);
+
+/* Host-only introspection (no GPU needed; used by the CPU test-suite): the Euler-tour event
+ * stripes built from an arena (4 x uint32 per entry: preorder idx, position, signed-delta bytes
+ * for read allele ref/A/C/G, delta byte for T) and the read bucketing plan.  Both return a
+ * count (>= 0) or a negative WEPP_E_* code.  */
+int64_t wepp_host_euler_stripes(int32_t n_nodes, const int32_t* parent, const int64_t* mut_off, const int32_t* mut_pos,
+                                const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size,
+                                int32_t stripe_width, uint32_t* entries, int64_t capacity, int64_t* stripe_off,
+                                int32_t stripe_off_len);
+int64_t wepp_host_read_plan(int32_t genome_size, int32_t stripe_width, int32_t reads_per_lane, int64_t n_reads,
+                            const int32_t* start, const int32_t* end, const int32_t* degree, const int64_t* rm_off,
+                            const int32_t* rm_pos, const uint8_t* rm_nuc, int64_t* perm, int32_t* qs, int32_t* qe,
+                            int32_t* bin, int32_t* reads_per_tile);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WEPP_B200_H */

@@ -1,0 +1,92 @@
+"""ctypes binding of libwepp_b200.so (include/wepp_b200.h).  Fails loudly if the CUDA
+library has not been built — there is no CPU fallback in the product path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwepp_b200.so")
+
+i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+VP = C.c_void_p
+
+
+class WeppStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        "n_nodes", "n_events", "n_euler_entries", "n_reads", "n_buckets", "n_lists", "n_tiles",
+        "list_entries_total", "scanned_entries", "scanned_read_entries", "algorithmic_bytes",
+        "kernel_launches")] + [("ms_place_total", C.c_float), ("ms_scan_kernel", C.c_float),
+                               ("ms_node_kernels", C.c_float), ("reads_per_tile", C.c_int32),
+                               ("stripe_width", C.c_int32)]
+
+    def as_dict(self) -> dict:
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+# name -> (restype, argtypes); every symbol include/wepp_b200.h declares
+SIGNATURES = {
+    "wepp_create": (C.c_int, [C.c_int, C.POINTER(VP)]),
+    "wepp_destroy": (None, [VP]),
+    "wepp_last_error": (C.c_char_p, []),
+    "wepp_abi_version": (C.c_int, []),
+    "wepp_set_options": (C.c_int, [VP, C.c_int32, C.c_int32]),
+    "wepp_set_arena": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, C.c_int32]),
+    "wepp_set_reads": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, VP]),
+    "wepp_set_mapped": (C.c_int, [VP, VP]),
+    "wepp_place": (C.c_int, [VP, C.c_int32, C.c_int64]),
+    "wepp_place_subset": (C.c_int, [VP, C.c_int64, VP, C.c_int32, C.c_int64]),
+    "wepp_get_read_results": (C.c_int, [VP, VP, VP]),
+    "wepp_get_node_results": (C.c_int, [VP, VP, VP]),
+    "wepp_get_epp": (C.c_int, [VP, VP, VP, C.c_int64, C.POINTER(C.c_int64)]),
+    "wepp_cartesian_map": (C.c_int, [VP, C.c_int64] + [VP] * 11),
+    "wepp_rescore": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, C.c_int64]),
+    "wepp_device_buffer": (C.c_int, [VP, C.c_int32, C.POINTER(VP), C.POINTER(C.c_int64)]),
+    "wepp_get_stats": (C.c_int, [VP, C.POINTER(WeppStats)]),
+    "wepp_host_euler_stripes": (C.c_int64, [C.c_int32, VP, VP, VP, VP, VP, C.c_int32, C.c_int32, VP, C.c_int64, VP, C.c_int32]),
+    "wepp_host_read_plan": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [VP] * 10 + [C.POINTER(C.c_int32)]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m wepp_b200.build` "
+                "(nvcc, sm_100a).  wepp_b200 has no CPU fallback.")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def ptr(a):
+    """Pointer to a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(VP)
+
+
+class WeppError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"wepp_b200 error {code}: {msg}")
+        self.code = code
+
+
+def check(rc: int) -> int:
+    if rc < 0:
+        raise WeppError(int(rc), load().wepp_last_error().decode("utf-8", "replace"))
+    return rc

@@ -1,0 +1,285 @@
+// host_prep.cpp — see host_prep.h.
+#include "host_prep.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <unordered_map>
+
+namespace wepp {
+
+namespace {
+
+constexpr int NUM_RANGE_BINS = 50;  // reference: src/WEPP/config.hpp:13
+
+// Mismatch state of a haplotype whose last event at a position has (mut, ref), for a read
+// whose allele class there is c: 0 = "as reference" (no entry in the read's mutation list),
+// 1..4 = the read carries A/C/G/T.  Reference: src/WEPP/initial_filter.cpp:64-66 —
+//   read_nuc = (read has a mutation here) ? its mut_nuc : event.ref_nuc;
+//   mismatch = read_nuc != N && read_nuc != event.mut_nuc.
+inline int mismatch_after(int c, int mut, int ref) {
+    if (c == 0) return mut != ref;
+    return (1 << (c - 1)) != mut;
+}
+// Before the first event on the path the state is the seed set (initial_filter.cpp:118-123):
+// a mismatch iff the read carries a non-N mutation at the position.
+inline int mismatch_seed(int c) { return c != 0; }
+
+inline uint32_t pack4(const int* d) {
+    return (uint32_t)(uint8_t)(int8_t)d[0] | ((uint32_t)(uint8_t)(int8_t)d[1] << 8) |
+           ((uint32_t)(uint8_t)(int8_t)d[2] << 16) | ((uint32_t)(uint8_t)(int8_t)d[3] << 24);
+}
+
+}  // namespace
+
+std::string build_euler_stripes(int32_t n_nodes, const int32_t* parent, const int64_t* mut_off,
+                                const int32_t* mut_pos, const uint8_t* mut_ref, const uint8_t* mut_nuc,
+                                int32_t genome_size, int32_t stripe_width, EulerStripes& out) {
+    if (n_nodes < 1) return "arena has no nodes";
+    if (n_nodes >= (1 << 30)) return "arena too large (n_nodes must be < 2^30)";
+    if (genome_size < NUM_RANGE_BINS) return "genome_size must be >= 50";
+    if (stripe_width < 1) return "stripe_width must be >= 1";
+    if (parent[0] != -1) return "parent[0] must be -1";
+    if (mut_off[0] != 0) return "mut_off[0] must be 0";
+    const int64_t n_mut = mut_off[n_nodes];
+
+    // subtree ends from the preorder parent array (validates parent[v] < v)
+    std::vector<int32_t> sub_end(n_nodes);
+    {
+        std::vector<int32_t> size(n_nodes, 1);
+        for (int32_t v = n_nodes - 1; v >= 1; --v) {
+            int32_t p = parent[v];
+            if (p < 0 || p >= v) return "parent[v] must satisfy 0 <= parent[v] < v (preorder)";
+            size[p] += size[v];
+        }
+        for (int32_t v = 0; v < n_nodes; ++v) sub_end[v] = v + size[v];
+        // preorder validity: v must lie inside its parent's interval, which the sizes above
+        // only guarantee if the numbering really is a DFS order.
+        for (int32_t v = 1; v < n_nodes; ++v)
+            if (sub_end[v] > sub_end[parent[v]]) return "node numbering is not a preorder of the tree";
+    }
+
+    // nearest-ancestor event per position, maintained along the DFS
+    std::vector<int64_t> last_ev((size_t)genome_size + 1, -1);
+    std::vector<int64_t> prev_ev((size_t)n_mut, -1);
+    {
+        std::vector<int32_t> stack;
+        for (int32_t v = 0; v < n_nodes; ++v) {
+            while (!stack.empty() && sub_end[stack.back()] <= v) {
+                int32_t u = stack.back();
+                stack.pop_back();
+                for (int64_t k = mut_off[u + 1] - 1; k >= mut_off[u]; --k) last_ev[mut_pos[k]] = prev_ev[k];
+            }
+            if (mut_off[v + 1] < mut_off[v]) return "mut_off must be non-decreasing";
+            for (int64_t k = mut_off[v]; k < mut_off[v + 1]; ++k) {
+                int32_t p = mut_pos[k];
+                if (p < 1 || p > genome_size) return "mutation position outside [1, genome_size]";
+                if (mut_nuc[k] < 1 || mut_nuc[k] > 15 || mut_ref[k] < 1 || mut_ref[k] > 15)
+                    return "mutation nucleotide code outside 1..15";
+                if (last_ev[p] >= mut_off[v]) return "a node has two mutations at the same position";
+                prev_ev[k] = last_ev[p];
+                last_ev[p] = k;
+            }
+            stack.push_back(v);
+        }
+    }
+
+    // entries (enter + exit), then counting sort by (stripe, idx)
+    const int32_t q = stripe_width;
+    const int32_t n_stripes = genome_size / q + 1;
+    std::vector<Entry> raw;
+    raw.reserve((size_t)n_mut * 2);
+    int64_t n_events = 0;
+    for (int32_t v = 0; v < n_nodes; ++v) {
+        for (int64_t k = mut_off[v]; k < mut_off[v + 1]; ++k) {
+            int d[5];
+            bool any = false;
+            const int64_t pk = prev_ev[k];
+            for (int c = 0; c < 5; ++c) {
+                int after = mismatch_after(c, mut_nuc[k], mut_ref[k]);
+                int before = pk < 0 ? mismatch_seed(c) : mismatch_after(c, mut_nuc[pk], mut_ref[pk]);
+                d[c] = after - before;
+                any |= d[c] != 0;
+            }
+            if (!any) continue;  // event changes nothing for any read: drop
+            ++n_events;
+            raw.push_back(Entry{(uint32_t)v, (uint32_t)mut_pos[k], pack4(d), (uint32_t)(uint8_t)(int8_t)d[4]});
+            if (sub_end[v] < n_nodes) {
+                int nd[5];
+                for (int c = 0; c < 5; ++c) nd[c] = -d[c];
+                raw.push_back(Entry{(uint32_t)sub_end[v], (uint32_t)mut_pos[k], pack4(nd), (uint32_t)(uint8_t)(int8_t)nd[4]});
+            }
+        }
+    }
+    // pass 1: stable counting sort by idx
+    std::vector<Entry> by_idx(raw.size());
+    {
+        std::vector<int64_t> cnt((size_t)n_nodes + 1, 0);
+        for (const Entry& e : raw) ++cnt[e.x + 1];
+        for (int32_t v = 0; v < n_nodes; ++v) cnt[v + 1] += cnt[v];
+        for (const Entry& e : raw) by_idx[cnt[e.x]++] = e;
+    }
+    raw.clear();
+    raw.shrink_to_fit();
+    // pass 2: stable counting sort by stripe
+    out.stripe_width = q;
+    out.n_stripes = n_stripes;
+    out.n_events = n_events;
+    out.stripe_off.assign((size_t)n_stripes + 1, 0);
+    for (const Entry& e : by_idx) ++out.stripe_off[e.y / q + 1];
+    for (int32_t s = 0; s < n_stripes; ++s) out.stripe_off[s + 1] += out.stripe_off[s];
+    out.entries.resize(by_idx.size());
+    {
+        std::vector<int64_t> cur(out.stripe_off.begin(), out.stripe_off.end() - 1);
+        for (const Entry& e : by_idx) out.entries[cur[e.y / q]++] = e;
+    }
+    return "";
+}
+
+std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t n_reads, const int32_t* start,
+                            const int32_t* end, const int32_t* degree, const int64_t* rm_off, const int32_t* rm_pos,
+                            const uint8_t* rm_nuc, int32_t reads_per_lane, const int64_t* subset, int64_t n_subset,
+                            ReadPlan& out) {
+    const int32_t q = es.stripe_width;
+    const int32_t bin_size = genome_size / NUM_RANGE_BINS;
+    const int64_t n_sel = subset ? n_subset : n_reads;
+    out = ReadPlan();
+    out.n_reads = n_sel;
+
+    // bucket key per selected read
+    std::vector<int32_t> bucket_of((size_t)n_sel);
+    std::unordered_map<uint64_t, int32_t> bucket_id, list_id;
+    std::vector<int64_t> bucket_count;
+    for (int64_t i = 0; i < n_sel; ++i) {
+        const int64_t r = subset ? subset[i] : i;
+        if (r < 0 || r >= n_reads) return "read index out of range";
+        const int32_t s = start[r], e = end[r];
+        if (s < 1 || s > genome_size || e > genome_size || e < s - 1)
+            return "read window must satisfy 1 <= start <= genome_size, start-1 <= end <= genome_size";
+        if (degree[r] < 0) return "read degree must be >= 0";
+        if (rm_off[r + 1] < rm_off[r]) return "rm_off must be non-decreasing";
+        int32_t prev = s - 1;
+        for (int64_t k = rm_off[r]; k < rm_off[r + 1]; ++k) {
+            if (rm_pos[k] <= prev || rm_pos[k] > e) return "read mutations must be sorted, unique and inside [start,end]";
+            prev = rm_pos[k];
+            const uint8_t c = rm_nuc[k];
+            if (!(c == 1 || c == 2 || c == 4 || c == 8 || c == 15)) return "read allele code must be one of 1,2,4,8,15";
+        }
+        const int32_t qs = s / q, qe = std::max(e, s) / q;
+        const int32_t bin = std::min(s / bin_size, NUM_RANGE_BINS - 1);
+        const uint64_t lkey = ((uint64_t)qs << 32) | (uint32_t)qe;
+        auto li = list_id.find(lkey);
+        int32_t l;
+        if (li == list_id.end()) {
+            l = (int32_t)out.lists.size();
+            list_id.emplace(lkey, l);
+            ListDesc ld;
+            ld.qs = qs;
+            ld.qe = qe;
+            ld.b0 = qs * q;
+            ld.width = (qe - qs + 1) * q;
+            ld.n = (int32_t)(1 + es.stripe_off[qe + 1] - es.stripe_off[qs]);
+            ld.off = 0;
+            ld.pad = 0;
+            out.lists.push_back(ld);
+        } else {
+            l = li->second;
+        }
+        const uint64_t bkey = ((uint64_t)l << 8) | (uint32_t)bin;
+        auto bi = bucket_id.find(bkey);
+        int32_t b;
+        if (bi == bucket_id.end()) {
+            b = (int32_t)out.buckets.size();
+            bucket_id.emplace(bkey, b);
+            out.buckets.push_back(BucketDesc{0, l, bin});
+            bucket_count.push_back(0);
+        } else {
+            b = bi->second;
+        }
+        bucket_of[i] = b;
+        ++bucket_count[b];
+    }
+    if (out.lists.size() > 0) {
+        for (const ListDesc& l : out.lists) {
+            if (l.width > 65535) return "read window wider than 65535 bases is not supported";
+            out.max_width = std::max(out.max_width, l.width);
+        }
+    }
+    // offsets
+    int64_t off = 0;
+    for (ListDesc& l : out.lists) {
+        l.off = off;
+        off += l.n;
+    }
+    out.list_entries_total = off;
+    int64_t acc = 0;
+    for (BucketDesc& b : out.buckets) {
+        b.acc_off = acc;
+        acc += out.lists[b.list].n;
+    }
+    out.acc_total = acc;
+
+    // reads per tile
+    int32_t k = reads_per_lane;
+    if (k != 2 && k != 4 && k != 8) {
+        k = out.max_width <= 224 ? 8 : (out.max_width <= 448 ? 4 : 2);
+        auto tiles_for = [&](int kk) {
+            int64_t t = 0;
+            for (int64_t c : bucket_count) t += (c + 32 * kk - 1) / (32 * kk);
+            return t;
+        };
+        while (k > 2 && tiles_for(k) < 2368) k >>= 1;  // keep >= 2 tiles per resident warp when reads are few
+    }
+    out.reads_per_tile = 32 * k;
+
+    // counting sort of the selected reads by bucket
+    const size_t nb = out.buckets.size();
+    std::vector<int64_t> first(nb + 1, 0);
+    for (size_t b = 0; b < nb; ++b) first[b + 1] = first[b] + bucket_count[b];
+    out.perm.resize((size_t)n_sel);
+    {
+        std::vector<int64_t> cur(first.begin(), first.end() - 1);
+        for (int64_t i = 0; i < n_sel; ++i) out.perm[cur[bucket_of[i]]++] = subset ? subset[i] : i;
+    }
+    out.start.resize((size_t)n_sel);
+    out.end.resize((size_t)n_sel);
+    out.degree.resize((size_t)n_sel);
+    out.rm_off.assign((size_t)n_sel + 1, 0);
+    for (int64_t i = 0; i < n_sel; ++i) {
+        const int64_t r = out.perm[i];
+        out.start[i] = start[r];
+        out.end[i] = end[r];
+        out.degree[i] = degree[r];
+        out.rm_off[i + 1] = out.rm_off[i] + (rm_off[r + 1] - rm_off[r]);
+    }
+    out.rm_pos.resize((size_t)out.rm_off[n_sel]);
+    out.rm_code.resize((size_t)out.rm_off[n_sel]);
+    for (int64_t i = 0; i < n_sel; ++i) {
+        const int64_t r = out.perm[i];
+        int64_t o = out.rm_off[i];
+        for (int64_t kk = rm_off[r]; kk < rm_off[r + 1]; ++kk, ++o) {
+            out.rm_pos[o] = rm_pos[kk];
+            const uint8_t c = rm_nuc[kk];
+            out.rm_code[o] = c == 1 ? 1 : c == 2 ? 2 : c == 4 ? 3 : c == 8 ? 4 : 5;
+        }
+    }
+    // tiles, longest lists first (LPT order for the persistent-warp scheduler)
+    for (size_t b = 0; b < nb; ++b) {
+        const int64_t c = bucket_count[b];
+        for (int64_t o = 0; o < c; o += out.reads_per_tile) {
+            TileDesc t;
+            t.first = first[b] + o;
+            t.count = (int32_t)std::min<int64_t>(out.reads_per_tile, c - o);
+            t.bucket = (int32_t)b;
+            out.tiles.push_back(t);
+            out.scanned_entries += out.lists[out.buckets[b].list].n;
+        }
+        out.scanned_read_entries += c * (int64_t)out.lists[out.buckets[b].list].n;
+    }
+    std::stable_sort(out.tiles.begin(), out.tiles.end(), [&](const TileDesc& a, const TileDesc& b) {
+        return out.lists[out.buckets[a.bucket].list].n > out.lists[out.buckets[b.bucket].list].n;
+    });
+    return "";
+}
+
+}  // namespace wepp

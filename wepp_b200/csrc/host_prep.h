@@ -1,0 +1,88 @@
+// host_prep.h — host-side flattening for the placement path.
+//
+// (1) Tree side: turns the preorder arena (reference: arena::from_mat, src/WEPP/arena.cpp:3-56)
+//     into Euler-tour "entries": every mutation event of node v becomes an ENTER entry at
+//     preorder index v and an EXIT entry at v's subtree end, each carrying a signed-delta
+//     table — the change in mismatch count the event causes for a read whose allele at that
+//     position is ref / A / C / G / T (N and "outside the read" never change anything).
+//     The table folds in the reference's merge semantics (src/WEPP/initial_filter.cpp:59-87):
+//     the state after an event depends only on the read allele and the event's mut/ref
+//     nucleotides; the state before it is that of the nearest ancestor event at the same
+//     position, or the seed set (:118-123) when there is none.
+// (2) Read side: sorts reads into window buckets (stripe-aligned genome intervals x count
+//     bin) and cuts the buckets into warp tiles.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace wepp {
+
+// Device/host shared 16-byte Euler entry.
+//  master (stripe) form : x = preorder idx, y = absolute position, z = delta bytes for codes
+//                         0..3 (ref,A,C,G), w = byte0 delta for code 4 (T), other bytes 0.
+//  bucket-list form     : x = idx | (segment non-empty ? 1u<<31 : 0), y = countable nodes in
+//                         the segment [idx, next idx), z as above, w = byte0 delta T,
+//                         byte1 = 0 (code 5: N / outside), bytes 2..3 = position - bucket start.
+struct Entry {
+    uint32_t x, y, z, w;
+};
+
+struct EulerStripes {
+    int32_t stripe_width = 32;
+    int32_t n_stripes = 0;
+    int64_t n_events = 0;           // events with a non-zero delta table
+    std::vector<int64_t> stripe_off;  // n_stripes + 1
+    std::vector<Entry> entries;       // grouped by stripe (= pos / stripe_width), idx ascending within
+};
+
+// Returns "" on success, else an error message.
+std::string build_euler_stripes(int32_t n_nodes, const int32_t* parent, const int64_t* mut_off,
+                                const int32_t* mut_pos, const uint8_t* mut_ref, const uint8_t* mut_nuc,
+                                int32_t genome_size, int32_t stripe_width, EulerStripes& out);
+
+struct ListDesc {      // one Euler list per distinct stripe range
+    int64_t off;       // first entry in the concatenated list buffer (entry 0 is the dummy at idx 0)
+    int32_t n;         // entries including the dummy
+    int32_t qs, qe;    // stripe range, inclusive
+    int32_t b0;        // first position covered = qs * stripe_width
+    int32_t width;     // positions covered
+    int32_t pad;
+};
+struct BucketDesc {    // list x count bin: owns one accumulator row
+    int64_t acc_off;   // offset of this bucket's per-segment accumulators
+    int32_t list;
+    int32_t bin;       // min(start / (G/50), 49)  (initial_filter.cpp:146,169)
+};
+struct TileDesc {
+    int64_t first;     // first read (sorted order)
+    int32_t count;     // reads in tile (<= 32*K)
+    int32_t bucket;
+};
+
+struct ReadPlan {
+    int64_t n_reads = 0;
+    int32_t reads_per_tile = 256;
+    int32_t max_width = 0;
+    // reads in bucket-sorted order
+    std::vector<int32_t> start, end, degree;
+    std::vector<int64_t> rm_off;
+    std::vector<int32_t> rm_pos;
+    std::vector<uint8_t> rm_code;   // 1..4 = A,C,G,T ; 5 = N
+    std::vector<int64_t> perm;      // sorted index -> caller's index
+    std::vector<ListDesc> lists;
+    std::vector<BucketDesc> buckets;
+    std::vector<TileDesc> tiles;    // longest lists first
+    int64_t list_entries_total = 0;
+    int64_t acc_total = 0;
+    int64_t scanned_entries = 0;       // sum over tiles of list length
+    int64_t scanned_read_entries = 0;  // sum over reads of list length
+};
+
+// reads_per_lane: 0 = pick from the widest bucket, else 2/4/8.
+std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t n_reads, const int32_t* start,
+                            const int32_t* end, const int32_t* degree, const int64_t* rm_off, const int32_t* rm_pos,
+                            const uint8_t* rm_nuc, int32_t reads_per_lane, const int64_t* subset, int64_t n_subset,
+                            ReadPlan& out);
+
+}  // namespace wepp

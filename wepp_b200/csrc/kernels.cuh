@@ -1,0 +1,544 @@
+// kernels.cuh — sm_100a kernels of the placement path.
+//
+// Data layout in HBM (all built by wepp_set_arena / wepp_set_reads):
+//   stripes      Entry[2E']   Euler entries of all events, grouped by genome stripe
+//                              (pos / stripe_width), preorder index ascending inside a stripe
+//   lists        Entry[]      one Euler list per distinct read-window stripe range: the k-way
+//                              merge (by preorder index) of the stripes it covers, entry 0 = a
+//                              dummy at index 0; each entry carries its segment's node count
+//   reads        SoA          start/end/degree + sparse (pos, code) mutations, bucket-sorted
+//   accS/accC    double/int32 per bucket, per list segment: sum of read weights / degrees whose
+//                              EPP set contains the segment
+//   diff_lo/hi   uint64[N+1]  128-bit fixed-point difference array for the per-node score
+//   counts       int32[(N+1)*50]  difference array, scanned in place into the result
+//
+// Kernels (reference lines they replace in src/WEPP/initial_filter.cpp):
+//   build_lists_kernel / finalize_lists_kernel   per-window Euler CSR (replaces the range trees,
+//                                                 arena.cpp:68-169)
+//   place_kernel<K>        K1 signed delta (:59-87) + K2 Euler prefix sum (:101-104) + K3
+//                          min / multiplicity / EPP emission (:89-99, :126-134) + K3'
+//                          per-segment weight accumulation (:167-177); one warp = one tile of
+//                          32*K reads in lock step over the list, K reads per lane
+//   expand_kernel + scan kernels   segment accumulators -> per-node score / counts (:199-211)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "host_prep.h"
+
+namespace wepp {
+
+constexpr uint32_t IDX_MASK = 0x3FFFFFFFu;
+constexpr uint32_t SEG_FLAG = 0x80000000u;
+constexpr int NBINS = 50;
+constexpr int FIX_SHIFT = 80;  // score fixed point: value * 2^80 in a signed 128-bit integer
+
+struct PlaceParams {
+    const Entry* lists;
+    const ListDesc* list_desc;
+    const BucketDesc* buckets;
+    const TileDesc* tiles;
+    int32_t n_tiles;
+    int32_t n_nodes;
+    int* tile_counter;
+    // reads (bucket-sorted)
+    const int32_t* start;
+    const int32_t* end;
+    const int32_t* degree;
+    const int64_t* rm_off;
+    const int32_t* rm_pos;
+    const uint8_t* rm_code;
+    const int64_t* perm;
+    // mask
+    const uint8_t* mapped;  // may be null
+    // outputs
+    int32_t* max_pars;  // caller order
+    int32_t* mult;
+    double* accS;
+    int32_t* accC;
+    int accumulate;  // 0 for place_subset
+    // EPP lists
+    int32_t epp_cap;
+    unsigned long long epp_capacity;
+    unsigned long long* epp_total;
+    int64_t* epp_off;  // caller order, -1 = not cached
+    int32_t* epp_nodes;
+    int32_t smem_per_warp;
+};
+
+template <int K> struct Elem;
+template <> struct Elem<8> { using type = uint32_t; };
+template <> struct Elem<4> { using type = uint16_t; };
+template <> struct Elem<2> { using type = uint8_t; };
+
+__device__ __forceinline__ uint4 ld_entry(const Entry* p) {
+    return __ldg(reinterpret_cast<const uint4*>(p));
+}
+
+// ---------------------------------------------------------------------------------------------
+// List construction: rank-by-binary-search k-way merge of the stripes a list covers.
+// grid = (chunks, n_lists), one thread per source entry.
+__global__ void build_lists_kernel(const Entry* __restrict__ stripes, const int64_t* __restrict__ stripe_off,
+                                   const ListDesc* __restrict__ list_desc, Entry* __restrict__ out, int q) {
+    const ListDesc ld = list_desc[blockIdx.y];
+    const int64_t src0 = stripe_off[ld.qs];
+    const int n_src = ld.n - 1;
+    Entry* dst = out + ld.off;
+    if (blockIdx.x == 0 && threadIdx.x == 0) dst[0] = Entry{0u, 0u, 0u, 0u};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
+        const uint4 e = ld_entry(stripes + src0 + i);
+        const int s = (int)(e.y / (uint32_t)q);
+        int64_t rank = 1 + (src0 + i - stripe_off[s]);
+        for (int t = ld.qs; t <= ld.qe; ++t) {
+            if (t == s) continue;
+            int64_t lo = stripe_off[t], hi = stripe_off[t + 1];
+            const int64_t base = lo;
+            // stripes before mine: count idx <= mine; after mine: count idx < mine
+            const uint32_t key = t < s ? e.x + 1u : e.x;
+            while (lo < hi) {
+                const int64_t mid = (lo + hi) >> 1;
+                if (__ldg(&stripes[mid].x) < key) lo = mid + 1; else hi = mid;
+            }
+            rank += lo - base;
+        }
+        Entry o;
+        o.x = e.x;
+        o.y = 0;
+        o.z = e.z;
+        o.w = (e.w & 0xFFu) | ((e.y - (uint32_t)ld.b0) << 16);
+        dst[rank] = o;
+    }
+}
+
+// Segment lengths and countable-node counts.  grid = (chunks, n_lists).
+__global__ void finalize_lists_kernel(Entry* __restrict__ lists, const ListDesc* __restrict__ list_desc,
+                                      int n_nodes, const int32_t* __restrict__ mapped_prefix) {
+    const ListDesc ld = list_desc[blockIdx.y];
+    Entry* e = lists + ld.off;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ld.n; i += gridDim.x * blockDim.x) {
+        const uint32_t idx = e[i].x & IDX_MASK;
+        const uint32_t nxt = (i + 1 < ld.n) ? (e[i + 1].x & IDX_MASK) : (uint32_t)n_nodes;
+        const uint32_t len = nxt - idx;
+        uint32_t ucnt = len;
+        if (mapped_prefix) ucnt -= (uint32_t)(mapped_prefix[nxt] - mapped_prefix[idx]);
+        e[i].y = ucnt;
+        e[i].x = idx | (len ? SEG_FLAG : 0u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The placement kernel.  Persistent warps; each warp pulls tiles from a global counter.
+template <int K>
+__global__ void __launch_bounds__(128) place_kernel(const PlaceParams p) {
+    using ET = typename Elem<K>::type;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* wbase = smem + (size_t)warp * p.smem_per_warp;
+    uint4* ebuf = reinterpret_cast<uint4*>(wbase);   // 32 staged entries
+    ET* codes = reinterpret_cast<ET*>(wbase + 512);  // [width][32] read-allele codes, K nibbles per lane
+    const unsigned FULL = 0xFFFFFFFFu;
+
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(p.tile_counter, 1);
+        t = __shfl_sync(FULL, t, 0);
+        if (t >= p.n_tiles) break;
+        const TileDesc td = p.tiles[t];
+        const BucketDesc bd = p.buckets[td.bucket];
+        const ListDesc ld = p.list_desc[bd.list];
+        const Entry* ent = p.lists + ld.off;
+        const int n = ld.n;
+
+        // ---- read tile -> shared allele-code table --------------------------------------------
+        int s_rel[K], e_rel[K], run0[K];
+        int64_t rid[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            const int ti = lane * K + j;
+            const bool valid = ti < td.count;
+            rid[j] = valid ? td.first + ti : -1;
+            s_rel[j] = valid ? p.start[rid[j]] - ld.b0 : 1;
+            e_rel[j] = valid ? p.end[rid[j]] - ld.b0 : 0;
+            run0[j] = 0;
+        }
+        __syncwarp();
+        for (int pos = 0; pos < ld.width; ++pos) {
+            uint32_t w = 0;
+#pragma unroll
+            for (int j = 0; j < K; ++j) w |= ((pos >= s_rel[j] && pos <= e_rel[j]) ? 0u : 5u) << (4 * j);
+            codes[pos * 32 + lane] = (ET)w;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            if (rid[j] >= 0) {
+                const int64_t a = p.rm_off[rid[j]], b = p.rm_off[rid[j] + 1];
+                for (int64_t k = a; k < b; ++k) {
+                    const int pr = p.rm_pos[k] - ld.b0;
+                    const uint32_t c = p.rm_code[k];
+                    uint32_t w = codes[pr * 32 + lane];
+                    w = (w & ~(0xFu << (4 * j))) | (c << (4 * j));
+                    codes[pr * 32 + lane] = (ET)w;
+                    run0[j] += (c <= 4u);  // seed set: non-N mutations (initial_filter.cpp:118-123)
+                }
+            }
+        }
+        __syncwarp();
+
+        // ---- pass 1: prefix sum of signed deltas, running min and its multiplicity --------------
+        int run[K], best[K], cnt[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            run[j] = run0[j];
+            best[j] = 0x7FFFFFFF;
+            cnt[j] = 0;
+        }
+        {
+            uint4 nxt = make_uint4(0, 0, 0, 0);
+            if (lane < n) nxt = ld_entry(ent + lane);
+            for (int base = 0; base < n; base += 32) {
+                ebuf[lane] = nxt;
+                __syncwarp();
+                if (base + 32 + lane < n) nxt = ld_entry(ent + base + 32 + lane);
+                const int m = min(32, n - base);
+#pragma unroll 4
+                for (int ii = 0; ii < m; ++ii) {
+                    const uint4 e = ebuf[ii];
+                    const uint32_t w = codes[(e.w >> 16) * 32 + lane];
+                    const uint32_t d0 = __byte_perm(e.z, e.w, w);
+                    uint32_t d1 = 0;
+                    if (K == 8) d1 = __byte_perm(e.z, e.w, w >> 16);
+#pragma unroll
+                    for (int j = 0; j < K; ++j)
+                        run[j] = __dp4a((int)(j < 4 ? d0 : d1), (int)(1u << (8 * (j & 3))), run[j]);
+                    if (e.x & SEG_FLAG) {
+                        const int ucnt = (int)e.y;
+#pragma unroll
+                        for (int j = 0; j < K; ++j) {
+                            if (run[j] < best[j]) {
+                                best[j] = run[j];
+                                cnt[j] = ucnt;
+                            } else if (run[j] == best[j]) {
+                                cnt[j] += ucnt;
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- per-read results -------------------------------------------------------------------
+        double wgt[K];
+        int deg[K];
+        unsigned long long wp[K];
+        uint32_t small_mask = 0;
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            wgt[j] = 0.0;
+            deg[j] = 0;
+            wp[j] = 0;
+            if (rid[j] >= 0) {
+                const int64_t orig = p.perm[rid[j]];
+                p.max_pars[orig] = best[j];
+                p.mult[orig] = cnt[j];
+                const int d = p.degree[rid[j]];
+                if (cnt[j] > 0) {
+                    // node_score, initial_filter.hpp:54-57
+                    wgt[j] = (double)d / ((double)(1 + best[j]) * (double)cnt[j]);
+                    deg[j] = d;
+                }
+                long long off = -1;
+                if (p.epp_off) {
+                    if (cnt[j] > 0 && cnt[j] <= p.epp_cap) {
+                        const unsigned long long o = atomicAdd(p.epp_total, (unsigned long long)cnt[j]);
+                        if (o + (unsigned long long)cnt[j] <= p.epp_capacity) {
+                            off = (long long)o;
+                            wp[j] = o;
+                            small_mask |= 1u << j;
+                        }
+                    } else if (cnt[j] == 0) {
+                        off = 0;  // empty but known
+                    }
+                    p.epp_off[orig] = off;
+                }
+            }
+        }
+        const bool need_pass2 = p.accumulate || __any_sync(FULL, small_mask != 0);
+        if (!need_pass2) continue;
+
+        // ---- pass 2: which segments attain the min -> weights into the segment accumulators,
+        //      EPP node lists for reads under the cache cap ---------------------------------------
+#pragma unroll
+        for (int j = 0; j < K; ++j) run[j] = run0[j];
+        double* accS = p.accS + bd.acc_off;
+        int32_t* accC = p.accC + bd.acc_off;
+        {
+            uint4 nxt = make_uint4(0, 0, 0, 0);
+            if (lane < n) nxt = ld_entry(ent + lane);
+            for (int base = 0; base < n; base += 32) {
+                ebuf[lane] = nxt;
+                __syncwarp();
+                if (base + 32 + lane < n) nxt = ld_entry(ent + base + 32 + lane);
+                const int m = min(32, n - base);
+#pragma unroll 2
+                for (int ii = 0; ii < m; ++ii) {
+                    const uint4 e = ebuf[ii];
+                    const uint32_t w = codes[(e.w >> 16) * 32 + lane];
+                    const uint32_t d0 = __byte_perm(e.z, e.w, w);
+                    uint32_t d1 = 0;
+                    if (K == 8) d1 = __byte_perm(e.z, e.w, w >> 16);
+#pragma unroll
+                    for (int j = 0; j < K; ++j)
+                        run[j] = __dp4a((int)(j < 4 ? d0 : d1), (int)(1u << (8 * (j & 3))), run[j]);
+                    if (e.x & SEG_FLAG) {
+                        double s = 0.0;
+                        int c = 0;
+                        uint32_t hit = 0;
+#pragma unroll
+                        for (int j = 0; j < K; ++j) {
+                            const bool eq = run[j] == best[j];
+                            s += eq ? wgt[j] : 0.0;
+                            c += eq ? deg[j] : 0;
+                            hit |= eq ? (1u << j) : 0u;
+                        }
+                        hit &= small_mask;
+                        if (hit) {  // rare: explicit EPP lists (sorted: the list is in preorder)
+#pragma unroll
+                            for (int j = 0; j < K; ++j) {
+                                if (hit & (1u << j)) {
+                                    uint32_t v = e.x & IDX_MASK;
+                                    uint32_t u = e.y;
+                                    while (u) {
+                                        if (!p.mapped || !p.mapped[v]) {
+                                            p.epp_nodes[wp[j]++] = (int32_t)v;
+                                            --u;
+                                        }
+                                        ++v;
+                                    }
+                                }
+                            }
+                        }
+                        if (p.accumulate) {
+#pragma unroll
+                            for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+                            c = __reduce_add_sync(FULL, c);
+                            if (lane == 0) {
+                                if (s != 0.0) atomicAdd(accS + base + ii, s);
+                                if (c != 0) atomicAdd(accC + base + ii, c);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Segment accumulators -> per-node difference arrays.  grid = (chunks, n_buckets).
+__device__ __forceinline__ void dbl_to_fix(double d, unsigned long long& lo, long long& hi) {
+    lo = 0;
+    hi = 0;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(d);
+    const int ex = (int)((bits >> 52) & 0x7FF);
+    if (ex == 0) return;  // zero / denormal
+    const unsigned long long man = (bits & 0xFFFFFFFFFFFFFull) | (1ull << 52);
+    const int sh = ex - 1075 + FIX_SHIFT;
+    if (sh >= 64) {
+        hi = (long long)(man << (sh - 64));
+    } else if (sh > 0) {
+        lo = man << sh;
+        hi = (long long)(man >> (64 - sh));
+    } else if (sh == 0) {
+        lo = man;
+    } else if (sh > -53) {
+        lo = man >> (-sh);
+    }
+}
+
+__device__ __forceinline__ void atomic_add128(unsigned long long* dlo, unsigned long long* dhi, unsigned long long lo,
+                                              long long hi) {
+    const unsigned long long old = atomicAdd(dlo, lo);
+    const unsigned long long carry = (old + lo < old) ? 1ull : 0ull;
+    const unsigned long long h = (unsigned long long)hi + carry;
+    if (h) atomicAdd(dhi, h);
+}
+
+__global__ void expand_kernel(const Entry* __restrict__ lists, const ListDesc* __restrict__ list_desc,
+                              const BucketDesc* __restrict__ buckets, const double* __restrict__ accS,
+                              const int32_t* __restrict__ accC, unsigned long long* __restrict__ diff_lo,
+                              unsigned long long* __restrict__ diff_hi, int32_t* __restrict__ counts) {
+    const BucketDesc bd = buckets[blockIdx.y];
+    const ListDesc ld = list_desc[bd.list];
+    const Entry* e = lists + ld.off;
+    const double* s = accS + bd.acc_off;
+    const int32_t* c = accC + bd.acc_off;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ld.n; i += gridDim.x * blockDim.x) {
+        const double cur = s[i], prv = i ? s[i - 1] : 0.0;
+        const int32_t ccur = c[i], cprv = i ? c[i - 1] : 0;
+        if (cur == prv && ccur == cprv) continue;
+        const uint32_t idx = __ldg(&e[i].x) & IDX_MASK;
+        if (cur != prv) {
+            unsigned long long alo, blo;
+            long long ahi, bhi;
+            dbl_to_fix(cur, alo, ahi);
+            dbl_to_fix(prv, blo, bhi);
+            const unsigned long long lo = alo - blo;
+            const long long hi = ahi - bhi - (alo < blo ? 1 : 0);
+            atomic_add128(diff_lo + idx, diff_hi + idx, lo, hi);
+        }
+        if (ccur != cprv) atomicAdd(counts + (size_t)idx * NBINS + bd.bin, ccur - cprv);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// 128-bit inclusive prefix sum over nodes -> double score.  Three phases, CHUNK nodes per block.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;
+
+struct U128 {
+    unsigned long long lo, hi;
+};
+__device__ __forceinline__ U128 add128(U128 a, U128 b) {
+    U128 r;
+    r.lo = a.lo + b.lo;
+    r.hi = a.hi + b.hi + (r.lo < a.lo ? 1ull : 0ull);
+    return r;
+}
+__device__ __forceinline__ U128 shfl_up128(U128 v, int d) {
+    U128 r;
+    r.lo = __shfl_up_sync(0xFFFFFFFFu, v.lo, d);
+    r.hi = __shfl_up_sync(0xFFFFFFFFu, v.hi, d);
+    return r;
+}
+
+// block-wide exclusive scan of per-thread totals; returns this thread's exclusive prefix and the
+// block total in `total`.
+__device__ __forceinline__ U128 block_exclusive128(U128 v, U128& total) {
+    __shared__ U128 warp_tot[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    U128 inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        U128 o = shfl_up128(inc, d);
+        if (lane >= d) inc = add128(inc, o);
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    U128 off = {0, 0};
+    U128 tot = {0, 0};
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
+        if (w < warp) off = add128(off, warp_tot[w]);
+        tot = add128(tot, warp_tot[w]);
+    }
+    total = tot;
+    U128 exc;  // inclusive - own
+    exc.lo = inc.lo - v.lo;
+    exc.hi = inc.hi - v.hi - (inc.lo < v.lo ? 1ull : 0ull);
+    __syncthreads();
+    return add128(off, exc);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) score_chunk_sum_kernel(const unsigned long long* __restrict__ lo,
+                                                                        const unsigned long long* __restrict__ hi, int n,
+                                                                        U128* __restrict__ chunk_tot) {
+    const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+    U128 acc = {0, 0};
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) acc = add128(acc, U128{lo[base + k], hi[base + k]});
+    U128 total;
+    block_exclusive128(acc, total);
+    if (threadIdx.x == 0) chunk_tot[blockIdx.x] = total;
+}
+
+__global__ void score_chunk_scan_kernel(U128* __restrict__ chunk_tot, int n_chunks) {
+    // single block; exclusive scan in place
+    __shared__ U128 carry_s;
+    if (threadIdx.x == 0) carry_s = U128{0, 0};
+    __syncthreads();
+    for (int base = 0; base < n_chunks; base += SCAN_THREADS) {
+        const int i = base + threadIdx.x;
+        U128 v = i < n_chunks ? chunk_tot[i] : U128{0, 0};
+        U128 total;
+        U128 exc = block_exclusive128(v, total);
+        const U128 carry = carry_s;
+        if (i < n_chunks) chunk_tot[i] = add128(carry, exc);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = add128(carry, total);
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) score_apply_kernel(const unsigned long long* __restrict__ lo,
+                                                                    const unsigned long long* __restrict__ hi, int n,
+                                                                    const U128* __restrict__ chunk_off,
+                                                                    const uint8_t* __restrict__ mapped,
+                                                                    double* __restrict__ score) {
+    const int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
+    U128 v[SCAN_ITEMS];
+    U128 acc = {0, 0};
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? U128{lo[base + k], hi[base + k]} : U128{0, 0};
+        acc = add128(acc, v[k]);
+    }
+    U128 total;
+    U128 run = add128(block_exclusive128(acc, total), chunk_off[blockIdx.x]);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        run = add128(run, v[k]);
+        if (base + k < n) {
+            // fixed point -> double (value is non-negative up to rounding of the inputs)
+            const double d = ((double)(long long)run.hi * 18446744073709551616.0 + (double)run.lo) *
+                             8.271806125530277e-25;  // 2^-80
+            score[base + k] = (mapped && mapped[base + k]) ? 0.0 : d;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// counts: in-place inclusive prefix along nodes of int32[(N+1)][50].
+constexpr int CNT_CHUNK = 1024;  // nodes per block
+
+__global__ void __launch_bounds__(64) counts_chunk_sum_kernel(const int32_t* __restrict__ counts, int n,
+                                                               int32_t* __restrict__ chunk_tot) {
+    const int b = threadIdx.x;
+    if (b >= NBINS) return;
+    const int v0 = blockIdx.x * CNT_CHUNK, v1 = min(n, v0 + CNT_CHUNK);
+    int32_t acc = 0;
+#pragma unroll 8
+    for (int v = v0; v < v1; ++v) acc += counts[(size_t)v * NBINS + b];
+    chunk_tot[(size_t)blockIdx.x * NBINS + b] = acc;
+}
+
+// exclusive scan over chunks, one thread per bin (out of place so the loads pipeline)
+__global__ void counts_chunk_scan_kernel(const int32_t* __restrict__ chunk_tot, int32_t* __restrict__ chunk_off,
+                                         int n_chunks) {
+    const int b = threadIdx.x;
+    if (b >= NBINS) return;
+    int32_t acc = 0;
+#pragma unroll 8
+    for (int c = 0; c < n_chunks; ++c) {
+        chunk_off[(size_t)c * NBINS + b] = acc;
+        acc += chunk_tot[(size_t)c * NBINS + b];
+    }
+}
+
+__global__ void __launch_bounds__(64) counts_apply_kernel(int32_t* __restrict__ counts, int n,
+                                                           const int32_t* __restrict__ chunk_off,
+                                                           const uint8_t* __restrict__ mapped) {
+    const int b = threadIdx.x;
+    if (b >= NBINS) return;
+    const int v0 = blockIdx.x * CNT_CHUNK, v1 = min(n, v0 + CNT_CHUNK);
+    int32_t acc = chunk_off[(size_t)blockIdx.x * NBINS + b];
+    for (int v = v0; v < v1; ++v) {
+        acc += counts[(size_t)v * NBINS + b];
+        counts[(size_t)v * NBINS + b] = (mapped && mapped[v]) ? 0 : acc;
+    }
+}
+
+}  // namespace wepp

@@ -1,0 +1,643 @@
+// wepp_abi.cu — the C ABI declared in include/wepp_b200.h: context, device memory, launches.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/wepp_b200.h"
+#include "host_prep.h"
+#include "kernels.cuh"
+#include "rescore.cuh"
+
+using namespace wepp;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU(call)                                                                                        \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return fail(WEPP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));               \
+    } while (0)
+
+// Grow-only device buffer.
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+}  // namespace
+
+struct wepp_handle {
+    int device = 0;
+    int n_sms = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    int32_t opt_q = 32, opt_k = 0;
+
+    // arena
+    bool has_arena = false;
+    int32_t n_nodes = 0, genome = 0;
+    std::vector<int32_t> parent;  // kept for rescore (root paths)
+    std::vector<int64_t> mut_off;
+    std::vector<int32_t> mut_pos;
+    std::vector<uint8_t> mut_ref, mut_nuc;
+    EulerStripes es;
+    DevBuf<Entry> d_stripes;
+    DevBuf<int64_t> d_stripe_off;
+
+    // mask
+    bool has_mask = false;
+    DevBuf<uint8_t> d_mapped;
+    DevBuf<int32_t> d_mapped_prefix;
+    bool lists_final = false;
+
+    // reads (caller copy kept for subset plans and rescore)
+    bool has_reads = false;
+    int64_t n_reads = 0;
+    std::vector<int32_t> r_start, r_end, r_degree;
+    std::vector<int64_t> r_off;
+    std::vector<int32_t> r_pos;
+    std::vector<uint8_t> r_nuc;
+
+    struct DevPlan {
+        ReadPlan plan;
+        DevBuf<int32_t> start, end, degree, rm_pos;
+        DevBuf<int64_t> rm_off, perm;
+        DevBuf<uint8_t> rm_code;
+        DevBuf<ListDesc> lists;
+        DevBuf<BucketDesc> buckets;
+        DevBuf<TileDesc> tiles;
+        DevBuf<Entry> entries;
+        bool final_for_mask = false;
+        void release() {
+            start.release(); end.release(); degree.release(); rm_pos.release(); rm_off.release(); perm.release();
+            rm_code.release(); lists.release(); buckets.release(); tiles.release(); entries.release();
+        }
+    };
+    DevPlan full, sub;
+
+    // accumulators and outputs
+    DevBuf<double> d_accS;
+    DevBuf<int32_t> d_accC;
+    DevBuf<int32_t> d_maxpars, d_mult;
+    DevBuf<double> d_score;
+    DevBuf<int32_t> d_counts;
+    DevBuf<unsigned long long> d_diff_lo, d_diff_hi;
+    DevBuf<U128> d_chunk128;
+    DevBuf<int32_t> d_cchunk_tot, d_cchunk_off;
+    DevBuf<int64_t> d_epp_off;
+    DevBuf<int32_t> d_epp_nodes;
+    DevBuf<unsigned long long> d_epp_total;
+    DevBuf<int> d_tile_counter;
+    bool has_results = false;
+    bool has_epp = false;
+    int64_t epp_capacity = 0;
+
+    wepp_stats stats = {};
+};
+
+namespace {
+
+template <typename T>
+cudaError_t upload(DevBuf<T>& b, const std::vector<T>& v, cudaStream_t s) {
+    cudaError_t e = b.ensure(v.size());
+    if (e != cudaSuccess) return e;
+    if (v.empty()) return cudaSuccess;
+    return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp) {
+    ReadPlan& pl = dp.plan;
+    CU(upload(dp.start, pl.start, h->stream));
+    CU(upload(dp.end, pl.end, h->stream));
+    CU(upload(dp.degree, pl.degree, h->stream));
+    CU(upload(dp.rm_off, pl.rm_off, h->stream));
+    CU(upload(dp.rm_pos, pl.rm_pos, h->stream));
+    CU(upload(dp.rm_code, pl.rm_code, h->stream));
+    CU(upload(dp.perm, pl.perm, h->stream));
+    CU(upload(dp.lists, pl.lists, h->stream));
+    CU(upload(dp.buckets, pl.buckets, h->stream));
+    CU(upload(dp.tiles, pl.tiles, h->stream));
+    CU(dp.entries.ensure((size_t)pl.list_entries_total));
+    if (!pl.lists.empty()) {
+        int max_n = 0;
+        for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
+        dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.lists.size());
+        build_lists_kernel<<<grid, 256, 0, h->stream>>>(h->d_stripes.p, h->d_stripe_off.p, dp.lists.p, dp.entries.p,
+                                                        h->es.stripe_width);
+        CU(cudaGetLastError());
+    }
+    dp.final_for_mask = false;
+    return WEPP_OK;
+}
+
+int finalize_plan(wepp_handle* h, wepp_handle::DevPlan& dp) {
+    if (dp.final_for_mask || dp.plan.lists.empty()) return WEPP_OK;
+    int max_n = 0;
+    for (const ListDesc& l : dp.plan.lists) max_n = std::max(max_n, l.n);
+    dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)dp.plan.lists.size());
+    finalize_lists_kernel<<<grid, 256, 0, h->stream>>>(dp.entries.p, dp.lists.p, h->n_nodes,
+                                                       h->has_mask ? h->d_mapped_prefix.p : nullptr);
+    CU(cudaGetLastError());
+    dp.final_for_mask = true;
+    return WEPP_OK;
+}
+
+template <int K>
+int launch_place(wepp_handle* h, const PlaceParams& pp, int width) {
+    using ET = typename Elem<K>::type;
+    const int warps = 4;
+    PlaceParams p = pp;
+    p.smem_per_warp = (int)((512 + (size_t)width * 32 * sizeof(ET) + 15) & ~(size_t)15);
+    const size_t smem = (size_t)p.smem_per_warp * warps;
+    if (smem > h->smem_optin)
+        return fail(WEPP_E_INVALID, "read window too wide for shared memory (" + std::to_string(width) + " bases)");
+    CU(cudaFuncSetAttribute(place_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_kernel<K>, warps * 32, smem));
+    per_sm = std::max(per_sm, 1);
+    const int64_t want = (p.n_tiles + warps - 1) / warps;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)per_sm * h->n_sms));
+    place_kernel<K><<<grid, warps * 32, smem, h->stream>>>(p);
+    CU(cudaGetLastError());
+    return WEPP_OK;
+}
+
+int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t epp_cap, int64_t epp_capacity) {
+    ReadPlan& pl = dp.plan;
+    int rc = finalize_plan(h, dp);
+    if (rc) return rc;
+    const int n = h->n_nodes;
+    int64_t launches = 0;
+
+    CU(h->d_maxpars.ensure((size_t)h->n_reads));
+    CU(h->d_mult.ensure((size_t)h->n_reads));
+    CU(h->d_tile_counter.ensure(1));
+    CU(cudaMemsetAsync(h->d_tile_counter.p, 0, sizeof(int), h->stream));
+    CU(h->d_epp_total.ensure(1));
+    CU(cudaMemsetAsync(h->d_epp_total.p, 0, sizeof(unsigned long long), h->stream));
+    const bool want_epp = epp_cap > 0 && epp_capacity > 0;
+    if (want_epp) {
+        CU(h->d_epp_off.ensure((size_t)h->n_reads));
+        CU(h->d_epp_nodes.ensure((size_t)epp_capacity));
+        CU(cudaMemsetAsync(h->d_epp_off.p, 0xFF, (size_t)h->n_reads * sizeof(int64_t), h->stream));
+    }
+    if (accumulate) {
+        CU(h->d_accS.ensure((size_t)pl.acc_total));
+        CU(h->d_accC.ensure((size_t)pl.acc_total));
+        CU(cudaMemsetAsync(h->d_accS.p, 0, (size_t)pl.acc_total * sizeof(double), h->stream));
+        CU(cudaMemsetAsync(h->d_accC.p, 0, (size_t)pl.acc_total * sizeof(int32_t), h->stream));
+        CU(h->d_score.ensure((size_t)n));
+        CU(h->d_counts.ensure(((size_t)n + 1) * NBINS));
+        CU(h->d_diff_lo.ensure((size_t)n + 1));
+        CU(h->d_diff_hi.ensure((size_t)n + 1));
+        CU(cudaMemsetAsync(h->d_counts.p, 0, ((size_t)n + 1) * NBINS * sizeof(int32_t), h->stream));
+        CU(cudaMemsetAsync(h->d_diff_lo.p, 0, ((size_t)n + 1) * sizeof(unsigned long long), h->stream));
+        CU(cudaMemsetAsync(h->d_diff_hi.p, 0, ((size_t)n + 1) * sizeof(unsigned long long), h->stream));
+    }
+
+    PlaceParams pp = {};
+    pp.lists = dp.entries.p;
+    pp.list_desc = dp.lists.p;
+    pp.buckets = dp.buckets.p;
+    pp.tiles = dp.tiles.p;
+    pp.n_tiles = (int32_t)pl.tiles.size();
+    pp.n_nodes = n;
+    pp.tile_counter = h->d_tile_counter.p;
+    pp.start = dp.start.p;
+    pp.end = dp.end.p;
+    pp.degree = dp.degree.p;
+    pp.rm_off = dp.rm_off.p;
+    pp.rm_pos = dp.rm_pos.p;
+    pp.rm_code = dp.rm_code.p;
+    pp.perm = dp.perm.p;
+    pp.mapped = h->has_mask ? h->d_mapped.p : nullptr;
+    pp.max_pars = h->d_maxpars.p;
+    pp.mult = h->d_mult.p;
+    pp.accS = h->d_accS.p;
+    pp.accC = h->d_accC.p;
+    pp.accumulate = accumulate ? 1 : 0;
+    pp.epp_cap = want_epp ? epp_cap : 0;
+    pp.epp_capacity = want_epp ? (unsigned long long)epp_capacity : 0ull;
+    pp.epp_total = h->d_epp_total.p;
+    pp.epp_off = want_epp ? h->d_epp_off.p : nullptr;
+    pp.epp_nodes = want_epp ? h->d_epp_nodes.p : nullptr;
+
+    CU(cudaEventRecord(h->ev[0], h->stream));
+    if (pp.n_tiles > 0) {
+        const int k = pl.reads_per_tile / 32;
+        if (k == 8) rc = launch_place<8>(h, pp, pl.max_width);
+        else if (k == 4) rc = launch_place<4>(h, pp, pl.max_width);
+        else rc = launch_place<2>(h, pp, pl.max_width);
+        if (rc) return rc;
+        ++launches;
+    }
+    CU(cudaEventRecord(h->ev[1], h->stream));
+    if (accumulate) {
+        if (!pl.buckets.empty()) {
+            int max_n = 0;
+            for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
+            dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
+            expand_kernel<<<grid, 256, 0, h->stream>>>(dp.entries.p, dp.lists.p, dp.buckets.p, h->d_accS.p,
+                                                       h->d_accC.p, h->d_diff_lo.p, h->d_diff_hi.p, h->d_counts.p);
+            CU(cudaGetLastError());
+            ++launches;
+        }
+        const int n_chunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+        CU(h->d_chunk128.ensure((size_t)n_chunks));
+        score_chunk_sum_kernel<<<n_chunks, SCAN_THREADS, 0, h->stream>>>(h->d_diff_lo.p, h->d_diff_hi.p, n,
+                                                                         h->d_chunk128.p);
+        score_chunk_scan_kernel<<<1, SCAN_THREADS, 0, h->stream>>>(h->d_chunk128.p, n_chunks);
+        score_apply_kernel<<<n_chunks, SCAN_THREADS, 0, h->stream>>>(h->d_diff_lo.p, h->d_diff_hi.p, n,
+                                                                     h->d_chunk128.p,
+                                                                     h->has_mask ? h->d_mapped.p : nullptr,
+                                                                     h->d_score.p);
+        const int c_chunks = (n + CNT_CHUNK - 1) / CNT_CHUNK;
+        CU(h->d_cchunk_tot.ensure((size_t)c_chunks * NBINS));
+        CU(h->d_cchunk_off.ensure((size_t)c_chunks * NBINS));
+        counts_chunk_sum_kernel<<<c_chunks, 64, 0, h->stream>>>(h->d_counts.p, n, h->d_cchunk_tot.p);
+        counts_chunk_scan_kernel<<<1, 64, 0, h->stream>>>(h->d_cchunk_tot.p, h->d_cchunk_off.p, c_chunks);
+        counts_apply_kernel<<<c_chunks, 64, 0, h->stream>>>(h->d_counts.p, n, h->d_cchunk_off.p,
+                                                            h->has_mask ? h->d_mapped.p : nullptr);
+        CU(cudaGetLastError());
+        launches += 6;
+    }
+    CU(cudaEventRecord(h->ev[2], h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+
+    float ms_scan = 0, ms_node = 0;
+    CU(cudaEventElapsedTime(&ms_scan, h->ev[0], h->ev[1]));
+    CU(cudaEventElapsedTime(&ms_node, h->ev[1], h->ev[2]));
+    wepp_stats& st = h->stats;
+    st.n_nodes = n;
+    st.n_events = h->es.n_events;
+    st.n_euler_entries = (int64_t)h->es.entries.size();
+    st.n_reads = pl.n_reads;
+    st.n_buckets = (int64_t)pl.buckets.size();
+    st.n_lists = (int64_t)pl.lists.size();
+    st.n_tiles = (int64_t)pl.tiles.size();
+    st.list_entries_total = pl.list_entries_total;
+    st.scanned_entries = pl.scanned_entries;
+    st.scanned_read_entries = pl.scanned_read_entries;
+    st.kernel_launches = launches;
+    st.ms_scan_kernel = ms_scan;
+    st.ms_node_kernels = ms_node;
+    st.ms_place_total = ms_scan + ms_node;
+    st.reads_per_tile = pl.reads_per_tile;
+    st.stripe_width = h->es.stripe_width;
+    // Algorithmic bytes of one place (DESIGN.md "Roofline"): two passes over each tile's Euler
+    // list (16 B entries), the packed reads once, per-read results, the segment accumulators
+    // written and read once, and the per-node difference arrays / results written and scanned.
+    const int64_t rm = pl.rm_off.empty() ? 0 : pl.rm_off.back();
+    int64_t bytes = pl.scanned_entries * 16 * (accumulate ? 2 : 1);
+    bytes += pl.n_reads * (12 + 8 + 8) + rm * 5;
+    bytes += pl.n_reads * 8;
+    if (accumulate) {
+        bytes += pl.acc_total * 12 * 2;
+        bytes += (int64_t)n * (16 + 8 + 200) * 2;
+    }
+    st.algorithmic_bytes = bytes;
+    h->has_results = true;
+    h->has_epp = want_epp;
+    h->epp_capacity = want_epp ? epp_capacity : 0;
+    return WEPP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* wepp_last_error(void) { return g_err.c_str(); }
+int wepp_abi_version(void) { return 1; }
+
+int wepp_create(int device, wepp_handle** out) {
+    if (!out) return fail(WEPP_E_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(WEPP_E_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") +
+                                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    if (device < 0 || device >= count) return fail(WEPP_E_INVALID, "device ordinal out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(WEPP_E_CUDA, std::string("device ") + prop.name + " is not sm_100 class; this library is built for sm_100a only");
+    wepp_handle* h = new wepp_handle();
+    h->device = device;
+    h->n_sms = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& ev : h->ev) CU(cudaEventCreate(&ev));
+    *out = h;
+    return WEPP_OK;
+}
+
+void wepp_destroy(wepp_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    h->d_stripes.release(); h->d_stripe_off.release(); h->d_mapped.release(); h->d_mapped_prefix.release();
+    h->full.release(); h->sub.release();
+    h->d_accS.release(); h->d_accC.release(); h->d_maxpars.release(); h->d_mult.release(); h->d_score.release();
+    h->d_counts.release(); h->d_diff_lo.release(); h->d_diff_hi.release(); h->d_chunk128.release();
+    h->d_cchunk_tot.release(); h->d_cchunk_off.release(); h->d_epp_off.release(); h->d_epp_nodes.release();
+    h->d_epp_total.release(); h->d_tile_counter.release();
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int wepp_set_options(wepp_handle* h, int32_t stripe_width, int32_t reads_per_lane) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (h->has_arena) return fail(WEPP_E_STATE, "wepp_set_options must precede wepp_set_arena");
+    if (stripe_width < 1 || stripe_width > 4096) return fail(WEPP_E_INVALID, "stripe_width must be in 1..4096");
+    if (!(reads_per_lane == 0 || reads_per_lane == 2 || reads_per_lane == 4 || reads_per_lane == 8))
+        return fail(WEPP_E_INVALID, "reads_per_lane must be 0, 2, 4 or 8");
+    h->opt_q = stripe_width;
+    h->opt_k = reads_per_lane;
+    return WEPP_OK;
+}
+
+int wepp_set_arena(wepp_handle* h, int32_t n_nodes, const int32_t* parent, const int64_t* mut_off,
+                   const int32_t* mut_pos, const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (!parent || !mut_off) return fail(WEPP_E_INVALID, "parent / mut_off is NULL");
+    if (n_nodes >= 1 && mut_off[n_nodes] > 0 && (!mut_pos || !mut_ref || !mut_nuc))
+        return fail(WEPP_E_INVALID, "mutation arrays are NULL");
+    CU(cudaSetDevice(h->device));
+    std::string err = build_euler_stripes(n_nodes, parent, mut_off, mut_pos, mut_ref, mut_nuc, genome_size, h->opt_q, h->es);
+    if (!err.empty()) return fail(WEPP_E_INVALID, err);
+    h->n_nodes = n_nodes;
+    h->genome = genome_size;
+    h->parent.assign(parent, parent + n_nodes);
+    h->mut_off.assign(mut_off, mut_off + n_nodes + 1);
+    const int64_t nm = mut_off[n_nodes];
+    h->mut_pos.assign(mut_pos, mut_pos + nm);
+    h->mut_ref.assign(mut_ref, mut_ref + nm);
+    h->mut_nuc.assign(mut_nuc, mut_nuc + nm);
+    CU(upload(h->d_stripes, h->es.entries, h->stream));
+    CU(upload(h->d_stripe_off, h->es.stripe_off, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    h->has_arena = true;
+    h->has_reads = false;
+    h->has_mask = false;
+    h->has_results = false;
+    return WEPP_OK;
+}
+
+int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const int32_t* end,
+                   const int32_t* degree, const int64_t* rm_off, const int32_t* rm_pos, const uint8_t* rm_nuc) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (!h->has_arena) return fail(WEPP_E_STATE, "wepp_set_arena must be called first");
+    if (n_reads < 0) return fail(WEPP_E_INVALID, "n_reads < 0");
+    if (n_reads > 0 && (!start || !end || !degree || !rm_off)) return fail(WEPP_E_INVALID, "read arrays are NULL");
+    CU(cudaSetDevice(h->device));
+    static const int64_t zero_off[1] = {0};
+    if (n_reads == 0) rm_off = zero_off;
+    std::string err = build_read_plan(h->es, h->genome, n_reads, start, end, degree, rm_off, rm_pos, rm_nuc, h->opt_k,
+                                      nullptr, 0, h->full.plan);
+    if (!err.empty()) return fail(WEPP_E_INVALID, err);
+    h->n_reads = n_reads;
+    h->r_start.assign(start, start + n_reads);
+    h->r_end.assign(end, end + n_reads);
+    h->r_degree.assign(degree, degree + n_reads);
+    h->r_off.assign(rm_off, rm_off + n_reads + 1);
+    const int64_t nm = rm_off[n_reads];
+    h->r_pos.assign(rm_pos, rm_pos + nm);
+    h->r_nuc.assign(rm_nuc, rm_nuc + nm);
+    int rc = upload_plan(h, h->full);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    h->has_reads = true;
+    h->has_results = false;
+    return WEPP_OK;
+}
+
+int wepp_set_mapped(wepp_handle* h, const uint8_t* mapped) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (!h->has_arena) return fail(WEPP_E_STATE, "wepp_set_arena must be called first");
+    CU(cudaSetDevice(h->device));
+    bool any = false;
+    if (mapped)
+        for (int32_t v = 0; v < h->n_nodes && !any; ++v) any = mapped[v] != 0;
+    h->has_mask = any;
+    if (any) {
+        std::vector<uint8_t> m(mapped, mapped + h->n_nodes);
+        for (auto& x : m) x = x ? 1 : 0;
+        std::vector<int32_t> pre((size_t)h->n_nodes + 1, 0);
+        for (int32_t v = 0; v < h->n_nodes; ++v) pre[v + 1] = pre[v] + m[v];
+        CU(upload(h->d_mapped, m, h->stream));
+        CU(upload(h->d_mapped_prefix, pre, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    h->full.final_for_mask = false;
+    h->sub.final_for_mask = false;
+    return WEPP_OK;
+}
+
+int wepp_place(wepp_handle* h, int32_t epp_cap, int64_t epp_capacity) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (!h->has_reads) return fail(WEPP_E_STATE, "wepp_set_reads must be called first");
+    CU(cudaSetDevice(h->device));
+    return run_place(h, h->full, true, epp_cap, epp_capacity);
+}
+
+int wepp_place_subset(wepp_handle* h, int64_t n_sel, const int64_t* read_idx, int32_t epp_cap, int64_t epp_capacity) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (!h->has_reads) return fail(WEPP_E_STATE, "wepp_set_reads must be called first");
+    if (n_sel < 0 || (n_sel > 0 && !read_idx)) return fail(WEPP_E_INVALID, "bad subset");
+    CU(cudaSetDevice(h->device));
+    std::string err = build_read_plan(h->es, h->genome, h->n_reads, h->r_start.data(), h->r_end.data(), h->r_degree.data(),
+                                      h->r_off.data(), h->r_pos.data(), h->r_nuc.data(), h->opt_k, read_idx, n_sel,
+                                      h->sub.plan);
+    if (!err.empty()) return fail(WEPP_E_INVALID, err);
+    int rc = upload_plan(h, h->sub);
+    if (rc) return rc;
+    if (!h->has_results) {  // per-read arrays may not exist yet
+        CU(h->d_maxpars.ensure((size_t)h->n_reads));
+        CU(h->d_mult.ensure((size_t)h->n_reads));
+    }
+    return run_place(h, h->sub, false, epp_cap, epp_capacity);
+}
+
+int wepp_get_read_results(wepp_handle* h, int32_t* max_parsimony, int32_t* multiplicity) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (!h->has_results) return fail(WEPP_E_STATE, "no placement results yet");
+    CU(cudaSetDevice(h->device));
+    if (max_parsimony) CU(cudaMemcpy(max_parsimony, h->d_maxpars.p, (size_t)h->n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (multiplicity) CU(cudaMemcpy(multiplicity, h->d_mult.p, (size_t)h->n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return WEPP_OK;
+}
+
+int wepp_get_node_results(wepp_handle* h, double* score, int32_t* counts) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (!h->has_results || !h->d_score.p) return fail(WEPP_E_STATE, "no per-node results yet (call wepp_place)");
+    CU(cudaSetDevice(h->device));
+    if (score) CU(cudaMemcpy(score, h->d_score.p, (size_t)h->n_nodes * sizeof(double), cudaMemcpyDeviceToHost));
+    if (counts) CU(cudaMemcpy(counts, h->d_counts.p, (size_t)h->n_nodes * NBINS * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return WEPP_OK;
+}
+
+int wepp_get_epp(wepp_handle* h, int64_t* epp_off, int32_t* epp_nodes, int64_t capacity, int64_t* n_epp) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (!h->has_results || !h->has_epp) return fail(WEPP_E_STATE, "the last place call did not request EPP lists");
+    if (!epp_off) return fail(WEPP_E_INVALID, "epp_off is NULL");
+    CU(cudaSetDevice(h->device));
+    const int64_t r = h->n_reads;
+    std::vector<int64_t> off((size_t)r);
+    std::vector<int32_t> mult((size_t)r);
+    CU(cudaMemcpy(off.data(), h->d_epp_off.p, (size_t)r * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(mult.data(), h->d_mult.p, (size_t)r * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    unsigned long long used = 0;
+    CU(cudaMemcpy(&used, h->d_epp_total.p, sizeof(used), cudaMemcpyDeviceToHost));
+    used = std::min<unsigned long long>(used, (unsigned long long)h->epp_capacity);
+    std::vector<int32_t> dev_nodes((size_t)used);
+    if (used) CU(cudaMemcpy(dev_nodes.data(), h->d_epp_nodes.p, (size_t)used * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    // device lists are in allocation order; hand them back in read order
+    int64_t total = 0;
+    for (int64_t i = 0; i < r; ++i) {
+        epp_off[i] = total;
+        if (off[i] >= 0 && mult[i] > 0) total += mult[i];
+    }
+    epp_off[r] = total;
+    if (n_epp) *n_epp = total;
+    if (epp_nodes) {
+        if (total > capacity) return fail(WEPP_E_CAPACITY, "epp_nodes capacity too small");
+        for (int64_t i = 0; i < r; ++i)
+            if (off[i] >= 0 && mult[i] > 0)
+                std::memcpy(epp_nodes + epp_off[i], dev_nodes.data() + off[i], (size_t)mult[i] * sizeof(int32_t));
+    }
+    return WEPP_OK;
+}
+
+int wepp_cartesian_map(wepp_handle* h, int64_t n_reads, const int32_t* start, const int32_t* end,
+                       const int32_t* degree, const int64_t* rm_off, const int32_t* rm_pos, const uint8_t* rm_nuc,
+                       const uint8_t* mapped, int32_t* max_parsimony, int32_t* multiplicity, double* score,
+                       int32_t* counts) {
+    int rc = wepp_set_reads(h, n_reads, start, end, degree, rm_off, rm_pos, rm_nuc);
+    if (rc) return rc;
+    rc = wepp_set_mapped(h, mapped);
+    if (rc) return rc;
+    rc = wepp_place(h, 0, 0);
+    if (rc) return rc;
+    rc = wepp_get_read_results(h, max_parsimony, multiplicity);
+    if (rc) return rc;
+    return wepp_get_node_results(h, score, counts);
+}
+
+int wepp_device_buffer(wepp_handle* h, int32_t which, void** dev_ptr, int64_t* n_bytes) {
+    if (!h || !dev_ptr) return fail(WEPP_E_INVALID, "NULL argument");
+    if (!h->has_results) return fail(WEPP_E_STATE, "no placement results yet");
+    void* p = nullptr;
+    int64_t b = 0;
+    switch (which) {
+        case WEPP_BUF_SCORE: p = h->d_score.p; b = (int64_t)h->n_nodes * 8; break;
+        case WEPP_BUF_COUNTS: p = h->d_counts.p; b = (int64_t)h->n_nodes * NBINS * 4; break;
+        case WEPP_BUF_MAX_PARS: p = h->d_maxpars.p; b = h->n_reads * 4; break;
+        case WEPP_BUF_MULT: p = h->d_mult.p; b = h->n_reads * 4; break;
+        default: return fail(WEPP_E_INVALID, "unknown buffer id");
+    }
+    if (!p) return fail(WEPP_E_STATE, "buffer not allocated");
+    *dev_ptr = p;
+    if (n_bytes) *n_bytes = b;
+    return WEPP_OK;
+}
+
+int wepp_get_stats(wepp_handle* h, wepp_stats* out) {
+    if (!h || !out) return fail(WEPP_E_INVALID, "NULL argument");
+    *out = h->stats;
+    return WEPP_OK;
+}
+
+// Host-only view of the Euler stripes (no GPU needed): used by the CPU test-suite to check the
+// signed-delta tables against the oracle.  entries = 4 x uint32 per entry (Entry master form).
+int64_t wepp_host_euler_stripes(int32_t n_nodes, const int32_t* parent, const int64_t* mut_off, const int32_t* mut_pos,
+                                const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size,
+                                int32_t stripe_width, uint32_t* entries, int64_t capacity, int64_t* stripe_off,
+                                int32_t stripe_off_len) {
+    EulerStripes es;
+    std::string err = build_euler_stripes(n_nodes, parent, mut_off, mut_pos, mut_ref, mut_nuc, genome_size, stripe_width, es);
+    if (!err.empty()) return fail(WEPP_E_INVALID, err);
+    const int64_t n = (int64_t)es.entries.size();
+    if (entries) {
+        if (capacity < n) return fail(WEPP_E_CAPACITY, "entries capacity too small");
+        std::memcpy(entries, es.entries.data(), (size_t)n * sizeof(Entry));
+    }
+    if (stripe_off) {
+        if (stripe_off_len < es.n_stripes + 1) return fail(WEPP_E_CAPACITY, "stripe_off too small");
+        std::memcpy(stripe_off, es.stripe_off.data(), ((size_t)es.n_stripes + 1) * sizeof(int64_t));
+    }
+    return n;
+}
+
+// Host-only view of the read plan: bucket-sorted permutation and, per sorted read, the list's
+// stripe range; returns the number of tiles (or a negative error).
+int64_t wepp_host_read_plan(int32_t genome_size, int32_t stripe_width, int32_t reads_per_lane, int64_t n_reads,
+                            const int32_t* start, const int32_t* end, const int32_t* degree, const int64_t* rm_off,
+                            const int32_t* rm_pos, const uint8_t* rm_nuc, int64_t* perm, int32_t* qs, int32_t* qe,
+                            int32_t* bin, int32_t* reads_per_tile) {
+    EulerStripes es;
+    es.stripe_width = stripe_width;
+    es.n_stripes = genome_size / stripe_width + 1;
+    es.stripe_off.assign((size_t)es.n_stripes + 1, 0);
+    ReadPlan pl;
+    std::string err = build_read_plan(es, genome_size, n_reads, start, end, degree, rm_off, rm_pos, rm_nuc,
+                                      reads_per_lane, nullptr, 0, pl);
+    if (!err.empty()) return fail(WEPP_E_INVALID, err);
+    for (const TileDesc& t : pl.tiles)
+        for (int64_t i = t.first; i < t.first + t.count; ++i) {
+            const BucketDesc& b = pl.buckets[t.bucket];
+            if (perm) perm[i] = pl.perm[i];
+            if (qs) qs[i] = pl.lists[b.list].qs;
+            if (qe) qe[i] = pl.lists[b.list].qe;
+            if (bin) bin[i] = b.bin;
+        }
+    if (reads_per_tile) *reads_per_tile = pl.reads_per_tile;
+    return (int64_t)pl.tiles.size();
+}
+
+int wepp_rescore(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, int32_t* min_dist, int32_t* dist,
+                 int64_t* am_off, int32_t* am_idx, int64_t am_capacity) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (!h->has_reads) return fail(WEPP_E_STATE, "wepp_set_reads must be called first");
+    if (n_cand < 1 || !cand_nodes || !min_dist) return fail(WEPP_E_INVALID, "bad candidate set / min_dist is NULL");
+    CU(cudaSetDevice(h->device));
+    std::string err;
+    int rc = rescore_run(h->device, h->stream, h->n_nodes, h->genome, h->parent.data(), h->mut_off.data(), h->mut_pos.data(),
+                         h->mut_ref.data(), h->mut_nuc.data(), h->n_reads, h->r_start.data(), h->r_end.data(),
+                         h->r_off.data(), h->r_pos.data(), h->r_nuc.data(), n_cand, cand_nodes, min_dist, dist, am_off,
+                         am_idx, am_capacity, err);
+    if (rc) return fail(rc, err);
+    return WEPP_OK;
+}
+
+}  // extern "C"
