@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — reads placed/s of WEPP's parsimonious read placement on B200(s).
+
+    python bench.py --gpus N --steps K --warmup W              # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...    # the reference's CPU placement
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): a synthetic
+public-scale SARS-CoV-2 MAT (8M arena nodes, genome 29,903) x ARTIC-like 150-bp amplicon
+reads, read-sharded: every GPU places 1.25M collapsed reads against the replicated tree
+(weak scaling; 8 GPUs = the full 10M reads).  One step = one cartesian_map over the rank's
+shard: placement kernel + segment expansion + per-node scans, and for N>1 the NCCL
+all-reduce of the per-node score / read-count arrays.
+
+One JSON line is printed by rank 0 (see README / DESIGN.md for the keys).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NODES_FULL = 8_000_000
+READS_PER_GPU_FULL = 1_250_000
+GENOME = 29903
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink nodes and reads (development only)")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-baseline budget per measurement")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload(scale: float, rank: int):
+    from wepp_b200 import synth
+    n_nodes = max(int(NODES_FULL * scale), 1000)
+    n_reads = max(int(READS_PER_GPU_FULL * scale), 256)
+    arena = synth.make_arena(n_nodes, GENOME, synth.SEED)
+    reads = synth.make_reads(arena, n_reads, synth.SEED + 1000 * rank)
+    return arena, reads
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.device), "-lms", "100"], stdout=f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def cuda_view(ptr: int, n: int, typestr: str, device: int):
+    """torch tensor over a library-owned device buffer (for NCCL)."""
+    import torch
+
+    class _V:
+        pass
+    v = _V()
+    v.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+    return torch.as_tensor(v, device=f"cuda:{device}")
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference(arena, reads, seconds: float):
+    """The reference's CPU placement on a bounded read sample with all host threads: the
+    shim-compiled reference object code (oracle/_ref) when present, else the oracle port."""
+    import oracle
+    cores = os.cpu_count() or 1
+    kind = "port"
+    runner = None
+    try:
+        from oracle import ref as oref
+        if oref.available() and oref.fits_in_memory(arena.n_nodes):
+            kind = "reference"
+            runner = oref
+    except Exception:
+        runner = None
+    # calibrate: one read per thread, then size the sample for `seconds`
+    n0 = min(reads.n_reads, cores)
+    sample = reads.slice(0, n0)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        sess = runner.Session(arena, threads=cores)
+        t_build = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        sess.cartesian_map(sample)
+    else:
+        t_build = 0.0
+        oracle.cartesian_map(arena, sample, None, n_threads=cores, want_node=False)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    n1 = int(min(reads.n_reads, max(n0, n0 * seconds / dt)))
+    n1 = max(cores, (n1 // cores) * cores)
+    n1 = min(n1, reads.n_reads)
+    sample = reads.slice(0, n1)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        sess.cartesian_map(sample)
+        sess.close()
+    else:
+        oracle.cartesian_map(arena, sample, None, n_threads=cores, want_node=False)
+    dt = max(time.perf_counter() - t0, 1e-6)
+    return {"value": n1 / dt, "unit": "reads/s", "cores": cores, "kind": kind,
+            "sample": f"{n1} of the step's {reads.n_reads} reads vs all {arena.n_nodes} nodes, {dt:.1f} s"
+                      + (f" (+{t_build:.1f} s reference arena build, untimed)" if kind == "reference" else "")}
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    arena, reads = workload(args.scale, 0)
+    vals = []
+    base = None
+    for _ in range(max(1, min(args.steps, 3))):
+        base = cpu_reference(arena, reads, args.cpu_seconds)
+        vals.append(base["value"])
+    v = float(np.median(vals))
+    base["value"] = v
+    out = {"impl": "reference", "metric": "reads placed/s", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+           "config": config_dict(arena, reads, args), "cpu_baseline": base,
+           "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def config_dict(arena, reads, args):
+    return {"workload": f"C3 synthetic SARS-CoV-2-scale MAT ({arena.n_nodes} arena nodes, {arena.n_events} events, "
+                        f"genome {GENOME}) x {reads.n_reads} ARTIC-like 150-bp collapsed reads per GPU "
+                        f"(read-sharded; 8 GPUs = 10M reads)",
+            "nodes": arena.n_nodes, "reads_per_gpu": reads.n_reads, "seed": 20260101,
+            "l2": "inputs exceed L2 (Euler lists + 1.6 GB per-node arrays are re-zeroed and re-streamed every step)"}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import torch
+    import torch.distributed as dist
+    from wepp_b200.placement import Placer
+
+    torch.cuda.set_device(local_rank)
+    dev = local_rank
+    arena, reads = workload(args.scale, rank)
+    p = Placer(dev)
+    stream = torch.cuda.current_stream()
+    p.set_stream(stream.cuda_stream)
+    t0 = time.perf_counter()
+    p.set_arena(arena)
+    t_arena = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    p.set_reads(reads)
+    t_reads = time.perf_counter() - t0
+
+    def allreduce_nodes():
+        if world == 1:
+            return
+        sp, sb = p.device_buffer(1)
+        cp, cb = p.device_buffer(2)
+        dist.all_reduce(cuda_view(cp, cb // 4, "<i4", dev))
+        dist.all_reduce(cuda_view(sp, sb // 8, "<f8", dev))
+
+    def step():
+        p.place(0, 0, sync=False)
+        allreduce_nodes()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    scan_ms = []
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    # the dominant kernel's own launch time (CUDA events on the launching stream), separate short loop
+    for _ in range(3):
+        p.place(0, 0, sync=True)
+        scan_ms.append(p.stats()["ms_scan_kernel"])
+    st = p.stats()
+    if world > 1:
+        t = torch.tensor([ms], device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    reads_total = reads.n_reads * world
+    value = reads_total / (ms_per_step / 1e3)
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        n, r = arena.n_nodes, reads.n_reads
+        mp = torch.empty(r, dtype=torch.int32, pin_memory=True).numpy()
+        mu = torch.empty(r, dtype=torch.int32, pin_memory=True).numpy()
+        sc = torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
+        ct = torch.empty((n, 50), dtype=torch.int32, pin_memory=True).numpy()
+        from wepp_b200._lib import check, ptr
+
+        def e2e_step():
+            p.set_reads(reads)          # host packing + H2D + per-window Euler list build
+            p.set_mapped(None)
+            p.place(0, 0, sync=False)
+            allreduce_nodes()
+            check(p.lib.wepp_get_read_results(p.h, ptr(mp), ptr(mu)))
+            if rank == 0 or world == 1:
+                check(p.lib.wepp_get_node_results(p.h, ptr(sc), ptr(ct)))
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        k_e2e = max(1, min(args.steps, 3))
+        for _ in range(k_e2e):
+            e2e_step()
+        barrier()
+        dt = (time.perf_counter() - t0) / k_e2e
+        if world > 1:
+            t = torch.tensor([dt], device=f"cuda:{dev}")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = int(r * (12 + 8 + 8) + reads.rm_pos.shape[0] * 5 + st["n_tiles"] * 16 + st["n_lists"] * 32)
+        d2h = int(r * 8 + n * (8 + 200))
+        e2e = {"value": reads_total / dt, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": dt * 1e3}
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    k_ms = float(np.mean(scan_ms))
+    # algorithmic bytes of the placement kernel alone: two passes over each tile's Euler list
+    # (16-B entries), one 12-B accumulator update per (tile, entry), packed reads in, results out
+    alg = (st["scanned_entries"] * (16 * 2 + 12) + reads.n_reads * (12 + 8 + 8 + 8) + reads.rm_pos.shape[0] * 5)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("nodes") == arena.n_nodes and tj.get("reads_per_gpu") == reads.n_reads:
+                traffic = tj.get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    achieved = alg / (k_ms / 1e3) / 1e9
+    out = {
+        "metric": "reads placed/s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config_dict(arena, reads, args),
+        "read_x_node_scores_per_s": value * arena.n_nodes,
+        "touched_read_entries_per_s": st["scanned_read_entries"] * 2 * world / (ms_per_step / 1e3),
+        "e2e": e2e, "gpu_launches": int(st["kernel_launches"] * args.steps),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "place_kernel", "kernel_ms": k_ms,
+                     "algorithmic_bytes_per_launch": int(alg), "peak_source": peak_src,
+                     "note": "issue-bound tile scan: lists are L2-resident, see DESIGN.md"},
+        "clocks": clocks,
+        "setup_s": {"flatten_tree": t_arena, "pack_reads_and_build_lists": t_reads},
+        "stats": {k: st[k] for k in ("n_tiles", "n_lists", "n_buckets", "reads_per_tile", "stripe_width",
+                                     "list_entries_total", "scanned_entries", "ms_scan_kernel", "ms_node_kernels")},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_reference(arena, reads, args.cpu_seconds)
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=None)
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

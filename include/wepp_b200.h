@@ -57,6 +57,13 @@ void        wepp_destroy(wepp_handle* h);
 const char* wepp_last_error(void);
 int         wepp_abi_version(void);
 
+/* Stream control.  By default the handle owns a private non-blocking stream.  wepp_set_stream
+ * makes every later launch and copy use the caller's cudaStream_t (passed as void*), so the
+ * caller can order its own work (NCCL collectives, CUDA events) against the placement.
+ * wepp_place / wepp_place_subset only enqueue work; wepp_sync (or any wepp_get_*) waits.  */
+int wepp_set_stream(wepp_handle* h, void* cuda_stream);
+int wepp_sync(wepp_handle* h);
+
 /* Tunables (optional, before wepp_set_arena): stripe width in bases used to bucket read
  * windows (default 32) and reads per warp lane K in {2,4,8} (0 = choose per bucket). */
 int wepp_set_options(wepp_handle* h, int32_t stripe_width, int32_t reads_per_lane);

@@ -1,0 +1,177 @@
+"""GPU suite: the CUDA path through the C ABI against the oracle (bit-exact integers, scores to
+1e-9 relative — the reference's own tie tolerance SCORE_EPSILON, src/WEPP/config.hpp:15)."""
+import numpy as np
+import pytest
+
+import oracle
+from tests import cases
+from wepp_b200 import synth
+from wepp_b200.placement import Placer, WeppFilter
+
+pytestmark = pytest.mark.gpu
+
+SCORE_RTOL = 1e-9   # doubles: relative tolerance (plus 1e-15 absolute for exact zeros)
+
+
+def _check(arena, reads, mapped, q=None, k=None, epp_cap=None, threads=4):
+    epp_cap = arena.n_nodes if epp_cap is None else epp_cap
+    o = oracle.cartesian_map(arena, reads, mapped, n_threads=threads, epp_cap=epp_cap)
+    p = Placer(0, stripe_width=q, reads_per_lane=k)
+    p.set_arena(arena)
+    p.set_reads(reads)
+    p.set_mapped(mapped)
+    p.place(epp_cap, int(o["epp_off"][-1]) + 16)
+    mp, mu = p.read_results()
+    sc, ct = p.node_results()
+    off, nodes = p.epp()
+    assert np.array_equal(mp, o["max_parsimony"])
+    assert np.array_equal(mu, o["multiplicity"])
+    assert np.array_equal(ct, o["counts"])
+    np.testing.assert_allclose(sc, o["score"], rtol=SCORE_RTOL, atol=1e-15)
+    assert np.array_equal(off, o["epp_off"])
+    assert np.array_equal(nodes, o["epp_nodes"])
+    st = p.stats()
+    p.close()
+    return st
+
+
+@pytest.mark.parametrize("seed,q,k", [(0, 8, 8), (1, 8, 4), (2, 16, 2), (3, 4, 0), (4, 32, 8), (5, 1, 2)])
+def test_tiny_cases_all_edge_kinds(seed, q, k):
+    arena, reads, mapped = cases.tiny_case(seed)
+    _check(arena, reads, None, q, k)
+    _check(arena, reads, mapped, q, k)
+
+
+@pytest.mark.parametrize("k", [0, 2, 4, 8])
+def test_small_case(k):
+    arena, reads = cases.small_case()
+    st = _check(arena, reads, None, 32, k)
+    assert st["n_tiles"] > 0 and st["kernel_launches"] >= 7
+
+
+def test_small_case_with_mask_and_cap():
+    arena, reads = cases.small_case(seed=11)
+    rng = np.random.default_rng(5)
+    mapped = (rng.random(arena.n_nodes) < 0.3).astype(np.uint8)
+    _check(arena, reads, mapped, 32, 0, epp_cap=64)
+
+
+def test_empty_and_ragged_inputs():
+    arena, reads = cases.small_case(seed=3, n_reads=70)
+    # zero reads
+    p = Placer(0)
+    p.set_arena(arena)
+    p.set_reads(reads.slice(0, 0))
+    p.place(0, 0)
+    sc, ct = p.node_results()
+    assert not sc.any() and not ct.any()
+    p.close()
+    # one read, and a read count that is not a multiple of the tile size
+    _check(arena, reads.slice(0, 1), None)
+    _check(arena, reads.slice(0, 33), None, k=2)
+    # single-node tree
+    one = synth.Arena(arena.genome_size, arena.ref_codes, np.array([-1], np.int32), np.array([0, 0], np.int64),
+                      np.zeros(0, np.int32), np.zeros(0, np.uint8), np.zeros(0, np.uint8))
+    _check(one, reads, None)
+
+
+def test_everything_mapped_gives_zero_multiplicity():
+    arena, reads = cases.small_case(seed=5, n_reads=100)
+    mapped = np.ones(arena.n_nodes, np.uint8)
+    o = oracle.cartesian_map(arena, reads, mapped)
+    assert not o["multiplicity"].any()
+    _check(arena, reads, mapped)
+
+
+def test_medium_case_c2_shape():
+    """SARS-CoV-2 shape at 1/50 scale: 20k nodes x 20k reads, genome 29,903."""
+    arena, reads, _ = synth.config_shape("C2", scale=0.02)
+    _check(arena, reads, None, epp_cap=2048, threads=8)
+
+
+def test_long_reads_c4_shape():
+    """ONT shape (1.1 kb windows) at small scale: exercises wide buckets / K=2."""
+    arena = synth.make_arena(6000, 29903, 5)
+    reads = synth.make_reads(arena, 300, 5, amplicons=synth.amplicon_scheme(29903, 29, 1058, 1201, 5),
+                             full_amplicon=True, err=0.03, n_rate=0.05, n_templates=40)
+    _check(arena, reads, None, epp_cap=2048, threads=8)
+
+
+def test_place_subset_under_mask_matches_oracle():
+    """remove_read's recompute path (initial_filter.cpp:298-302)."""
+    arena, reads = cases.small_case(seed=13)
+    rng = np.random.default_rng(1)
+    mapped = (rng.random(arena.n_nodes) < 0.25).astype(np.uint8)
+    sel = np.sort(rng.choice(reads.n_reads, 37, replace=False)).astype(np.int64)
+    p = Placer(0)
+    p.set_arena(arena)
+    p.set_reads(reads)
+    p.place(0, 0)
+    base_mp, base_mu = p.read_results()
+    p.set_mapped(mapped)
+    p.place_subset(sel, arena.n_nodes, 37 * arena.n_nodes)
+    mp, mu = p.read_results()
+    off, nodes = p.epp()
+    o = oracle.cartesian_map(arena, reads.take(sel), mapped, epp_cap=arena.n_nodes)
+    assert np.array_equal(mp[sel], o["max_parsimony"]) and np.array_equal(mu[sel], o["multiplicity"])
+    rest = np.setdiff1d(np.arange(reads.n_reads), sel)
+    assert np.array_equal(mp[rest], base_mp[rest]) and np.array_equal(mu[rest], base_mu[rest])
+    for i, r in enumerate(sel):
+        assert np.array_equal(nodes[off[r]:off[r + 1]], o["epp_nodes"][o["epp_off"][i]:o["epp_off"][i + 1]])
+    p.close()
+
+
+def test_cartesian_map_host_call_and_filter_mirror():
+    arena, reads = cases.small_case(seed=17)
+    o = oracle.cartesian_map(arena, reads, None, n_threads=4)
+    p = Placer(0)
+    p.set_arena(arena)
+    mp, mu, sc, ct = p.cartesian_map_host(reads)
+    assert np.array_equal(mp, o["max_parsimony"]) and np.array_equal(mu, o["multiplicity"])
+    assert np.array_equal(ct, o["counts"])
+    np.testing.assert_allclose(sc, o["score"], rtol=SCORE_RTOL, atol=1e-15)
+    f = WeppFilter(p).cartesian_map(reads)
+    assert np.array_equal(f.max_parismony, mp)
+    off, nodes = f.epp_positions_cache
+    assert np.array_equal(off, o["epp_off"]) and np.array_equal(nodes, o["epp_nodes"])
+    assert f.dist_divergence.shape == (arena.n_nodes,)
+    p.close()
+
+
+def test_rescore_matches_oracle():
+    arena, reads = cases.small_case(seed=19)
+    rng = np.random.default_rng(2)
+    cand = rng.choice(arena.n_nodes, 150, replace=False).astype(np.int32)
+    p = Placer(0)
+    p.set_arena(arena)
+    p.set_reads(reads)
+    md, dist, off, idx = p.rescore(cand, want_dist=True)
+    omd, odist, ooff, oidx = oracle.rescore(arena, reads, cand)
+    assert np.array_equal(md, omd) and np.array_equal(dist, odist)
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx)
+    p.close()
+
+
+def test_full_size_properties():
+    """Size-independent properties at a size the oracle cannot finish: (1) degrees are
+    conserved — sum over nodes of counts[v][b] == sum over reads in bin b of degree*multiplicity;
+    (2) sum of scores == sum of degree/(1+p) over reads with a non-empty EPP set; (3) idempotence."""
+    arena, reads, _ = synth.config_shape("C2", scale=0.2)   # 200k nodes x 200k reads
+    p = Placer(0)
+    p.set_arena(arena)
+    p.set_reads(reads)
+    p.place(0, 0)
+    mp, mu = p.read_results()
+    sc, ct = p.node_results()
+    bins = np.minimum(reads.start // (arena.genome_size // 50), 49)
+    expect = np.bincount(bins, weights=reads.degree.astype(np.float64) * mu, minlength=50)
+    assert np.array_equal(ct.sum(axis=0, dtype=np.int64), expect.astype(np.int64))
+    tot = (reads.degree / (1.0 + mp))[mu > 0].sum()
+    assert abs(sc.sum() - tot) <= 1e-9 * tot
+    assert mp.min() >= 0 and mu.min() >= 1 and mu.max() <= arena.n_nodes
+    p.place(0, 0)
+    mp2, mu2 = p.read_results()
+    sc2, ct2 = p.node_results()
+    assert np.array_equal(mp, mp2) and np.array_equal(mu, mu2) and np.array_equal(ct, ct2)
+    np.testing.assert_allclose(sc, sc2, rtol=1e-12)
+    p.close()

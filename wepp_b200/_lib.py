@@ -36,6 +36,8 @@ SIGNATURES = {
     "wepp_destroy": (None, [VP]),
     "wepp_last_error": (C.c_char_p, []),
     "wepp_abi_version": (C.c_int, []),
+    "wepp_set_stream": (C.c_int, [VP, VP]),
+    "wepp_sync": (C.c_int, [VP]),
     "wepp_set_options": (C.c_int, [VP, C.c_int32, C.c_int32]),
     "wepp_set_arena": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, C.c_int32]),
     "wepp_set_reads": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, VP]),

@@ -58,6 +58,8 @@ struct wepp_handle {
     int n_sms = 148;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    bool stats_pending = false;
     cudaEvent_t ev[6] = {};
     int32_t opt_q = 32, opt_k = 0;
 
@@ -290,11 +292,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         launches += 6;
     }
     CU(cudaEventRecord(h->ev[2], h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-
-    float ms_scan = 0, ms_node = 0;
-    CU(cudaEventElapsedTime(&ms_scan, h->ev[0], h->ev[1]));
-    CU(cudaEventElapsedTime(&ms_node, h->ev[1], h->ev[2]));
+    h->stats_pending = true;
     wepp_stats& st = h->stats;
     st.n_nodes = n;
     st.n_events = h->es.n_events;
@@ -307,9 +305,6 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     st.scanned_entries = pl.scanned_entries;
     st.scanned_read_entries = pl.scanned_read_entries;
     st.kernel_launches = launches;
-    st.ms_scan_kernel = ms_scan;
-    st.ms_node_kernels = ms_node;
-    st.ms_place_total = ms_scan + ms_node;
     st.reads_per_tile = pl.reads_per_tile;
     st.stripe_width = h->es.stripe_width;
     // Algorithmic bytes of one place (DESIGN.md "Roofline"): two passes over each tile's Euler
@@ -372,7 +367,7 @@ void wepp_destroy(wepp_handle* h) {
     h->d_cchunk_tot.release(); h->d_cchunk_off.release(); h->d_epp_off.release(); h->d_epp_nodes.release();
     h->d_epp_total.release(); h->d_tile_counter.release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
-    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
 
@@ -493,8 +488,9 @@ int wepp_get_read_results(wepp_handle* h, int32_t* max_parsimony, int32_t* multi
     if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
     if (!h->has_results) return fail(WEPP_E_STATE, "no placement results yet");
     CU(cudaSetDevice(h->device));
-    if (max_parsimony) CU(cudaMemcpy(max_parsimony, h->d_maxpars.p, (size_t)h->n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    if (multiplicity) CU(cudaMemcpy(multiplicity, h->d_mult.p, (size_t)h->n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (max_parsimony) CU(cudaMemcpyAsync(max_parsimony, h->d_maxpars.p, (size_t)h->n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    if (multiplicity) CU(cudaMemcpyAsync(multiplicity, h->d_mult.p, (size_t)h->n_reads * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return WEPP_OK;
 }
 
@@ -502,8 +498,9 @@ int wepp_get_node_results(wepp_handle* h, double* score, int32_t* counts) {
     if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
     if (!h->has_results || !h->d_score.p) return fail(WEPP_E_STATE, "no per-node results yet (call wepp_place)");
     CU(cudaSetDevice(h->device));
-    if (score) CU(cudaMemcpy(score, h->d_score.p, (size_t)h->n_nodes * sizeof(double), cudaMemcpyDeviceToHost));
-    if (counts) CU(cudaMemcpy(counts, h->d_counts.p, (size_t)h->n_nodes * NBINS * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (score) CU(cudaMemcpyAsync(score, h->d_score.p, (size_t)h->n_nodes * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (counts) CU(cudaMemcpyAsync(counts, h->d_counts.p, (size_t)h->n_nodes * NBINS * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return WEPP_OK;
 }
 
@@ -515,13 +512,15 @@ int wepp_get_epp(wepp_handle* h, int64_t* epp_off, int32_t* epp_nodes, int64_t c
     const int64_t r = h->n_reads;
     std::vector<int64_t> off((size_t)r);
     std::vector<int32_t> mult((size_t)r);
-    CU(cudaMemcpy(off.data(), h->d_epp_off.p, (size_t)r * sizeof(int64_t), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(mult.data(), h->d_mult.p, (size_t)r * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpyAsync(off.data(), h->d_epp_off.p, (size_t)r * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(mult.data(), h->d_mult.p, (size_t)r * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     unsigned long long used = 0;
-    CU(cudaMemcpy(&used, h->d_epp_total.p, sizeof(used), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpyAsync(&used, h->d_epp_total.p, sizeof(used), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     used = std::min<unsigned long long>(used, (unsigned long long)h->epp_capacity);
     std::vector<int32_t> dev_nodes((size_t)used);
-    if (used) CU(cudaMemcpy(dev_nodes.data(), h->d_epp_nodes.p, (size_t)used * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (used) CU(cudaMemcpyAsync(dev_nodes.data(), h->d_epp_nodes.p, (size_t)used * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     // device lists are in allocation order; hand them back in read order
     int64_t total = 0;
     for (int64_t i = 0; i < r; ++i) {
@@ -572,8 +571,36 @@ int wepp_device_buffer(wepp_handle* h, int32_t which, void** dev_ptr, int64_t* n
     return WEPP_OK;
 }
 
+int wepp_sync(wepp_handle* h) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return WEPP_OK;
+}
+
+int wepp_set_stream(wepp_handle* h, void* cuda_stream) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    return WEPP_OK;
+}
+
 int wepp_get_stats(wepp_handle* h, wepp_stats* out) {
     if (!h || !out) return fail(WEPP_E_INVALID, "NULL argument");
+    if (h->stats_pending) {
+        CU(cudaSetDevice(h->device));
+        CU(cudaEventSynchronize(h->ev[2]));
+        float ms_scan = 0, ms_node = 0;
+        CU(cudaEventElapsedTime(&ms_scan, h->ev[0], h->ev[1]));
+        CU(cudaEventElapsedTime(&ms_node, h->ev[1], h->ev[2]));
+        h->stats.ms_scan_kernel = ms_scan;
+        h->stats.ms_node_kernels = ms_node;
+        h->stats.ms_place_total = ms_scan + ms_node;
+        h->stats_pending = false;
+    }
     *out = h->stats;
     return WEPP_OK;
 }

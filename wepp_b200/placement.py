@@ -69,12 +69,22 @@ class Placer:
         check(self.lib.wepp_set_mapped(self.h, ptr(m)))
 
     # -- compute -----------------------------------------------------------------------------
-    def place(self, epp_cap: int = 0, epp_capacity: int = 0) -> None:
+    def set_stream(self, cuda_stream: int) -> None:
+        """Run all later work on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
+        check(self.lib.wepp_set_stream(self.h, C.c_void_p(int(cuda_stream))))
+
+    def sync(self) -> None:
+        check(self.lib.wepp_sync(self.h))
+
+    def place(self, epp_cap: int = 0, epp_capacity: int = 0, sync: bool = True) -> None:
         check(self.lib.wepp_place(self.h, int(epp_cap), int(epp_capacity)))
+        if sync:
+            self.sync()
 
     def place_subset(self, read_idx, epp_cap: int = 0, epp_capacity: int = 0) -> None:
         idx = _c(read_idx, np.int64)
         check(self.lib.wepp_place_subset(self.h, idx.shape[0], ptr(idx), int(epp_cap), int(epp_capacity)))
+        self.sync()
 
     # -- outputs -----------------------------------------------------------------------------
     def read_results(self):
@@ -151,7 +161,7 @@ class WeppFilter:
         p = self.placer
         p.set_reads(reads)
         p.set_mapped(mapped)
-        cap = int(epp_capacity if epp_capacity is not None else min(reads.n_reads * 64 + 1024, 1 << 28))
+        cap = int(epp_capacity if epp_capacity is not None else min(reads.n_reads * MAX_CACHED_EPP_SIZE + 1024, 1 << 28))
         p.place(MAX_CACHED_EPP_SIZE, cap)
         self.max_parismony, self.parsimony_multiplicity = p.read_results()
         self.epp_positions_cache = p.epp()
