@@ -209,7 +209,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dev = local_rank
     arena, reads = workload(args.scale, rank)
-    p = Placer(dev)
+    k_env = int(os.environ.get("WEPP_READS_PER_LANE", "0"))   # development knob
+    q_env = int(os.environ.get("WEPP_STRIPE_WIDTH", "32"))
+    p = Placer(dev, stripe_width=q_env, reads_per_lane=k_env)
     stream = torch.cuda.current_stream()
     p.set_stream(stream.cuda_stream)
     t0 = time.perf_counter()

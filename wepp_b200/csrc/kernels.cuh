@@ -71,6 +71,23 @@ template <> struct Elem<8> { using type = uint32_t; };
 template <> struct Elem<4> { using type = uint16_t; };
 template <> struct Elem<2> { using type = uint8_t; };
 
+// prmt without __byte_perm's selector masking: codes are <= 5, so bit 3 of a selector nibble
+// (sign-replicate mode) is never set.
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+// Per-warp shared-memory layout of place_kernel (bytes from the warp's base).
+constexpr int RED_G = 8;              // entries reduced together in pass 2
+constexpr int RED_S_STRIDE = 36;      // doubles per staged row: 32 lanes + pad (conflict-free column sums)
+constexpr int RED_C_STRIDE = 33;      // ints per staged row
+constexpr int SMEM_EBUF = 0;                                        // 32 staged entries (512 B)
+constexpr int SMEM_REDS = 512;                                      // double[RED_G][RED_S_STRIDE]
+constexpr int SMEM_REDC = SMEM_REDS + RED_G * RED_S_STRIDE * 8;     // int[RED_G][RED_C_STRIDE]
+constexpr int SMEM_CODES = (SMEM_REDC + RED_G * RED_C_STRIDE * 4 + 15) & ~15;
+
 __device__ __forceinline__ uint4 ld_entry(const Entry* p) {
     return __ldg(reinterpret_cast<const uint4*>(p));
 }
@@ -135,7 +152,9 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceParams p) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem + (size_t)warp * p.smem_per_warp;
     uint4* ebuf = reinterpret_cast<uint4*>(wbase);   // 32 staged entries
-    ET* codes = reinterpret_cast<ET*>(wbase + 512);  // [width][32] read-allele codes, K nibbles per lane
+    double* redS = reinterpret_cast<double*>(wbase + SMEM_REDS);
+    int* redC = reinterpret_cast<int*>(wbase + SMEM_REDC);
+    ET* codes = reinterpret_cast<ET*>(wbase + SMEM_CODES);  // [width][32] read-allele codes, K nibbles per lane
     const unsigned FULL = 0xFFFFFFFFu;
 
     for (;;) {
@@ -205,9 +224,9 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceParams p) {
                 for (int ii = 0; ii < m; ++ii) {
                     const uint4 e = ebuf[ii];
                     const uint32_t w = codes[(e.w >> 16) * 32 + lane];
-                    const uint32_t d0 = __byte_perm(e.z, e.w, w);
+                    const uint32_t d0 = prmt(e.z, e.w, w);
                     uint32_t d1 = 0;
-                    if (K == 8) d1 = __byte_perm(e.z, e.w, w >> 16);
+                    if (K == 8) d1 = prmt(e.z, e.w, w >> 16);
 #pragma unroll
                     for (int j = 0; j < K; ++j)
                         run[j] = __dp4a((int)(j < 4 ? d0 : d1), (int)(1u << (8 * (j & 3))), run[j]);
@@ -281,53 +300,75 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceParams p) {
                 __syncwarp();
                 if (base + 32 + lane < n) nxt = ld_entry(ent + base + 32 + lane);
                 const int m = min(32, n - base);
+                for (int g0 = 0; g0 < m; g0 += RED_G) {
+                    const int gm = min(RED_G, m - g0);
 #pragma unroll 2
-                for (int ii = 0; ii < m; ++ii) {
-                    const uint4 e = ebuf[ii];
-                    const uint32_t w = codes[(e.w >> 16) * 32 + lane];
-                    const uint32_t d0 = __byte_perm(e.z, e.w, w);
-                    uint32_t d1 = 0;
-                    if (K == 8) d1 = __byte_perm(e.z, e.w, w >> 16);
+                    for (int gi = 0; gi < gm; ++gi) {
+                        const int ii = g0 + gi;
+                        const uint4 e = ebuf[ii];
+                        const uint32_t w = codes[(e.w >> 16) * 32 + lane];
+                        const uint32_t d0 = prmt(e.z, e.w, w);
+                        uint32_t d1 = 0;
+                        if (K == 8) d1 = prmt(e.z, e.w, w >> 16);
 #pragma unroll
-                    for (int j = 0; j < K; ++j)
-                        run[j] = __dp4a((int)(j < 4 ? d0 : d1), (int)(1u << (8 * (j & 3))), run[j]);
-                    if (e.x & SEG_FLAG) {
+                        for (int j = 0; j < K; ++j)
+                            run[j] = __dp4a((int)(j < 4 ? d0 : d1), (int)(1u << (8 * (j & 3))), run[j]);
                         double s = 0.0;
                         int c = 0;
-                        uint32_t hit = 0;
-#pragma unroll
-                        for (int j = 0; j < K; ++j) {
-                            const bool eq = run[j] == best[j];
-                            s += eq ? wgt[j] : 0.0;
-                            c += eq ? deg[j] : 0;
-                            hit |= eq ? (1u << j) : 0u;
-                        }
-                        hit &= small_mask;
-                        if (hit) {  // rare: explicit EPP lists (sorted: the list is in preorder)
+                        if (e.x & SEG_FLAG) {
+                            uint32_t hit = 0;
 #pragma unroll
                             for (int j = 0; j < K; ++j) {
-                                if (hit & (1u << j)) {
-                                    uint32_t v = e.x & IDX_MASK;
-                                    uint32_t u = e.y;
-                                    while (u) {
-                                        if (!p.mapped || !p.mapped[v]) {
-                                            p.epp_nodes[wp[j]++] = (int32_t)v;
-                                            --u;
+                                const bool eq = run[j] == best[j];
+                                s += eq ? wgt[j] : 0.0;
+                                c += eq ? deg[j] : 0;
+                                hit |= eq ? (1u << j) : 0u;
+                            }
+                            hit &= small_mask;
+                            if (hit) {  // rare: explicit EPP lists (sorted: the list is in preorder)
+#pragma unroll
+                                for (int j = 0; j < K; ++j) {
+                                    if (hit & (1u << j)) {
+                                        uint32_t v = e.x & IDX_MASK;
+                                        uint32_t u = e.y;
+                                        while (u) {
+                                            if (!p.mapped || !p.mapped[v]) {
+                                                p.epp_nodes[wp[j]++] = (int32_t)v;
+                                                --u;
+                                            }
+                                            ++v;
                                         }
-                                        ++v;
                                     }
                                 }
                             }
                         }
-                        if (p.accumulate) {
+                        if (p.accumulate) {  // stage this lane's partial sums for entry gi
+                            redS[gi * RED_S_STRIDE + lane] = s;
+                            redC[gi * RED_C_STRIDE + lane] = c;
+                        }
+                    }
+                    if (p.accumulate) {
+                        // column sums: lane (e = lane/4, part = lane%4) adds 8 of the 32 staged values
+                        __syncwarp();
+                        const int er = lane >> 2, part = lane & 3;
+                        double s = 0.0;
+                        int c = 0;
+                        if (er < gm) {
 #pragma unroll
-                            for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
-                            c = __reduce_add_sync(FULL, c);
-                            if (lane == 0) {
-                                if (s != 0.0) atomicAdd(accS + base + ii, s);
-                                if (c != 0) atomicAdd(accC + base + ii, c);
+                            for (int k = 0; k < 8; ++k) {
+                                s += redS[er * RED_S_STRIDE + part + 4 * k];
+                                c += redC[er * RED_C_STRIDE + part + 4 * k];
                             }
                         }
+                        s += __shfl_xor_sync(FULL, s, 1);
+                        c += __shfl_xor_sync(FULL, c, 1);
+                        s += __shfl_xor_sync(FULL, s, 2);
+                        c += __shfl_xor_sync(FULL, c, 2);
+                        if (part == 0 && er < gm) {
+                            if (s != 0.0) atomicAdd(accS + base + g0 + er, s);
+                            if (c != 0) atomicAdd(accC + base + g0 + er, c);
+                        }
+                        __syncwarp();
                     }
                 }
                 __syncwarp();

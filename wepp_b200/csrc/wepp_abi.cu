@@ -177,7 +177,7 @@ int launch_place(wepp_handle* h, const PlaceParams& pp, int width) {
     using ET = typename Elem<K>::type;
     const int warps = 4;
     PlaceParams p = pp;
-    p.smem_per_warp = (int)((512 + (size_t)width * 32 * sizeof(ET) + 15) & ~(size_t)15);
+    p.smem_per_warp = (int)((SMEM_CODES + (size_t)width * 32 * sizeof(ET) + 15) & ~(size_t)15);
     const size_t smem = (size_t)p.smem_per_warp * warps;
     if (smem > h->smem_optin)
         return fail(WEPP_E_INVALID, "read window too wide for shared memory (" + std::to_string(width) + " bases)");
