@@ -1,0 +1,89 @@
+// int_pipes.cu — per-SMSP reciprocal throughput of the integer ops the placement kernel is made of.
+// One CTA per SM, W warps, each lane runs 8 independent dependency chains of one op.
+// Prints cycles per warp-instruction per SM sub-partition (SMSP) at 4, 8 and 16 warps/SM.
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#define ITER 4096
+
+template <int OP>
+__global__ void k(int* out, long long* cyc, int a0, int b0) {
+    int r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = a0 + j + threadIdx.x;
+    int b = b0, c = b0 * 3 + 1;
+    double d[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = (double)(j + threadIdx.x);
+    __syncthreads();
+    long long t0 = clock64();
+    for (int i = 0; i < ITER; ++i) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (OP == 0) r[j] = __dp4a(r[j], b, r[j]);                       // IDP.4A
+            if (OP == 1) asm volatile("mad.lo.s32 %0, %0, %1, %2;" : "+r"(r[j]) : "r"(b), "r"(c));   // IMAD
+            if (OP == 2) asm volatile("add.s32 %0, %0, %1;" : "+r"(r[j]) : "r"(b));                  // IADD3
+            if (OP == 3) asm volatile("min.s32 %0, %0, %1;" : "+r"(r[j]) : "r"(b + i));              // VIMNMX
+            if (OP == 4) asm volatile("{.reg .pred p; setp.lt.s32 p, %0, %1; selp.s32 %0, %1, %0, p;}" : "+r"(r[j]) : "r"(b + i));  // ISETP+SEL
+            if (OP == 5) asm volatile("prmt.b32 %0, %0, %1, %2;" : "+r"(r[j]) : "r"(b), "r"(c));     // PRMT
+            if (OP == 6) asm volatile("{.reg .pred p; setp.eq.s32 p, %1, %2; @p add.f64 %0, %0, %3;}" : "+d"(d[j]) : "r"(r[j]), "r"(b), "d"(1.5));  // ISETP + @DADD
+            if (OP == 7) asm volatile("add.f64 %0, %0, %1;" : "+d"(d[j]) : "d"(1.5));                // DADD
+            if (OP == 8) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(r[j]) : "r"(b), "r"(c));  // LOP3
+            if (OP == 9) asm volatile("shf.r.clamp.b32 %0, %0, %1, %2;" : "+r"(r[j]) : "r"(b), "r"(c)); // SHF
+            if (OP == 10) asm volatile("{.reg .pred p; setp.lt.s32 p, %0, %1; @p add.s32 %0, %0, %2;}" : "+r"(r[j]) : "r"(b + i), "r"(c)); // ISETP+@IADD
+            if (OP == 11) asm volatile("add.u16x2 %0, %0, %1;" : "+r"(r[j]) : "r"(b));               // packed add
+            if (OP == 12) asm volatile("min.s16x2 %0, %0, %1;" : "+r"(r[j]) : "r"(b + i));           // packed min
+            if (OP == 13) asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(r[j]) : "r"(b), "r"(c));  // IMAD as add (a*b const + r)
+            if (OP == 14) asm volatile("{.reg .pred p; setp.eq.s32 p, %0, %1; @p add.s32 %0, %0, %2;  min.s32 %0, %0, %1;}" : "+r"(r[j]) : "r"(b + i), "r"(c)); // setp+@add+min
+            if (OP == 15) r[j] += __popc(r[j] ^ b);                                                    // POPC (+LOP,+IADD)
+        }
+    }
+    long long t1 = clock64();
+    int acc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += r[j] + (int)d[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+template <int OP>
+void run(const char* name, int n_instr_per_iter) {
+    int* out; long long* cyc;
+    cudaMalloc(&out, 148 * 1024 * sizeof(int));
+    cudaMalloc(&cyc, 148 * sizeof(long long));
+    printf("%-26s", name);
+    for (int warps : {4, 8, 16, 32}) {
+        k<OP><<<148, warps * 32>>>(out, cyc, 1, 3);
+        cudaDeviceSynchronize();
+        long long h[148];
+        cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+        double avg = 0;
+        for (int i = 0; i < 148; ++i) avg += h[i];
+        avg /= 148;
+        // warp-instructions per SMSP = warps/4 * ITER * 8 * n_instr
+        double per = avg / ((warps / 4.0) * ITER * 8.0 * n_instr_per_iter);
+        printf("  w%-2d %6.2f", warps, per);
+    }
+    printf("   cyc/warp-instr/SMSP (%d instr per op)\n", n_instr_per_iter);
+    cudaFree(out); cudaFree(cyc);
+}
+
+int main() {
+    run<0>("IDP.4A", 1);
+    run<1>("IMAD", 1);
+    run<13>("IMAD (r += b*c)", 1);
+    run<2>("IADD", 1);
+    run<3>("min.s32 (VIMNMX)", 1);
+    run<4>("ISETP+SEL", 2);
+    run<10>("ISETP+@IADD", 2);
+    run<14>("ISETP+@IADD+MIN", 3);
+    run<5>("PRMT", 1);
+    run<8>("LOP3", 1);
+    run<9>("SHF", 1);
+    run<6>("ISETP+@DADD", 2);
+    run<7>("DADD", 1);
+    run<11>("add.u16x2", 1);
+    run<12>("min.s16x2", 1);
+    run<15>("LOP+POPC+IADD", 3);
+    return 0;
+}

@@ -63,7 +63,7 @@ struct PlaceParams {
     unsigned long long* epp_total;
     int64_t* epp_off;  // caller order, -1 = not cached
     int32_t* epp_nodes;
-    int32_t smem_per_warp;
+    int32_t smem_per_warp;  // unused (layout is compile-time); kept for ABI stability of the struct
 };
 
 template <int K> struct Elem;
@@ -79,14 +79,51 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     return r;
 }
 
-// Per-warp shared-memory layout of place_kernel (bytes from the warp's base).
+// min / multiplicity update for one read at one non-empty segment (initial_filter.cpp:89-99):
+//   run < best -> best = run, cnt = ucnt ;  run == best -> cnt += ucnt.  Five predicated ops.
+__device__ __forceinline__ void min_count_update(int& best, int& cnt, int run, int ucnt) {
+    asm("{\n\t"
+        ".reg .pred lt, le;\n\t"
+        "setp.lt.s32 lt, %2, %0;\n\t"
+        "setp.le.s32 le, %2, %0;\n\t"
+        "@lt mov.s32 %1, 0;\n\t"
+        "@le add.s32 %1, %1, %3;\n\t"
+        "min.s32 %0, %0, %2;\n\t"
+        "}"
+        : "+r"(best), "+r"(cnt)
+        : "r"(run), "r"(ucnt));
+}
+
+// weight / degree accumulation for one read at one segment: if (run == best) { s += w; c += d; hit |= bit; }
+__device__ __forceinline__ void eq_accumulate(double& s, int& c, uint32_t& hit, int run, int best, double w, int d,
+                                              uint32_t bit) {
+    asm("{\n\t"
+        ".reg .pred eq;\n\t"
+        "setp.eq.s32 eq, %3, %4;\n\t"
+        "@eq add.f64 %0, %0, %5;\n\t"
+        "@eq add.s32 %1, %1, %6;\n\t"
+        "@eq or.b32 %2, %2, %7;\n\t"
+        "}"
+        : "+d"(s), "+r"(c), "+r"(hit)
+        : "r"(run), "r"(best), "d"(w), "r"(d), "r"(bit));
+}
+
+// Shared-memory layout of place_kernel (one CTA = one tile of 32*K reads, PLACE_WARPS warps).
+//   per warp : 32 staged entries (512 B) + pass-2 reduction staging (double[8][36] + int[8][33])
+//   per CTA  : the read-allele code table [width][32] (K nibbles per lane element)
+// The per-warp staging areas double as the exchange buffer for the chunk summaries between
+// pass 1 and pass 2.
+constexpr int PLACE_WARPS = 4;
 constexpr int RED_G = 8;              // entries reduced together in pass 2
 constexpr int RED_S_STRIDE = 36;      // doubles per staged row: 32 lanes + pad (conflict-free column sums)
 constexpr int RED_C_STRIDE = 33;      // ints per staged row
 constexpr int SMEM_EBUF = 0;                                        // 32 staged entries (512 B)
 constexpr int SMEM_REDS = 512;                                      // double[RED_G][RED_S_STRIDE]
 constexpr int SMEM_REDC = SMEM_REDS + RED_G * RED_S_STRIDE * 8;     // int[RED_G][RED_C_STRIDE]
-constexpr int SMEM_CODES = (SMEM_REDC + RED_G * RED_C_STRIDE * 4 + 15) & ~15;
+constexpr int SMEM_WARP = (SMEM_REDC + RED_G * RED_C_STRIDE * 4 + 15) & ~15;   // bytes per warp
+constexpr int SMEM_CTRL = PLACE_WARPS * SMEM_WARP;                  // int tile id (16 B)
+constexpr int SMEM_WPB = SMEM_CTRL + 16;                            // u64[256] EPP write bases
+constexpr int SMEM_CODES = SMEM_WPB + 256 * 8;                      // code table
 
 __device__ __forceinline__ uint4 ld_entry(const Entry* p) {
     return __ldg(reinterpret_cast<const uint4*>(p));
@@ -144,86 +181,120 @@ __global__ void finalize_lists_kernel(Entry* __restrict__ lists, const ListDesc*
 }
 
 // ---------------------------------------------------------------------------------------------
-// The placement kernel.  Persistent warps; each warp pulls tiles from a global counter.
+// Out-of-line (rare) EPP list emission: nodes of one argmin segment that are not mapped.
+__device__ __noinline__ void emit_segment(int32_t* __restrict__ out, unsigned long long& wp, uint32_t v, uint32_t u,
+                                          const uint8_t* __restrict__ mapped) {
+    while (u) {
+        if (!mapped || !mapped[v]) {
+            out[wp++] = (int32_t)v;
+            --u;
+        }
+        ++v;
+    }
+}
+
+// The placement kernel.  Persistent CTAs; each CTA pulls tiles (32*K reads of one window bucket)
+// from a global counter.  The CTA's PLACE_WARPS warps share the tile's allele-code table and
+// each scans one contiguous chunk of the bucket's Euler list for ALL reads of the tile (lane =
+// K reads), a two-level Euler-tour scan:
+//   pass 1  per chunk: sum of deltas, min prefix, node count at the min  -> shared memory
+//   combine every warp folds the chunk summaries: global min, multiplicity, its own start offset
+//   pass 2  per chunk: segments attaining the min -> weight/degree sums into the segment
+//           accumulators (staged through shared memory, one atomic per segment per tile) and
+//           explicit EPP lists for reads under the cache cap.
 template <int K>
-__global__ void __launch_bounds__(128) place_kernel(const PlaceParams p) {
+__global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlaceParams p) {
     using ET = typename Elem<K>::type;
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* wbase = smem + (size_t)warp * p.smem_per_warp;
-    uint4* ebuf = reinterpret_cast<uint4*>(wbase);   // 32 staged entries
+    unsigned char* wbase = smem + (size_t)warp * SMEM_WARP;
+    uint4* ebuf = reinterpret_cast<uint4*>(wbase + SMEM_EBUF);
     double* redS = reinterpret_cast<double*>(wbase + SMEM_REDS);
     int* redC = reinterpret_cast<int*>(wbase + SMEM_REDC);
-    ET* codes = reinterpret_cast<ET*>(wbase + SMEM_CODES);  // [width][32] read-allele codes, K nibbles per lane
+    int* xch = reinterpret_cast<int*>(smem);  // exchange [PLACE_WARPS][3][32*K] ints, aliases the staging areas
+    int* ctrl = reinterpret_cast<int*>(smem + SMEM_CTRL);
+    unsigned long long* wpb = reinterpret_cast<unsigned long long*>(smem + SMEM_WPB);
+    ET* codes = reinterpret_cast<ET*>(smem + SMEM_CODES);
+    const ET* cl = codes + lane;  // this lane's column of the code table
     const unsigned FULL = 0xFFFFFFFFu;
+    constexpr int T = 32 * K;
+    static_assert(PLACE_WARPS * 3 * T * 4 <= PLACE_WARPS * SMEM_WARP, "exchange buffer must fit the staging areas");
 
     for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(p.tile_counter, 1);
-        t = __shfl_sync(FULL, t, 0);
+        __syncthreads();  // previous tile fully done (code table, exchange buffer)
+        if (threadIdx.x == 0) ctrl[0] = atomicAdd(p.tile_counter, 1);
+        __syncthreads();
+        const int t = ctrl[0];
         if (t >= p.n_tiles) break;
         const TileDesc td = p.tiles[t];
         const BucketDesc bd = p.buckets[td.bucket];
         const ListDesc ld = p.list_desc[bd.list];
         const Entry* ent = p.lists + ld.off;
         const int n = ld.n;
+        // this warp's chunk of the list (multiple of 32 entries)
+        const int cs = (((n + PLACE_WARPS - 1) / PLACE_WARPS) + 31) & ~31;
+        const int c0 = min(n, warp * cs), c1 = min(n, c0 + cs);
 
         // ---- read tile -> shared allele-code table --------------------------------------------
-        int s_rel[K], e_rel[K], run0[K];
+        int run0[K];
         int64_t rid[K];
+        {
+            int s_rel[K], e_rel[K];
 #pragma unroll
-        for (int j = 0; j < K; ++j) {
-            const int ti = lane * K + j;
-            const bool valid = ti < td.count;
-            rid[j] = valid ? td.first + ti : -1;
-            s_rel[j] = valid ? p.start[rid[j]] - ld.b0 : 1;
-            e_rel[j] = valid ? p.end[rid[j]] - ld.b0 : 0;
-            run0[j] = 0;
-        }
-        __syncwarp();
-        for (int pos = 0; pos < ld.width; ++pos) {
-            uint32_t w = 0;
+            for (int j = 0; j < K; ++j) {
+                const int ti = lane * K + j;
+                const bool valid = ti < td.count;
+                rid[j] = valid ? td.first + ti : -1;
+                s_rel[j] = valid ? p.start[rid[j]] - ld.b0 : 1;
+                e_rel[j] = valid ? p.end[rid[j]] - ld.b0 : 0;
+                run0[j] = 0;
+            }
+            for (int pos = warp; pos < ld.width; pos += PLACE_WARPS) {
+                uint32_t w = 0;
 #pragma unroll
-            for (int j = 0; j < K; ++j) w |= ((pos >= s_rel[j] && pos <= e_rel[j]) ? 0u : 5u) << (4 * j);
-            codes[pos * 32 + lane] = (ET)w;
+                for (int j = 0; j < K; ++j) w |= ((pos >= s_rel[j] && pos <= e_rel[j]) ? 0u : 5u) << (4 * j);
+                codes[pos * 32 + lane] = (ET)w;
+            }
         }
-        __syncwarp();
+        __syncthreads();
 #pragma unroll
         for (int j = 0; j < K; ++j) {
             if (rid[j] >= 0) {
                 const int64_t a = p.rm_off[rid[j]], b = p.rm_off[rid[j] + 1];
                 for (int64_t k = a; k < b; ++k) {
-                    const int pr = p.rm_pos[k] - ld.b0;
                     const uint32_t c = p.rm_code[k];
-                    uint32_t w = codes[pr * 32 + lane];
-                    w = (w & ~(0xFu << (4 * j))) | (c << (4 * j));
-                    codes[pr * 32 + lane] = (ET)w;
+                    if (warp == 0) {  // one owner per table column: no races
+                        const int pr = p.rm_pos[k] - ld.b0;
+                        uint32_t w = codes[pr * 32 + lane];
+                        w = (w & ~(0xFu << (4 * j))) | (c << (4 * j));
+                        codes[pr * 32 + lane] = (ET)w;
+                    }
                     run0[j] += (c <= 4u);  // seed set: non-N mutations (initial_filter.cpp:118-123)
                 }
             }
         }
-        __syncwarp();
+        __syncthreads();
 
-        // ---- pass 1: prefix sum of signed deltas, running min and its multiplicity --------------
+        // ---- pass 1: chunk-relative prefix sum of signed deltas, min prefix and its node count ----
         int run[K], best[K], cnt[K];
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-            run[j] = run0[j];
-            best[j] = 0x7FFFFFFF;
+            run[j] = 0;
+            best[j] = 0x3FFFFFFF;
             cnt[j] = 0;
         }
         {
             uint4 nxt = make_uint4(0, 0, 0, 0);
-            if (lane < n) nxt = ld_entry(ent + lane);
-            for (int base = 0; base < n; base += 32) {
+            if (c0 + lane < c1) nxt = ld_entry(ent + c0 + lane);
+            for (int base = c0; base < c1; base += 32) {
                 ebuf[lane] = nxt;
                 __syncwarp();
-                if (base + 32 + lane < n) nxt = ld_entry(ent + base + 32 + lane);
-                const int m = min(32, n - base);
+                if (base + 32 + lane < c1) nxt = ld_entry(ent + base + 32 + lane);
+                const int m = min(32, c1 - base);
 #pragma unroll 4
                 for (int ii = 0; ii < m; ++ii) {
                     const uint4 e = ebuf[ii];
-                    const uint32_t w = codes[(e.w >> 16) * 32 + lane];
+                    const uint32_t w = cl[(e.w >> 16) * 32];
                     const uint32_t d0 = prmt(e.z, e.w, w);
                     uint32_t d1 = 0;
                     if (K == 8) d1 = prmt(e.z, e.w, w >> 16);
@@ -233,21 +304,52 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceParams p) {
                     if (e.x & SEG_FLAG) {
                         const int ucnt = (int)e.y;
 #pragma unroll
-                        for (int j = 0; j < K; ++j) {
-                            if (run[j] < best[j]) {
-                                best[j] = run[j];
-                                cnt[j] = ucnt;
-                            } else if (run[j] == best[j]) {
-                                cnt[j] += ucnt;
-                            }
-                        }
+                        for (int j = 0; j < K; ++j) min_count_update(best[j], cnt[j], run[j], ucnt);
                     }
                 }
                 __syncwarp();
             }
         }
+        // ---- exchange chunk summaries, fold them ------------------------------------------------
+        __syncthreads();  // all warps are done with their staging areas
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            xch[(warp * 3 + 0) * T + j * 32 + lane] = run[j];
+            xch[(warp * 3 + 1) * T + j * 32 + lane] = best[j];
+            xch[(warp * 3 + 2) * T + j * 32 + lane] = cnt[j];
+        }
+        __syncthreads();
+        int epp_before[K];
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+            int off = run0[j], my_off = 0, gb = 0x3FFFFFFF;
+#pragma unroll
+            for (int w = 0; w < PLACE_WARPS; ++w) {
+                if (w == warp) my_off = off;
+                const int b = xch[(w * 3 + 1) * T + j * 32 + lane];
+                if (b != 0x3FFFFFFF) gb = min(gb, off + b);
+                off += xch[(w * 3 + 0) * T + j * 32 + lane];
+            }
+            int gc = 0, before = 0;
+            off = run0[j];
+#pragma unroll
+            for (int w = 0; w < PLACE_WARPS; ++w) {
+                const int b = xch[(w * 3 + 1) * T + j * 32 + lane];
+                const int c = xch[(w * 3 + 2) * T + j * 32 + lane];
+                if (b != 0x3FFFFFFF && off + b == gb) {
+                    gc += c;
+                    if (w < warp) before += c;
+                }
+                off += xch[(w * 3 + 0) * T + j * 32 + lane];
+            }
+            run[j] = my_off;      // pass 2 starts from this warp's absolute offset
+            best[j] = gb;
+            cnt[j] = gc;
+            epp_before[j] = before;
+        }
+        __syncthreads();  // exchange buffer consumed; staging areas are free again
 
-        // ---- per-read results -------------------------------------------------------------------
+        // ---- per-read results (warp 0 writes; EPP space is allocated by warp 0) ------------------
         double wgt[K];
         int deg[K];
         unsigned long long wp[K];
@@ -258,55 +360,68 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceParams p) {
             deg[j] = 0;
             wp[j] = 0;
             if (rid[j] >= 0) {
-                const int64_t orig = p.perm[rid[j]];
-                p.max_pars[orig] = best[j];
-                p.mult[orig] = cnt[j];
                 const int d = p.degree[rid[j]];
                 if (cnt[j] > 0) {
                     // node_score, initial_filter.hpp:54-57
                     wgt[j] = (double)d / ((double)(1 + best[j]) * (double)cnt[j]);
                     deg[j] = d;
                 }
-                long long off = -1;
-                if (p.epp_off) {
-                    if (cnt[j] > 0 && cnt[j] <= p.epp_cap) {
-                        const unsigned long long o = atomicAdd(p.epp_total, (unsigned long long)cnt[j]);
-                        if (o + (unsigned long long)cnt[j] <= p.epp_capacity) {
-                            off = (long long)o;
-                            wp[j] = o;
-                            small_mask |= 1u << j;
+                if (warp == 0) {
+                    const int64_t orig = p.perm[rid[j]];
+                    p.max_pars[orig] = best[j];
+                    p.mult[orig] = cnt[j];
+                    if (p.epp_off) {
+                        long long off = -1;
+                        unsigned long long base = ~0ull;
+                        if (cnt[j] > 0 && cnt[j] <= p.epp_cap) {
+                            const unsigned long long o = atomicAdd(p.epp_total, (unsigned long long)cnt[j]);
+                            if (o + (unsigned long long)cnt[j] <= p.epp_capacity) {
+                                off = (long long)o;
+                                base = o;
+                            }
+                        } else if (cnt[j] == 0) {
+                            off = 0;  // empty but known
                         }
-                    } else if (cnt[j] == 0) {
-                        off = 0;  // empty but known
+                        p.epp_off[orig] = off;
+                        wpb[j * 32 + lane] = base;
                     }
-                    p.epp_off[orig] = off;
+                }
+            } else if (warp == 0 && p.epp_off) {
+                wpb[j * 32 + lane] = ~0ull;
+            }
+        }
+        if (p.epp_off) {
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < K; ++j) {
+                const unsigned long long base = wpb[j * 32 + lane];
+                if (base != ~0ull) {
+                    wp[j] = base + (unsigned long long)epp_before[j];
+                    small_mask |= 1u << j;
                 }
             }
         }
-        const bool need_pass2 = p.accumulate || __any_sync(FULL, small_mask != 0);
+        const bool need_pass2 = p.accumulate || __syncthreads_or(small_mask != 0);
         if (!need_pass2) continue;
 
         // ---- pass 2: which segments attain the min -> weights into the segment accumulators,
         //      EPP node lists for reads under the cache cap ---------------------------------------
-#pragma unroll
-        for (int j = 0; j < K; ++j) run[j] = run0[j];
         double* accS = p.accS + bd.acc_off;
         int32_t* accC = p.accC + bd.acc_off;
         {
             uint4 nxt = make_uint4(0, 0, 0, 0);
-            if (lane < n) nxt = ld_entry(ent + lane);
-            for (int base = 0; base < n; base += 32) {
+            if (c0 + lane < c1) nxt = ld_entry(ent + c0 + lane);
+            for (int base = c0; base < c1; base += 32) {
                 ebuf[lane] = nxt;
                 __syncwarp();
-                if (base + 32 + lane < n) nxt = ld_entry(ent + base + 32 + lane);
-                const int m = min(32, n - base);
+                if (base + 32 + lane < c1) nxt = ld_entry(ent + base + 32 + lane);
+                const int m = min(32, c1 - base);
                 for (int g0 = 0; g0 < m; g0 += RED_G) {
                     const int gm = min(RED_G, m - g0);
 #pragma unroll 2
                     for (int gi = 0; gi < gm; ++gi) {
-                        const int ii = g0 + gi;
-                        const uint4 e = ebuf[ii];
-                        const uint32_t w = codes[(e.w >> 16) * 32 + lane];
+                        const uint4 e = ebuf[g0 + gi];
+                        const uint32_t w = cl[(e.w >> 16) * 32];
                         const uint32_t d0 = prmt(e.z, e.w, w);
                         uint32_t d1 = 0;
                         if (K == 8) d1 = prmt(e.z, e.w, w >> 16);
@@ -318,28 +433,12 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceParams p) {
                         if (e.x & SEG_FLAG) {
                             uint32_t hit = 0;
 #pragma unroll
-                            for (int j = 0; j < K; ++j) {
-                                const bool eq = run[j] == best[j];
-                                s += eq ? wgt[j] : 0.0;
-                                c += eq ? deg[j] : 0;
-                                hit |= eq ? (1u << j) : 0u;
-                            }
-                            hit &= small_mask;
+                            for (int j = 0; j < K; ++j)
+                                eq_accumulate(s, c, hit, run[j], best[j], wgt[j], deg[j], small_mask & (1u << j));
                             if (hit) {  // rare: explicit EPP lists (sorted: the list is in preorder)
 #pragma unroll
-                                for (int j = 0; j < K; ++j) {
-                                    if (hit & (1u << j)) {
-                                        uint32_t v = e.x & IDX_MASK;
-                                        uint32_t u = e.y;
-                                        while (u) {
-                                            if (!p.mapped || !p.mapped[v]) {
-                                                p.epp_nodes[wp[j]++] = (int32_t)v;
-                                                --u;
-                                            }
-                                            ++v;
-                                        }
-                                    }
-                                }
+                                for (int j = 0; j < K; ++j)
+                                    if (hit & (1u << j)) emit_segment(p.epp_nodes, wp[j], e.x & IDX_MASK, e.y, p.mapped);
                             }
                         }
                         if (p.accumulate) {  // stage this lane's partial sums for entry gi
@@ -371,7 +470,6 @@ __global__ void __launch_bounds__(128) place_kernel(const PlaceParams p) {
                         __syncwarp();
                     }
                 }
-                __syncwarp();
             }
         }
     }

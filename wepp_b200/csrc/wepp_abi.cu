@@ -175,19 +175,17 @@ int finalize_plan(wepp_handle* h, wepp_handle::DevPlan& dp) {
 template <int K>
 int launch_place(wepp_handle* h, const PlaceParams& pp, int width) {
     using ET = typename Elem<K>::type;
-    const int warps = 4;
     PlaceParams p = pp;
-    p.smem_per_warp = (int)((SMEM_CODES + (size_t)width * 32 * sizeof(ET) + 15) & ~(size_t)15);
-    const size_t smem = (size_t)p.smem_per_warp * warps;
+    p.smem_per_warp = SMEM_WARP;
+    const size_t smem = (size_t)SMEM_CODES + (((size_t)width * 32 * sizeof(ET) + 15) & ~(size_t)15);
     if (smem > h->smem_optin)
         return fail(WEPP_E_INVALID, "read window too wide for shared memory (" + std::to_string(width) + " bases)");
     CU(cudaFuncSetAttribute(place_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_kernel<K>, warps * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_kernel<K>, PLACE_WARPS * 32, smem));
     per_sm = std::max(per_sm, 1);
-    const int64_t want = (p.n_tiles + warps - 1) / warps;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)per_sm * h->n_sms));
-    place_kernel<K><<<grid, warps * 32, smem, h->stream>>>(p);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p.n_tiles, (int64_t)per_sm * h->n_sms));
+    place_kernel<K><<<grid, PLACE_WARPS * 32, smem, h->stream>>>(p);
     CU(cudaGetLastError());
     return WEPP_OK;
 }
