@@ -144,6 +144,27 @@ typedef struct wepp_stats {
 } wepp_stats;
 int wepp_get_stats(wepp_handle* h, wepp_stats* out);
 
+/* The arena builder (host side; no GPU needed).  Replaces the reference's arena constructor,
+ * src/WEPP/arena.hpp:56-79: masks read mutations at the masked sites (:62-72), derives the covered
+ * sites (site_read_map, :157-175), condenses the MAT to nodes that mutate a covered site
+ * (create_condensed_tree, src/WEPP/util.cpp:79-133) and flattens it in preorder (arena::from_mat,
+ * src/WEPP/arena.cpp:3-56).  Input tree: node 0 is the root, parent[v] < v, a node's children are
+ * taken in index order (the order the MAT loader created them), mutations sorted by position.
+ * Outputs (sizes from wepp_arena_dims): per arena node its parent, source MAT node, leaf_count,
+ * mutation CSR, and the CSR of MAT nodes folded into it (first = the source;
+ * condensed_node_mappings); and the masked reads' mutation CSR.  */
+typedef struct wepp_arena wepp_arena;
+int  wepp_arena_build(int32_t n_mat_nodes, const int32_t* parent, const int64_t* mut_off, const int32_t* mut_pos,
+                      const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size, int32_t n_masked,
+                      const int32_t* masked, int64_t n_reads, const int32_t* start, const int32_t* end,
+                      const int64_t* rm_off, const int32_t* rm_pos, const uint8_t* rm_nuc, wepp_arena** out);
+void wepp_arena_free(wepp_arena* a);
+int  wepp_arena_dims(const wepp_arena* a, int32_t* n_nodes, int64_t* n_muts, int64_t* n_read_muts, int64_t* n_mapped);
+int  wepp_arena_get(const wepp_arena* a, int32_t* parent, int32_t* source, int32_t* leaf_count, int64_t* mut_off,
+                    int32_t* mut_pos, uint8_t* mut_ref, uint8_t* mut_nuc, int64_t* map_off, int32_t* map_nodes);
+int  wepp_arena_get_reads(const wepp_arena* a, int64_t* rm_off, int32_t* rm_pos, uint8_t* rm_nuc);
+int  wepp_set_arena_from(wepp_handle* h, const wepp_arena* a);
+
 /* Host-only introspection (no GPU needed; used by the CPU test-suite): the Euler-tour event
  * stripes built from an arena (4 x uint32 per entry: preorder idx, position, signed-delta bytes
  * for read allele ref/A/C/G, delta byte for T) and the read bucketing plan.  Both return a

@@ -217,7 +217,14 @@ class concurrent_hash_map {
     };
     class iterator {
       public:
+        using iterator_category = std::forward_iterator_tag;
+        using value_type = std::pair<const K, V>;
+        using difference_type = std::ptrdiff_t;
+        using pointer = value_type*;
+        using reference = value_type&;
+        iterator() = default;
         explicit iterator(typename Map::iterator it) : it_(it) {}
+        iterator operator++(int) { iterator t = *this; ++it_; return t; }
         value_type& operator*() const { return it_->second->kv; }
         value_type* operator->() const { return &it_->second->kv; }
         iterator& operator++() { ++it_; return *this; }
@@ -233,8 +240,7 @@ class concurrent_hash_map {
 
     bool insert(const_accessor& a, const K& k) { return insert_impl(a, k, V()); }
     bool insert(const_accessor& a, const value_type& kv) { return insert_impl(a, kv.first, kv.second); }
-    template <typename P>
-    bool insert(const_accessor& a, P&& kv) { return insert_impl(a, kv.first, kv.second); }
+    bool insert(const_accessor& a, const std::pair<K, V>& kv) { return insert_impl(a, kv.first, kv.second); }
     bool insert(const value_type& kv) { const_accessor a; return insert_impl(a, kv.first, kv.second); }
     bool find(const_accessor& a, const K& k) {
         a.release();

@@ -1,0 +1,32 @@
+"""Live pin: where oracle/_ref/libwepp_ref.so exists (built from /root/reference by `make -C oracle
+ref`; it travels to the GPU box), the oracle and the arena builder are checked against the
+reference's own object code on cases that are NOT in the committed fixtures."""
+import numpy as np
+import pytest
+
+from oracle import ref
+
+pytestmark = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (reference tree not mounted)")
+
+
+def _live(seed):
+    import oracle
+    from tests import cases
+    from wepp_b200.placement import build_arena
+    tree, reads, _ = cases.tiny_case(seed) if seed < 1000 else (*cases.small_case(seed=seed, n_nodes=1500, n_reads=250), None)
+    rng = np.random.default_rng(seed)
+    masked = np.sort(rng.choice(np.arange(1, tree.genome_size + 1), 3, replace=False)).astype(np.int32)
+    s = ref.Session(tree, reads, masked=masked, threads=2)
+    a = s.arena()
+    arena, mreads, info = build_arena(tree, reads, masked)
+    ok = all(np.array_equal(a[k], info[k]) for k in ("parent", "source", "leaf_count", "mut_off", "mut_pos", "mut_nuc"))
+    r = s.cartesian_map()
+    o = oracle.cartesian_map(arena, mreads, None, n_threads=2, epp_cap=2048)
+    ok = ok and all(np.array_equal(r[k], o[k]) for k in ("max_parsimony", "multiplicity", "counts", "epp_off", "epp_nodes"))
+    ok = ok and np.allclose(r["score"], o["score"], rtol=1e-12, atol=0)
+    return bool(ok)
+
+
+@pytest.mark.parametrize("seed", [21, 22, 23, 1021])
+def test_oracle_and_arena_builder_match_live_reference(seed):
+    assert ref.run_case("tests.test_ref_live", "_live", seed)

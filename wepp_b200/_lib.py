@@ -51,6 +51,12 @@ SIGNATURES = {
     "wepp_rescore": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, C.c_int64]),
     "wepp_device_buffer": (C.c_int, [VP, C.c_int32, C.POINTER(VP), C.POINTER(C.c_int64)]),
     "wepp_get_stats": (C.c_int, [VP, C.POINTER(WeppStats)]),
+    "wepp_arena_build": (C.c_int, [C.c_int32, VP, VP, VP, VP, VP, C.c_int32, C.c_int32, VP, C.c_int64, VP, VP, VP, VP, VP, C.POINTER(VP)]),
+    "wepp_arena_free": (None, [VP]),
+    "wepp_arena_dims": (C.c_int, [VP, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "wepp_arena_get": (C.c_int, [VP] * 10),
+    "wepp_arena_get_reads": (C.c_int, [VP] * 4),
+    "wepp_set_arena_from": (C.c_int, [VP, VP]),
     "wepp_host_euler_stripes": (C.c_int64, [C.c_int32, VP, VP, VP, VP, VP, C.c_int32, C.c_int32, VP, C.c_int64, VP, C.c_int32]),
     "wepp_host_read_plan": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [VP] * 10 + [C.POINTER(C.c_int32)]),
 }

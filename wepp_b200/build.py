@@ -40,7 +40,8 @@ def build_cuda(force: bool = False) -> str:
     if not force and _newer(LIB, srcs):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    _run([nvcc, *NVCC_FLAGS, os.path.join(CSRC, "wepp_abi.cu"), os.path.join(CSRC, "host_prep.cpp"), "-o", LIB])
+    _run([nvcc, *NVCC_FLAGS, os.path.join(CSRC, "wepp_abi.cu"), os.path.join(CSRC, "host_prep.cpp"),
+          os.path.join(CSRC, "host_arena.cpp"), "-o", LIB])
     return LIB
 
 

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../include/wepp_b200.h"
+#include "host_arena.h"
 #include "host_prep.h"
 #include "kernels.cuh"
 #include "rescore.cuh"
@@ -325,6 +326,11 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
 
 }  // namespace
 
+template <typename T>
+static void copy_out(T* dst, const std::vector<T>& v) {
+    if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(T));
+}
+
 extern "C" {
 
 const char* wepp_last_error(void) { return g_err.c_str(); }
@@ -601,6 +607,60 @@ int wepp_get_stats(wepp_handle* h, wepp_stats* out) {
     }
     *out = h->stats;
     return WEPP_OK;
+}
+
+// ---- arena builder (host) ---------------------------------------------------------------------
+struct wepp_arena {
+    wepp::ArenaHost a;
+};
+
+int wepp_arena_build(int32_t n_mat_nodes, const int32_t* parent, const int64_t* mut_off, const int32_t* mut_pos,
+                     const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size, int32_t n_masked,
+                     const int32_t* masked, int64_t n_reads, const int32_t* start, const int32_t* end,
+                     const int64_t* rm_off, const int32_t* rm_pos, const uint8_t* rm_nuc, wepp_arena** out) {
+    if (!out || !parent || !mut_off || !rm_off) return fail(WEPP_E_INVALID, "NULL argument");
+    wepp_arena* a = new wepp_arena();
+    std::string err = build_arena(n_mat_nodes, parent, mut_off, mut_pos, mut_ref, mut_nuc, genome_size, n_masked, masked,
+                                  n_reads, start, end, rm_off, rm_pos, rm_nuc, a->a);
+    if (!err.empty()) {
+        delete a;
+        return fail(WEPP_E_INVALID, err);
+    }
+    *out = a;
+    return WEPP_OK;
+}
+
+void wepp_arena_free(wepp_arena* a) { delete a; }
+
+int wepp_arena_dims(const wepp_arena* a, int32_t* n_nodes, int64_t* n_muts, int64_t* n_read_muts, int64_t* n_mapped) {
+    if (!a) return fail(WEPP_E_INVALID, "arena is NULL");
+    if (n_nodes) *n_nodes = (int32_t)a->a.parent.size();
+    if (n_muts) *n_muts = (int64_t)a->a.mut_pos.size();
+    if (n_read_muts) *n_read_muts = (int64_t)a->a.rm_pos.size();
+    if (n_mapped) *n_mapped = (int64_t)a->a.map_nodes.size();
+    return WEPP_OK;
+}
+
+int wepp_arena_get(const wepp_arena* a, int32_t* parent, int32_t* source, int32_t* leaf_count, int64_t* mut_off,
+                   int32_t* mut_pos, uint8_t* mut_ref, uint8_t* mut_nuc, int64_t* map_off, int32_t* map_nodes) {
+    if (!a) return fail(WEPP_E_INVALID, "arena is NULL");
+    copy_out(parent, a->a.parent); copy_out(source, a->a.source); copy_out(leaf_count, a->a.leaf_count);
+    copy_out(mut_off, a->a.mut_off); copy_out(mut_pos, a->a.mut_pos); copy_out(mut_ref, a->a.mut_ref);
+    copy_out(mut_nuc, a->a.mut_nuc); copy_out(map_off, a->a.map_off); copy_out(map_nodes, a->a.map_nodes);
+    return WEPP_OK;
+}
+
+int wepp_arena_get_reads(const wepp_arena* a, int64_t* rm_off, int32_t* rm_pos, uint8_t* rm_nuc) {
+    if (!a) return fail(WEPP_E_INVALID, "arena is NULL");
+    copy_out(rm_off, a->a.rm_off); copy_out(rm_pos, a->a.rm_pos); copy_out(rm_nuc, a->a.rm_nuc);
+    return WEPP_OK;
+}
+
+int wepp_set_arena_from(wepp_handle* h, const wepp_arena* a) {
+    if (!h || !a) return fail(WEPP_E_INVALID, "NULL argument");
+    const wepp::ArenaHost& x = a->a;
+    return wepp_set_arena(h, (int32_t)x.parent.size(), x.parent.data(), x.mut_off.data(), x.mut_pos.data(),
+                          x.mut_ref.data(), x.mut_nuc.data(), x.genome_size);
 }
 
 // Host-only view of the Euler stripes (no GPU needed): used by the CPU test-suite to check the

@@ -177,3 +177,37 @@ class WeppFilter:
             prop = self.mapped_read_counts / true_counts[None, :].astype(np.float64)
         self.dist_divergence = (prop > READ_DIST_FACTOR_THRESHOLD).sum(axis=1) / max(active, 1)
         return self
+
+
+def build_arena(tree, reads, masked=None):
+    """Host-side arena construction (wepp_arena_build): returns (Arena, Reads, info) where Arena is
+    the flattened condensed tree, Reads the masked reads and info carries `source`, `leaf_count`
+    and the folded-node CSR (`map_off`, `map_nodes`)."""
+    from .synth import Arena, Reads
+    lib = _lib.load()
+    a = (_c(tree.parent, np.int32), _c(tree.mut_off, np.int64), _c(tree.mut_pos, np.int32), _c(tree.mut_ref, np.uint8),
+         _c(tree.mut_nuc, np.uint8))
+    m = _c(masked if masked is not None else [], np.int32)
+    r = (_c(reads.start, np.int32), _c(reads.end, np.int32), _c(reads.rm_off, np.int64), _c(reads.rm_pos, np.int32),
+         _c(reads.rm_nuc, np.uint8))
+    h = C.c_void_p()
+    check(lib.wepp_arena_build(a[0].shape[0], *[ptr(x) for x in a], int(tree.genome_size), m.shape[0], ptr(m),
+                               r[0].shape[0], *[ptr(x) for x in r], C.byref(h)))
+    try:
+        n, nm, nrm, nmap = C.c_int32(), C.c_int64(), C.c_int64(), C.c_int64()
+        check(lib.wepp_arena_dims(h, C.byref(n), C.byref(nm), C.byref(nrm), C.byref(nmap)))
+        n, nm, nrm, nmap = n.value, nm.value, nrm.value, nmap.value
+        out = {"parent": np.zeros(n, np.int32), "source": np.zeros(n, np.int32), "leaf_count": np.zeros(n, np.int32),
+               "mut_off": np.zeros(n + 1, np.int64), "mut_pos": np.zeros(nm, np.int32), "mut_ref": np.zeros(nm, np.uint8),
+               "mut_nuc": np.zeros(nm, np.uint8), "map_off": np.zeros(n + 1, np.int64), "map_nodes": np.zeros(nmap, np.int32)}
+        check(lib.wepp_arena_get(h, *[ptr(out[k]) for k in ("parent", "source", "leaf_count", "mut_off", "mut_pos",
+                                                           "mut_ref", "mut_nuc", "map_off", "map_nodes")]))
+        ro, rp, rn = np.zeros(reads.n_reads + 1, np.int64), np.zeros(nrm, np.int32), np.zeros(nrm, np.uint8)
+        check(lib.wepp_arena_get_reads(h, ptr(ro), ptr(rp), ptr(rn)))
+    finally:
+        lib.wepp_arena_free(h)
+    arena = Arena(int(tree.genome_size), tree.ref_codes, out["parent"], out["mut_off"], out["mut_pos"], out["mut_ref"],
+                  out["mut_nuc"])
+    mreads = Reads(np.asarray(reads.start, np.int32), np.asarray(reads.end, np.int32), np.asarray(reads.degree, np.int32),
+                   ro, rp, rn, dict(getattr(reads, "meta", {})))
+    return arena, mreads, out
