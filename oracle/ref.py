@@ -64,6 +64,21 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(VP)
 
 
+class _quiet:
+    """Silence the reference's own std::cout progress lines (fd 1) during a call."""
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        self._null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(self._null, 1)
+
+    def __exit__(self, *exc):
+        load().ref_flush() if hasattr(load(), "ref_flush") else None
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+        os.close(self._null)
+
+
 class Session:
     """One reference `arena` built from an (uncondensed) MAT-level tree and a read set."""
 
@@ -130,8 +145,9 @@ class Session:
         cap = int(min(r * 2048 + 1, 1 << 28)) if want_epp else 0
         en = np.zeros(max(cap, 1), np.int32) if want_epp else None
         m = None if mapped is None else _c(mapped, np.uint8)
-        ms = self.lib.ref_cartesian_map(C.c_int64(n_sel), _p(m), _p(mp), _p(mu), _p(sc), _p(ct), _p(dd), _p(eo), _p(en),
-                                        C.c_int64(cap))
+        with _quiet():
+            ms = self.lib.ref_cartesian_map(C.c_int64(n_sel), _p(m), _p(mp), _p(mu), _p(sc), _p(ct), _p(dd), _p(eo),
+                                            _p(en), C.c_int64(cap))
         return {"max_parsimony": mp, "multiplicity": mu, "score": sc, "counts": ct, "dist_divergence": dd,
                 "epp_off": eo, "epp_nodes": None if en is None else en[: int(eo[-1])], "ms": float(ms)}
 
@@ -151,7 +167,8 @@ class Session:
 
     def filter(self):
         buf = np.zeros(self.n_nodes, np.int32)
-        k = self.lib.ref_filter(_p(buf), C.c_int32(self.n_nodes))
+        with _quiet():
+            k = self.lib.ref_filter(_p(buf), C.c_int32(self.n_nodes))
         return buf[:k].copy()
 
     def close(self):

@@ -375,6 +375,8 @@ void ref_mutation_distance(int32_t n_cand, const int32_t* cand, int64_t n_reads,
             dist[r * n_cand + c] = ar.haplotypes()[cand[c]].mutation_distance(ar.reads()[r]);
 }
 
+void ref_flush(void) { std::cout.flush(); fflush(stdout); }
+
 // wepp_filter::filter (initial_filter.cpp:455-506): cartesian map + peak loop + neighbour expansion.
 int ref_filter(int32_t* selected, int32_t capacity) {
     std::vector<haplotype*> res = g_s.filt->filter(*g_s.ar);

@@ -1,0 +1,37 @@
+"""Read sharding and the per-node exchange step of the multi-GPU placement driver.
+
+Reads are independent units (the reference's own decomposition, src/WEPP/initial_filter.cpp:152):
+rank r places the contiguous slice shard_bounds(R, r, world); per-read outputs stay local.  The
+per-node arrays are combined with one sum all-reduce — the GPU form of the reference's
+mutex-serialised chunk merge (initial_filter.cpp:199-211).  The functions take torch tensors on
+any device, so the same code runs over NCCL (GPU buffers of the library, see bench.py) and over
+gloo (CPU tests)."""
+from __future__ import annotations
+
+
+def shard_bounds(n_reads: int, rank: int, world: int) -> tuple[int, int]:
+    return n_reads * rank // world, n_reads * (rank + 1) // world
+
+
+def allreduce_node_arrays(score, counts, group=None) -> None:
+    """In-place sum over ranks of score[N] (float64) and counts[N*50] (int32)."""
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(score, op=dist.ReduceOp.SUM, group=group)
+
+
+def gather_read_results(local, n_reads: int, rank: int, world: int, group=None):
+    """Concatenate per-read int32 results of all ranks in read order (rank slices are contiguous)."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or world == 1:
+        return local
+    sizes = [shard_bounds(n_reads, r, world)[1] - shard_bounds(n_reads, r, world)[0] for r in range(world)]
+    m = max(sizes)                                    # all_gather wants equal shapes: pad, then trim
+    padded = torch.zeros(m, dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    bufs = [torch.empty(m, dtype=local.dtype, device=local.device) for _ in sizes]
+    dist.all_gather(bufs, padded, group=group)
+    return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
