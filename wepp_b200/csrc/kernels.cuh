@@ -123,7 +123,9 @@ constexpr int SMEM_REDC = SMEM_REDS + RED_G * RED_S_STRIDE * 8;     // int[RED_G
 constexpr int SMEM_WARP = (SMEM_REDC + RED_G * RED_C_STRIDE * 4 + 15) & ~15;   // bytes per warp
 constexpr int SMEM_CTRL = PLACE_WARPS * SMEM_WARP;                  // int tile id (16 B)
 constexpr int SMEM_WPB = SMEM_CTRL + 16;                            // u64[256] EPP write bases
-constexpr int SMEM_CODES = SMEM_WPB + 256 * 8;                      // code table
+constexpr int SMEM_TBLS = SMEM_WPB + 256 * 8;                       // double[2][16][32] weight sums per 4-read pattern
+constexpr int SMEM_TBLC = SMEM_TBLS + 2 * 16 * 32 * 8;              // int[2][16][32] degree sums per 4-read pattern
+constexpr int SMEM_CODES = SMEM_TBLC + 2 * 16 * 32 * 4;             // code table
 
 __device__ __forceinline__ uint4 ld_entry(const Entry* p) {
     return __ldg(reinterpret_cast<const uint4*>(p));
@@ -214,6 +216,8 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlacePara
     int* xch = reinterpret_cast<int*>(smem);  // exchange [PLACE_WARPS][3][32*K] ints, aliases the staging areas
     int* ctrl = reinterpret_cast<int*>(smem + SMEM_CTRL);
     unsigned long long* wpb = reinterpret_cast<unsigned long long*>(smem + SMEM_WPB);
+    double* tblS = reinterpret_cast<double*>(smem + SMEM_TBLS);
+    int* tblC = reinterpret_cast<int*>(smem + SMEM_TBLC);
     ET* codes = reinterpret_cast<ET*>(smem + SMEM_CODES);
     const ET* cl = codes + lane;  // this lane's column of the code table
     const unsigned FULL = 0xFFFFFFFFu;
@@ -404,10 +408,40 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlacePara
         const bool need_pass2 = p.accumulate || __syncthreads_or(small_mask != 0);
         if (!need_pass2) continue;
 
+        // ---- pattern tables: for every subset of 4 of this lane's reads, the sum of their weights
+        //      and degrees, indexed by the NOT-at-min bit pattern (bit j set = read j is above its min).
+        //      All warps hold the same per-read results, so they split the 16 patterns. -------------
+        constexpr int H = (K + 3) / 4;  // nibbles per lane
+        if (p.accumulate) {
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                for (int pat = warp; pat < 16; pat += PLACE_WARPS) {
+                    double ws = 0.0;
+                    int ds = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int j = 4 * h + b;
+                        if (j < K && !((pat >> b) & 1)) {
+                            ws += wgt[j];
+                            ds += deg[j];
+                        }
+                    }
+                    tblS[(h * 16 + pat) * 32 + lane] = ws;
+                    tblC[(h * 16 + pat) * 32 + lane] = ds;
+                }
+            }
+        }
+        __syncthreads();
+
         // ---- pass 2: which segments attain the min -> weights into the segment accumulators,
-        //      EPP node lists for reads under the cache cap ---------------------------------------
+        //      EPP node lists for reads under the cache cap.  rel[j] = running score - min >= 0 at
+        //      every non-empty segment, so "at the min" is rel == 0 and min(rel,1) is its negation.
         double* accS = p.accS + bd.acc_off;
         int32_t* accC = p.accC + bd.acc_off;
+#pragma unroll
+        for (int j = 0; j < K; ++j) run[j] -= best[j];
+        const double* tS = tblS + lane;
+        const int* tC = tblC + lane;
         {
             uint4 nxt = make_uint4(0, 0, 0, 0);
             if (c0 + lane < c1) nxt = ld_entry(ent + c0 + lane);
@@ -431,14 +465,33 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlacePara
                         double s = 0.0;
                         int c = 0;
                         if (e.x & SEG_FLAG) {
-                            uint32_t hit = 0;
+                            uint32_t z[H];
 #pragma unroll
-                            for (int j = 0; j < K; ++j)
-                                eq_accumulate(s, c, hit, run[j], best[j], wgt[j], deg[j], small_mask & (1u << j));
-                            if (hit) {  // rare: explicit EPP lists (sorted: the list is in preorder)
+                            for (int h = 0; h < H; ++h) {
+                                uint32_t zz = 0;
 #pragma unroll
-                                for (int j = 0; j < K; ++j)
-                                    if (hit & (1u << j)) emit_segment(p.epp_nodes, wp[j], e.x & IDX_MASK, e.y, p.mapped);
+                                for (int b = 3; b >= 0; --b) {
+                                    const int j = 4 * h + b;
+                                    if (j < K) zz = zz * 2u + min((uint32_t)run[j], 1u);
+                                }
+                                z[h] = zz;
+                            }
+                            if (p.accumulate) {
+#pragma unroll
+                                for (int h = 0; h < H; ++h) {
+                                    s += tS[(h * 16 + z[h]) * 32];
+                                    c += tC[(h * 16 + z[h]) * 32];
+                                }
+                            }
+                            if (small_mask) {
+                                uint32_t neq = z[0];
+                                if (H == 2) neq |= z[H - 1] << 4;
+                                uint32_t hit = ~neq & small_mask;
+                                if (hit) {  // rare: explicit EPP lists (sorted: the list is in preorder)
+#pragma unroll
+                                    for (int j = 0; j < K; ++j)
+                                        if (hit & (1u << j)) emit_segment(p.epp_nodes, wp[j], e.x & IDX_MASK, e.y, p.mapped);
+                                }
                             }
                         }
                         if (p.accumulate) {  // stage this lane's partial sums for entry gi
