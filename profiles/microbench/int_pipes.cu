@@ -12,6 +12,9 @@ __global__ void k(int* out, long long* cyc, int a0, int b0) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) r[j] = a0 + j + threadIdx.x;
     int b = b0, c = b0 * 3 + 1;
+    int q[8], q2[8], bb[8]; unsigned x = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { q[j] = j; q2[j] = 2 * j; bb[j] = 0x7fff7fff; }
     double d[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) d[j] = (double)(j + threadIdx.x);
@@ -36,12 +39,34 @@ __global__ void k(int* out, long long* cyc, int a0, int b0) {
             if (OP == 13) asm volatile("mad.lo.s32 %0, %1, %2, %0;" : "+r"(r[j]) : "r"(b), "r"(c));  // IMAD as add (a*b const + r)
             if (OP == 14) asm volatile("{.reg .pred p; setp.eq.s32 p, %0, %1; @p add.s32 %0, %0, %2;  min.s32 %0, %0, %1;}" : "+r"(r[j]) : "r"(b + i), "r"(c)); // setp+@add+min
             if (OP == 15) r[j] += __popc(r[j] ^ b);                                                    // POPC (+LOP,+IADD)
+            if (OP == 16) {  // packed pass-1 step for one pair of reads: PRMT + VIADD.16x2 + VIMNMX.S16x2(+2 preds) + 2 @IADD + LOP3
+                unsigned dlt, nb;
+                asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(dlt) : "r"(b), "r"(c), "r"(i));
+                asm volatile("add.s16x2 %0, %0, %1;" : "+r"(r[j]) : "r"(dlt));
+                asm volatile("{.reg .pred ph, pl; .reg .u16 a0, a1, m0, m1;\n\t"
+                             "min.s16x2 %0, %3, %4;\n\t"
+                             "mov.b32 {m0, m1}, %0; mov.b32 {a0, a1}, %3;\n\t"
+                             "setp.eq.s16 pl, m0, a0; setp.eq.s16 ph, m1, a1;\n\t"
+                             "@pl add.s32 %1, %1, %5;\n\t"
+                             "@ph add.s32 %2, %2, %5;}"
+                             : "=r"(nb), "+r"(q[j]), "+r"(q2[j]) : "r"(r[j]), "r"(bb[j]), "r"(c));
+                x |= nb ^ bb[j];
+                bb[j] = nb;
+            }
+            if (OP == 17) asm volatile("{.reg .pred ph, pl; .reg .u16 a0, a1, m0, m1; .reg .b32 t;\n\t"
+                             "min.s16x2 t, %0, %2;\n\t"
+                             "mov.b32 {m0, m1}, t; mov.b32 {a0, a1}, %0;\n\t"
+                             "setp.eq.s16 pl, m0, a0; setp.eq.s16 ph, m1, a1;\n\t"
+                             "@pl add.s32 %1, %1, %3;\n\t"
+                             "@ph add.s32 %0, %0, %3;}"
+                             : "+r"(r[j]), "+r"(q[j]) : "r"(b + i), "r"(c));   // VIMNMX.S16x2 w/ preds + 2 @IADD
         }
     }
     long long t1 = clock64();
     int acc = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc += r[j] + (int)d[j];
+    for (int j = 0; j < 8; ++j) acc += r[j] + (int)d[j] + q[j] + q2[j] + bb[j];
+    acc += x;
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -85,5 +110,7 @@ int main() {
     run<11>("add.u16x2", 1);
     run<12>("min.s16x2", 1);
     run<15>("LOP+POPC+IADD", 3);
+    run<17>("VIMNMX.S16x2+P,2x@IADD", 3);
+    run<16>("packed pass-1 pair step", 6);
     return 0;
 }
