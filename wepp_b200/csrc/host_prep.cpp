@@ -222,13 +222,15 @@ std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t
     // reads per tile
     int32_t k = reads_per_lane;
     if (k != 2 && k != 4 && k != 8) {
-        k = out.max_width <= 224 ? 8 : (out.max_width <= 448 ? 4 : 2);
+        // selector table = width * 32 lanes * K bytes next to ~48 KB of staging: two CTAs per SM
+        // up to 256 (K=8) / 512 (K=4) bases
+        k = out.max_width <= 256 ? 8 : (out.max_width <= 640 ? 4 : 2);
         auto tiles_for = [&](int kk) {
             int64_t t = 0;
             for (int64_t c : bucket_count) t += (c + 32 * kk - 1) / (32 * kk);
             return t;
         };
-        while (k > 2 && tiles_for(k) < 2368) k >>= 1;  // keep >= 2 tiles per resident warp when reads are few
+        while (k > 2 && tiles_for(k) < 592) k >>= 1;  // keep >= 2 tiles per resident CTA when reads are few
     }
     out.reads_per_tile = 32 * k;
 

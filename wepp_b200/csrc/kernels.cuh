@@ -66,54 +66,82 @@ struct PlaceParams {
     int32_t smem_per_warp;  // unused (layout is compile-time); kept for ABI stability of the struct
 };
 
-template <int K> struct Elem;
-template <> struct Elem<8> { using type = uint32_t; };
-template <> struct Elem<4> { using type = uint16_t; };
-template <> struct Elem<2> { using type = uint8_t; };
+// Per-lane selector storage of the read-allele code table: one byte per read per window position,
+// (class | (class|8) << 4): fed to PRMT as two selector nibbles it yields the read's signed delta
+// byte followed by its sign replicated, i.e. a sign-extended 16-bit half.  Two reads = one
+// 16-bit selector = one packed s16x2 delta.  SHIFT turns Entry::w into the byte offset of the
+// position's row (row = 32 lanes * K bytes; bits 8..15 of Entry::w are zero by construction).
+template <int K> struct Sel;
+template <> struct Sel<8> { using type = uint2;    static constexpr int SHIFT = 8; };
+template <> struct Sel<4> { using type = uint32_t; static constexpr int SHIFT = 9; };
+template <> struct Sel<2> { using type = uint16_t; static constexpr int SHIFT = 10; };
 
-// prmt without __byte_perm's selector masking: codes are <= 5, so bit 3 of a selector nibble
-// (sign-replicate mode) is never set.
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
     uint32_t r;
     asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
     return r;
 }
 
-// min / multiplicity update for one read at one non-empty segment (initial_filter.cpp:89-99):
-//   run < best -> best = run, cnt = ucnt ;  run == best -> cnt += ucnt.  Five predicated ops.
-__device__ __forceinline__ void min_count_update(int& best, int& cnt, int run, int ucnt) {
-    asm("{\n\t"
-        ".reg .pred lt, le;\n\t"
-        "setp.lt.s32 lt, %2, %0;\n\t"
-        "setp.le.s32 le, %2, %0;\n\t"
-        "@lt mov.s32 %1, 0;\n\t"
-        "@le add.s32 %1, %1, %3;\n\t"
-        "min.s32 %0, %0, %2;\n\t"
-        "}"
-        : "+r"(best), "+r"(cnt)
-        : "r"(run), "r"(ucnt));
+// col = 32-bit shared-window address of the lane's column, off = byte offset of the position's row
+template <int K>
+__device__ __forceinline__ void load_sel(uint32_t col, uint32_t off, uint32_t (&s)[K / 2]) {
+    const uint32_t a = col + off;
+    if constexpr (K == 8) {
+        uint32_t x, y;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(x), "=r"(y) : "r"(a));
+        s[0] = x; s[1] = x >> 16; s[2] = y; s[3] = y >> 16;   // PRMT reads selector bits 0..15 only
+    } else if constexpr (K == 4) {
+        uint32_t x;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(a));
+        s[0] = x; s[1] = x >> 16;
+    } else {
+        uint32_t x;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(x) : "r"(a));
+        s[0] = x;
+    }
 }
 
-// weight / degree accumulation for one read at one segment: if (run == best) { s += w; c += d; hit |= bit; }
-__device__ __forceinline__ void eq_accumulate(double& s, int& c, uint32_t& hit, int run, int best, double w, int d,
-                                              uint32_t bit) {
+// Packed 16x2 arithmetic (sm_90+ hardware: VIADD.16x2, VIMNMX.S16x2 with two predicate outputs).
+// Pass-1 running sums are held as value + S_BIAS in each half so that halves stay non-negative
+// and the sum of the packed minima is a strictly monotone detector of "some minimum decreased".
+constexpr uint32_t S_BIAS = 0x1000u;
+constexpr uint32_t S_BIAS2 = 0x10001000u;
+constexpr uint32_t BEST_NONE = 0x3FFFu;
+constexpr uint32_t BEST_NONE2 = 0x3FFF3FFFu;
+constexpr int MAX_WINDOW = 4000;   // widest bucket the 16-bit halves are sized for (|score| < S_BIAS)
+
+// One pair of reads at one non-empty segment (initial_filter.cpp:89-99): b = min(s, b) per half,
+// and where s <= b the segment's countable nodes are added to the read's node count (a strict
+// decrease is repaired by the caller).  VIMNMX.S16x2 with two predicate outputs + two predicated adds.
+__device__ __forceinline__ void min_count2(uint32_t s, uint32_t& b, int& c_lo, int& c_hi, int ucnt) {
     asm("{\n\t"
-        ".reg .pred eq;\n\t"
-        "setp.eq.s32 eq, %3, %4;\n\t"
-        "@eq add.f64 %0, %0, %5;\n\t"
-        "@eq add.s32 %1, %1, %6;\n\t"
-        "@eq or.b32 %2, %2, %7;\n\t"
+        ".reg .pred ph, pl;\n\t"
+        ".reg .u16 a0, a1, m0, m1;\n\t"
+        "min.s16x2 %0, %3, %0;\n\t"
+        "mov.b32 {m0, m1}, %0;\n\t"
+        "mov.b32 {a0, a1}, %3;\n\t"
+        "setp.eq.s16 pl, m0, a0;\n\t"
+        "setp.eq.s16 ph, m1, a1;\n\t"
+        "@pl add.s32 %1, %1, %4;\n\t"
+        "@ph add.s32 %2, %2, %4;\n\t"
         "}"
-        : "+d"(s), "+r"(c), "+r"(hit)
-        : "r"(run), "r"(best), "d"(w), "r"(d), "r"(bit));
+        : "+r"(b), "+r"(c_lo), "+r"(c_hi)
+        : "r"(s), "r"(ucnt));
 }
+
+struct __align__(16) PatEntry {   // pass-2 pattern table entry
+    double w;
+    int32_t c;
+    int32_t pad;
+};
 
 // Shared-memory layout of place_kernel (one CTA = one tile of 32*K reads, PLACE_WARPS warps).
 //   per warp : 32 staged entries (512 B) + pass-2 reduction staging (double[8][36] + int[8][33])
-//   per CTA  : the read-allele code table [width][32] (K nibbles per lane element)
+//   per CTA  : tile id, EPP write bases, pattern tables, the read-allele selector table
 // The per-warp staging areas double as the exchange buffer for the chunk summaries between
-// pass 1 and pass 2.
-constexpr int PLACE_WARPS = 4;
+// pass 1 and pass 2.  The pattern tables must lie below 64 KB (their byte offsets are carried
+// in 16-bit halves).
+constexpr int PLACE_WARPS = 8;
 constexpr int RED_G = 8;              // entries reduced together in pass 2
 constexpr int RED_S_STRIDE = 36;      // doubles per staged row: 32 lanes + pad (conflict-free column sums)
 constexpr int RED_C_STRIDE = 33;      // ints per staged row
@@ -123,9 +151,11 @@ constexpr int SMEM_REDC = SMEM_REDS + RED_G * RED_S_STRIDE * 8;     // int[RED_G
 constexpr int SMEM_WARP = (SMEM_REDC + RED_G * RED_C_STRIDE * 4 + 15) & ~15;   // bytes per warp
 constexpr int SMEM_CTRL = PLACE_WARPS * SMEM_WARP;                  // int tile id (16 B)
 constexpr int SMEM_WPB = SMEM_CTRL + 16;                            // u64[256] EPP write bases
-constexpr int SMEM_TBLS = SMEM_WPB + 256 * 8;                       // double[2][16][32] weight sums per 4-read pattern
-constexpr int SMEM_TBLC = SMEM_TBLS + 2 * 16 * 32 * 8;              // int[2][16][32] degree sums per 4-read pattern
-constexpr int SMEM_CODES = SMEM_TBLC + 2 * 16 * 32 * 4;             // code table
+constexpr int SMEM_TBL = SMEM_WPB + 256 * 8;                        // PatEntry[2][16][32]: [even/odd reads][pattern][lane]
+constexpr int TBL_PAT_STRIDE = 32 * 16;                             // bytes per pattern row
+constexpr int TBL_HALF = 16 * TBL_PAT_STRIDE;                       // bytes per half table
+constexpr int SMEM_CODES = SMEM_TBL + 2 * TBL_HALF;                 // selector table
+static_assert(SMEM_CODES <= 65536, "pattern tables must be addressable with 16-bit offsets");
 
 __device__ __forceinline__ uint4 ld_entry(const Entry* p) {
     return __ldg(reinterpret_cast<const uint4*>(p));
@@ -196,17 +226,23 @@ __device__ __noinline__ void emit_segment(int32_t* __restrict__ out, unsigned lo
 }
 
 // The placement kernel.  Persistent CTAs; each CTA pulls tiles (32*K reads of one window bucket)
-// from a global counter.  The CTA's PLACE_WARPS warps share the tile's allele-code table and
-// each scans one contiguous chunk of the bucket's Euler list for ALL reads of the tile (lane =
-// K reads), a two-level Euler-tour scan:
+// from a global counter.  The CTA's PLACE_WARPS warps share the tile's selector table and each
+// scans one contiguous chunk of the bucket's Euler list for ALL reads of the tile (lane = K
+// reads held as K/2 packed s16x2 registers), a two-level Euler-tour scan:
 //   pass 1  per chunk: sum of deltas, min prefix, node count at the min  -> shared memory
+//           per entry and pair of reads: PRMT (signed delta pair) + VIADD.16x2 (prefix sum) +
+//           VIMNMX.S16x2 with its two predicates (running min, "<= min") + two predicated adds
+//           (node count); a strict decrease of any minimum is caught once per entry by comparing
+//           the sum of the packed minima and repaired out of line.
 //   combine every warp folds the chunk summaries: global min, multiplicity, its own start offset
 //   pass 2  per chunk: segments attaining the min -> weight/degree sums into the segment
 //           accumulators (staged through shared memory, one atomic per segment per tile) and
 //           explicit EPP lists for reads under the cache cap.
 template <int K>
-__global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlaceParams p) {
-    using ET = typename Elem<K>::type;
+__global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceParams p) {
+    using ST = typename Sel<K>::type;
+    constexpr int P = K / 2;           // packed pairs per lane
+    constexpr int SHIFT = Sel<K>::SHIFT;
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* wbase = smem + (size_t)warp * SMEM_WARP;
@@ -216,16 +252,17 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlacePara
     int* xch = reinterpret_cast<int*>(smem);  // exchange [PLACE_WARPS][3][32*K] ints, aliases the staging areas
     int* ctrl = reinterpret_cast<int*>(smem + SMEM_CTRL);
     unsigned long long* wpb = reinterpret_cast<unsigned long long*>(smem + SMEM_WPB);
-    double* tblS = reinterpret_cast<double*>(smem + SMEM_TBLS);
-    int* tblC = reinterpret_cast<int*>(smem + SMEM_TBLC);
-    ET* codes = reinterpret_cast<ET*>(smem + SMEM_CODES);
-    const ET* cl = codes + lane;  // this lane's column of the code table
+    PatEntry* tbl = reinterpret_cast<PatEntry*>(smem + SMEM_TBL);
+    unsigned char* codes = smem + SMEM_CODES;
+    const uint32_t col = (uint32_t)__cvta_generic_to_shared(codes + lane * K);  // this lane's column of the selector table
     const unsigned FULL = 0xFFFFFFFFu;
     constexpr int T = 32 * K;
     static_assert(PLACE_WARPS * 3 * T * 4 <= PLACE_WARPS * SMEM_WARP, "exchange buffer must fit the staging areas");
+    // byte offsets of this lane's pattern-table column: low half = even reads, high half = odd reads
+    const uint32_t tbase2 = (uint32_t)(SMEM_TBL + lane * 16) | ((uint32_t)(SMEM_TBL + TBL_HALF + lane * 16) << 16);
 
     for (;;) {
-        __syncthreads();  // previous tile fully done (code table, exchange buffer)
+        __syncthreads();  // previous tile fully done (selector table, exchange buffer)
         if (threadIdx.x == 0) ctrl[0] = atomicAdd(p.tile_counter, 1);
         __syncthreads();
         const int t = ctrl[0];
@@ -239,7 +276,7 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlacePara
         const int cs = (((n + PLACE_WARPS - 1) / PLACE_WARPS) + 31) & ~31;
         const int c0 = min(n, warp * cs), c1 = min(n, c0 + cs);
 
-        // ---- read tile -> shared allele-code table --------------------------------------------
+        // ---- read tile -> shared selector table -------------------------------------------------
         int run0[K];
         int64_t rid[K];
         {
@@ -254,10 +291,13 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlacePara
                 run0[j] = 0;
             }
             for (int pos = warp; pos < ld.width; pos += PLACE_WARPS) {
-                uint32_t w = 0;
+                uint32_t w[2] = {0u, 0u};
 #pragma unroll
-                for (int j = 0; j < K; ++j) w |= ((pos >= s_rel[j] && pos <= e_rel[j]) ? 0u : 5u) << (4 * j);
-                codes[pos * 32 + lane] = (ET)w;
+                for (int j = 0; j < K; ++j)   // class 0 (as reference) inside the window, class 5 outside
+                    w[j >> 2] |= ((pos >= s_rel[j] && pos <= e_rel[j]) ? 0x80u : 0xD5u) << (8 * (j & 3));
+                ST* row = reinterpret_cast<ST*>(codes) + pos * 32 + lane;
+                if constexpr (K == 8) *row = make_uint2(w[0], w[1]);
+                else *row = (ST)w[0];
             }
         }
         __syncthreads();
@@ -269,9 +309,7 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlacePara
                     const uint32_t c = p.rm_code[k];
                     if (warp == 0) {  // one owner per table column: no races
                         const int pr = p.rm_pos[k] - ld.b0;
-                        uint32_t w = codes[pr * 32 + lane];
-                        w = (w & ~(0xFu << (4 * j))) | (c << (4 * j));
-                        codes[pr * 32 + lane] = (ET)w;
+                        codes[(pr * 32 + lane) * K + j] = (unsigned char)(c | ((c | 8u) << 4));
                     }
                     run0[j] += (c <= 4u);  // seed set: non-N mutations (initial_filter.cpp:118-123)
                 }
@@ -281,13 +319,16 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlacePara
 
         // ---- pass 1: chunk-relative prefix sum of signed deltas, min prefix and its node count ----
         int run[K], best[K], cnt[K];
-#pragma unroll
-        for (int j = 0; j < K; ++j) {
-            run[j] = 0;
-            best[j] = 0x3FFFFFFF;
-            cnt[j] = 0;
-        }
         {
+            uint32_t S[P], B[P], oB[P];
+            uint32_t bsum = (uint32_t)P * BEST_NONE2;
+#pragma unroll
+            for (int q = 0; q < P; ++q) {
+                S[q] = S_BIAS2;
+                B[q] = oB[q] = BEST_NONE2;
+            }
+#pragma unroll
+            for (int j = 0; j < K; ++j) cnt[j] = 0;
             uint4 nxt = make_uint4(0, 0, 0, 0);
             if (c0 + lane < c1) nxt = ld_entry(ent + c0 + lane);
             for (int base = c0; base < c1; base += 32) {
@@ -298,20 +339,38 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlacePara
 #pragma unroll 4
                 for (int ii = 0; ii < m; ++ii) {
                     const uint4 e = ebuf[ii];
-                    const uint32_t w = cl[(e.w >> 16) * 32];
-                    const uint32_t d0 = prmt(e.z, e.w, w);
-                    uint32_t d1 = 0;
-                    if (K == 8) d1 = prmt(e.z, e.w, w >> 16);
+                    uint32_t sel[P];
+                    load_sel<K>(col, e.w >> SHIFT, sel);
 #pragma unroll
-                    for (int j = 0; j < K; ++j)
-                        run[j] = __dp4a((int)(j < 4 ? d0 : d1), (int)(1u << (8 * (j & 3))), run[j]);
+                    for (int q = 0; q < P; ++q) S[q] = __vadd2(S[q], prmt(e.z, e.w, sel[q]));
                     if (e.x & SEG_FLAG) {
                         const int ucnt = (int)e.y;
+                        uint32_t sum = 0;
 #pragma unroll
-                        for (int j = 0; j < K; ++j) min_count_update(best[j], cnt[j], run[j], ucnt);
+                        for (int q = 0; q < P; ++q) {
+                            min_count2(S[q], B[q], cnt[2 * q], cnt[2 * q + 1], ucnt);
+                            sum += B[q];
+                        }
+                        if (sum != bsum) {  // rare: some read reached a new strict minimum here
+#pragma unroll
+                            for (int q = 0; q < P; ++q) {   // oB = minima before this entry (they only change here)
+                                if ((S[q] & 0xFFFFu) < (oB[q] & 0xFFFFu)) cnt[2 * q] = ucnt;
+                                if ((S[q] >> 16) < (oB[q] >> 16)) cnt[2 * q + 1] = ucnt;
+                                oB[q] = B[q];
+                            }
+                            bsum = sum;
+                        }
                     }
                 }
                 __syncwarp();
+            }
+#pragma unroll
+            for (int q = 0; q < P; ++q) {
+                run[2 * q] = (int)(S[q] & 0xFFFFu) - (int)S_BIAS;
+                run[2 * q + 1] = (int)(S[q] >> 16) - (int)S_BIAS;
+                const uint32_t bl = B[q] & 0xFFFFu, bh = B[q] >> 16;
+                best[2 * q] = bl == BEST_NONE ? 0x3FFFFFFF : (int)bl - (int)S_BIAS;
+                best[2 * q + 1] = bh == BEST_NONE ? 0x3FFFFFFF : (int)bh - (int)S_BIAS;
             }
         }
         // ---- exchange chunk summaries, fold them ------------------------------------------------
@@ -408,40 +467,44 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlacePara
         const bool need_pass2 = p.accumulate || __syncthreads_or(small_mask != 0);
         if (!need_pass2) continue;
 
-        // ---- pattern tables: for every subset of 4 of this lane's reads, the sum of their weights
-        //      and degrees, indexed by the NOT-at-min bit pattern (bit j set = read j is above its min).
-        //      All warps hold the same per-read results, so they split the 16 patterns. -------------
-        constexpr int H = (K + 3) / 4;  // nibbles per lane
+        // ---- pattern tables: for the lane's even reads (low halves) and odd reads (high halves),
+        //      the sum of weights / degrees of the reads whose NOT-at-min bit is clear, indexed by
+        //      the P-bit pattern (bit q = read of pair q is above its min).  All warps hold the same
+        //      per-read results, so they split the 2 x 2^P patterns. --------------------------------
         if (p.accumulate) {
+            for (int hp = warp; hp < 2 * (1 << P); hp += PLACE_WARPS) {
+                const int h = hp >> P, pat = hp & ((1 << P) - 1);
+                double ws = 0.0;
+                int ds = 0;
 #pragma unroll
-            for (int h = 0; h < H; ++h) {
-                for (int pat = warp; pat < 16; pat += PLACE_WARPS) {
-                    double ws = 0.0;
-                    int ds = 0;
-#pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int j = 4 * h + b;
-                        if (j < K && !((pat >> b) & 1)) {
-                            ws += wgt[j];
-                            ds += deg[j];
-                        }
+                for (int q = 0; q < P; ++q) {
+                    if (!((pat >> q) & 1)) {
+                        ws += h ? wgt[2 * q + 1] : wgt[2 * q];
+                        ds += h ? deg[2 * q + 1] : deg[2 * q];
                     }
-                    tblS[(h * 16 + pat) * 32 + lane] = ws;
-                    tblC[(h * 16 + pat) * 32 + lane] = ds;
                 }
+                PatEntry pe;
+                pe.w = ws;
+                pe.c = ds;
+                pe.pad = 0;
+                tbl[(h * 16 + pat) * 32 + lane] = pe;
             }
         }
         __syncthreads();
 
         // ---- pass 2: which segments attain the min -> weights into the segment accumulators,
-        //      EPP node lists for reads under the cache cap.  rel[j] = running score - min >= 0 at
-        //      every non-empty segment, so "at the min" is rel == 0 and min(rel,1) is its negation.
+        //      EPP node lists for reads under the cache cap.  rel = running score - min >= 0 at
+        //      every non-empty segment, so min(rel, 1) is the read's NOT-at-min bit. ---------------
         double* accS = p.accS + bd.acc_off;
         int32_t* accC = p.accC + bd.acc_off;
+        uint32_t rel[P];
+        uint32_t small_lo = 0, small_hi = 0;
 #pragma unroll
-        for (int j = 0; j < K; ++j) run[j] -= best[j];
-        const double* tS = tblS + lane;
-        const int* tC = tblC + lane;
+        for (int q = 0; q < P; ++q) {
+            rel[q] = ((uint32_t)(run[2 * q] - best[2 * q]) & 0xFFFFu) | ((uint32_t)(run[2 * q + 1] - best[2 * q + 1]) << 16);
+            small_lo |= ((small_mask >> (2 * q)) & 1u) << q;
+            small_hi |= ((small_mask >> (2 * q + 1)) & 1u) << q;
+        }
         {
             uint4 nxt = make_uint4(0, 0, 0, 0);
             if (c0 + lane < c1) nxt = ld_entry(ent + c0 + lane);
@@ -455,42 +518,32 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32) place_kernel(const PlacePara
 #pragma unroll 2
                     for (int gi = 0; gi < gm; ++gi) {
                         const uint4 e = ebuf[g0 + gi];
-                        const uint32_t w = cl[(e.w >> 16) * 32];
-                        const uint32_t d0 = prmt(e.z, e.w, w);
-                        uint32_t d1 = 0;
-                        if (K == 8) d1 = prmt(e.z, e.w, w >> 16);
+                        uint32_t sel[P];
+                        load_sel<K>(col, e.w >> SHIFT, sel);
 #pragma unroll
-                        for (int j = 0; j < K; ++j)
-                            run[j] = __dp4a((int)(j < 4 ? d0 : d1), (int)(1u << (8 * (j & 3))), run[j]);
+                        for (int q = 0; q < P; ++q) rel[q] = __vadd2(rel[q], prmt(e.z, e.w, sel[q]));
                         double s = 0.0;
                         int c = 0;
                         if (e.x & SEG_FLAG) {
-                            uint32_t z[H];
+                            uint32_t tt = tbase2;
 #pragma unroll
-                            for (int h = 0; h < H; ++h) {
-                                uint32_t zz = 0;
-#pragma unroll
-                                for (int b = 3; b >= 0; --b) {
-                                    const int j = 4 * h + b;
-                                    if (j < K) zz = zz * 2u + min((uint32_t)run[j], 1u);
-                                }
-                                z[h] = zz;
-                            }
+                            for (int q = 0; q < P; ++q) tt += __vmins2(rel[q], 0x00010001u) * (uint32_t)(TBL_PAT_STRIDE << q);
                             if (p.accumulate) {
-#pragma unroll
-                                for (int h = 0; h < H; ++h) {
-                                    s += tS[(h * 16 + z[h]) * 32];
-                                    c += tC[(h * 16 + z[h]) * 32];
-                                }
+                                const PatEntry a = *reinterpret_cast<const PatEntry*>(smem + (tt & 0xFFFFu));
+                                const PatEntry b = *reinterpret_cast<const PatEntry*>(smem + (tt >> 16));
+                                s = a.w + b.w;
+                                c = a.c + b.c;
                             }
                             if (small_mask) {
-                                uint32_t neq = z[0];
-                                if (H == 2) neq |= z[H - 1] << 4;
-                                uint32_t hit = ~neq & small_mask;
-                                if (hit) {  // rare: explicit EPP lists (sorted: the list is in preorder)
+                                const uint32_t dd = tt - tbase2;   // per half: pattern * TBL_PAT_STRIDE
+                                const uint32_t hit_lo = ~((dd & 0xFFFFu) / TBL_PAT_STRIDE) & small_lo;
+                                const uint32_t hit_hi = ~((dd >> 16) / TBL_PAT_STRIDE) & small_hi;
+                                if (hit_lo | hit_hi) {  // rare: explicit EPP lists (sorted: the list is in preorder)
 #pragma unroll
-                                    for (int j = 0; j < K; ++j)
-                                        if (hit & (1u << j)) emit_segment(p.epp_nodes, wp[j], e.x & IDX_MASK, e.y, p.mapped);
+                                    for (int q = 0; q < P; ++q) {
+                                        if (hit_lo & (1u << q)) emit_segment(p.epp_nodes, wp[2 * q], e.x & IDX_MASK, e.y, p.mapped);
+                                        if (hit_hi & (1u << q)) emit_segment(p.epp_nodes, wp[2 * q + 1], e.x & IDX_MASK, e.y, p.mapped);
+                                    }
                                 }
                             }
                         }

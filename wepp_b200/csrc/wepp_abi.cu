@@ -175,11 +175,10 @@ int finalize_plan(wepp_handle* h, wepp_handle::DevPlan& dp) {
 
 template <int K>
 int launch_place(wepp_handle* h, const PlaceParams& pp, int width) {
-    using ET = typename Elem<K>::type;
     PlaceParams p = pp;
     p.smem_per_warp = SMEM_WARP;
-    const size_t smem = (size_t)SMEM_CODES + (((size_t)width * 32 * sizeof(ET) + 15) & ~(size_t)15);
-    if (smem > h->smem_optin)
+    const size_t smem = (size_t)SMEM_CODES + (((size_t)width * 32 * K + 15) & ~(size_t)15);
+    if (smem > h->smem_optin || width > MAX_WINDOW)
         return fail(WEPP_E_INVALID, "read window too wide for shared memory (" + std::to_string(width) + " bases)");
     CU(cudaFuncSetAttribute(place_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
