@@ -225,6 +225,33 @@ __device__ __noinline__ void emit_segment(int32_t* __restrict__ out, unsigned lo
     }
 }
 
+// ---- shared-window load/store helpers (32-bit shared addresses; immediate offsets fold into LDS/STS) ----
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double lds_f64(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+
 // The placement kernel.  Persistent CTAs; each CTA pulls tiles (32*K reads of one window bucket)
 // from a global counter.  The CTA's PLACE_WARPS warps share the tile's selector table and each
 // scans one contiguous chunk of the bucket's Euler list for ALL reads of the tile (lane = K
@@ -238,28 +265,34 @@ __device__ __noinline__ void emit_segment(int32_t* __restrict__ out, unsigned lo
 //   pass 2  per chunk: segments attaining the min -> weight/degree sums into the segment
 //           accumulators (staged through shared memory, one atomic per segment per tile) and
 //           explicit EPP lists for reads under the cache cap.
-template <int K>
+// Entries are staged 32 at a time through shared memory (zero entries pad the chunk's tail: a
+// zero entry changes nothing and is never a segment end), so both passes run branch-free over
+// whole batches.  ACC = accumulate per-segment weights (wepp_place); EPP = emit explicit lists.
+template <int K, bool ACC, bool EPP>
 __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceParams p) {
     using ST = typename Sel<K>::type;
     constexpr int P = K / 2;           // packed pairs per lane
     constexpr int SHIFT = Sel<K>::SHIFT;
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned char* wbase = smem + (size_t)warp * SMEM_WARP;
-    uint4* ebuf = reinterpret_cast<uint4*>(wbase + SMEM_EBUF);
-    double* redS = reinterpret_cast<double*>(wbase + SMEM_REDS);
-    int* redC = reinterpret_cast<int*>(wbase + SMEM_REDC);
+    const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t ebuf_s = smem_s + warp * SMEM_WARP + SMEM_EBUF;
+    const uint32_t redS_s = smem_s + warp * SMEM_WARP + SMEM_REDS;
+    const uint32_t redC_s = smem_s + warp * SMEM_WARP + SMEM_REDC;
     int* xch = reinterpret_cast<int*>(smem);  // exchange [PLACE_WARPS][3][32*K] ints, aliases the staging areas
     int* ctrl = reinterpret_cast<int*>(smem + SMEM_CTRL);
     unsigned long long* wpb = reinterpret_cast<unsigned long long*>(smem + SMEM_WPB);
     PatEntry* tbl = reinterpret_cast<PatEntry*>(smem + SMEM_TBL);
     unsigned char* codes = smem + SMEM_CODES;
-    const uint32_t col = (uint32_t)__cvta_generic_to_shared(codes + lane * K);  // this lane's column of the selector table
+    const uint32_t col = smem_s + SMEM_CODES + lane * K;  // this lane's column of the selector table
     const unsigned FULL = 0xFFFFFFFFu;
     constexpr int T = 32 * K;
     static_assert(PLACE_WARPS * 3 * T * 4 <= PLACE_WARPS * SMEM_WARP, "exchange buffer must fit the staging areas");
-    // byte offsets of this lane's pattern-table column: low half = even reads, high half = odd reads
-    const uint32_t tbase2 = (uint32_t)(SMEM_TBL + lane * 16) | ((uint32_t)(SMEM_TBL + TBL_HALF + lane * 16) << 16);
+    // shared addresses of this lane's pattern-table column: low half = even reads, high half = odd
+    // reads (the kernel is never launched in a cluster, so the shared window starts near 0)
+    if (smem_s + SMEM_CODES > 0xFFFFu) __trap();
+    const uint32_t tbase2 = (smem_s + SMEM_TBL + lane * 16) | ((smem_s + SMEM_TBL + TBL_HALF + lane * 16) << 16);
+    const uint32_t tzero = tbase2 + (uint32_t)(((1 << P) - 1) * TBL_PAT_STRIDE) * 0x00010001u;  // pattern "nobody at min" -> 0
 
     for (;;) {
         __syncthreads();  // previous tile fully done (selector table, exchange buffer)
@@ -332,33 +365,39 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
             uint4 nxt = make_uint4(0, 0, 0, 0);
             if (c0 + lane < c1) nxt = ld_entry(ent + c0 + lane);
             for (int base = c0; base < c1; base += 32) {
-                ebuf[lane] = nxt;
+                sts128(ebuf_s + lane * 16, nxt);
+                const uint32_t fm = __ballot_sync(FULL, (nxt.x & SEG_FLAG) != 0u);  // segment ends of this batch
                 __syncwarp();
+                nxt = make_uint4(0, 0, 0, 0);
                 if (base + 32 + lane < c1) nxt = ld_entry(ent + base + 32 + lane);
-                const int m = min(32, c1 - base);
-#pragma unroll 4
-                for (int ii = 0; ii < m; ++ii) {
-                    const uint4 e = ebuf[ii];
-                    uint32_t sel[P];
-                    load_sel<K>(col, e.w >> SHIFT, sel);
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t ea = ebuf_s + g * 128;
+                    const uint32_t fg = fm >> (8 * g);
 #pragma unroll
-                    for (int q = 0; q < P; ++q) S[q] = __vadd2(S[q], prmt(e.z, e.w, sel[q]));
-                    if (e.x & SEG_FLAG) {
-                        const int ucnt = (int)e.y;
-                        uint32_t sum = 0;
+                    for (int i = 0; i < 8; ++i) {
+                        const uint4 e = lds128(ea + i * 16);
+                        uint32_t sel[P];
+                        load_sel<K>(col, e.w >> SHIFT, sel);
 #pragma unroll
-                        for (int q = 0; q < P; ++q) {
-                            min_count2(S[q], B[q], cnt[2 * q], cnt[2 * q + 1], ucnt);
-                            sum += B[q];
-                        }
-                        if (sum != bsum) {  // rare: some read reached a new strict minimum here
+                        for (int q = 0; q < P; ++q) S[q] = __vadd2(S[q], prmt(e.z, e.w, sel[q]));
+                        if (fg & (1u << i)) {   // warp-uniform: non-empty segment ends here
+                            const int ucnt = (int)e.y;
+                            uint32_t sum = 0;
 #pragma unroll
-                            for (int q = 0; q < P; ++q) {   // oB = minima before this entry (they only change here)
-                                if ((S[q] & 0xFFFFu) < (oB[q] & 0xFFFFu)) cnt[2 * q] = ucnt;
-                                if ((S[q] >> 16) < (oB[q] >> 16)) cnt[2 * q + 1] = ucnt;
-                                oB[q] = B[q];
+                            for (int q = 0; q < P; ++q) {
+                                min_count2(S[q], B[q], cnt[2 * q], cnt[2 * q + 1], ucnt);
+                                sum += B[q];
                             }
-                            bsum = sum;
+                            if (__any_sync(FULL, sum != bsum)) {  // rare: some read reached a new strict minimum here
+#pragma unroll
+                                for (int q = 0; q < P; ++q) {   // oB = minima before this entry (they only change here)
+                                    if ((S[q] & 0xFFFFu) < (oB[q] & 0xFFFFu)) cnt[2 * q] = ucnt;
+                                    if ((S[q] >> 16) < (oB[q] >> 16)) cnt[2 * q + 1] = ucnt;
+                                    oB[q] = B[q];
+                                }
+                                bsum = sum;
+                            }
                         }
                     }
                 }
@@ -433,7 +472,7 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
                     const int64_t orig = p.perm[rid[j]];
                     p.max_pars[orig] = best[j];
                     p.mult[orig] = cnt[j];
-                    if (p.epp_off) {
+                    if (EPP && p.epp_off) {
                         long long off = -1;
                         unsigned long long base = ~0ull;
                         if (cnt[j] > 0 && cnt[j] <= p.epp_cap) {
@@ -449,11 +488,11 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
                         wpb[j * 32 + lane] = base;
                     }
                 }
-            } else if (warp == 0 && p.epp_off) {
+            } else if (EPP && warp == 0 && p.epp_off) {
                 wpb[j * 32 + lane] = ~0ull;
             }
         }
-        if (p.epp_off) {
+        if (EPP && p.epp_off) {
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < K; ++j) {
@@ -464,14 +503,15 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
                 }
             }
         }
-        const bool need_pass2 = p.accumulate || __syncthreads_or(small_mask != 0);
-        if (!need_pass2) continue;
+        if (!ACC) {
+            if (!__syncthreads_or(small_mask != 0)) continue;   // nothing to emit: no pass 2
+        }
 
         // ---- pattern tables: for the lane's even reads (low halves) and odd reads (high halves),
         //      the sum of weights / degrees of the reads whose NOT-at-min bit is clear, indexed by
         //      the P-bit pattern (bit q = read of pair q is above its min).  All warps hold the same
         //      per-read results, so they split the 2 x 2^P patterns. --------------------------------
-        if (p.accumulate) {
+        if (ACC) {
             for (int hp = warp; hp < 2 * (1 << P); hp += PLACE_WARPS) {
                 const int h = hp >> P, pat = hp & ((1 << P) - 1);
                 double ws = 0.0;
@@ -506,76 +546,92 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
             small_hi |= ((small_mask >> (2 * q + 1)) & 1u) << q;
         }
         {
+            const int er = lane >> 2, part = lane & 3;   // reduction role: entry er of the group, quarter `part` of the lanes
+            const uint32_t rS = redS_s + (er * RED_S_STRIDE + part) * 8;
+            const uint32_t rC = redC_s + (er * RED_C_STRIDE + part) * 4;
             uint4 nxt = make_uint4(0, 0, 0, 0);
             if (c0 + lane < c1) nxt = ld_entry(ent + c0 + lane);
             for (int base = c0; base < c1; base += 32) {
-                ebuf[lane] = nxt;
+                sts128(ebuf_s + lane * 16, nxt);
+                const uint32_t fm = __ballot_sync(FULL, (nxt.x & SEG_FLAG) != 0u);
                 __syncwarp();
+                nxt = make_uint4(0, 0, 0, 0);
                 if (base + 32 + lane < c1) nxt = ld_entry(ent + base + 32 + lane);
-                const int m = min(32, c1 - base);
-                for (int g0 = 0; g0 < m; g0 += RED_G) {
-                    const int gm = min(RED_G, m - g0);
-#pragma unroll 2
-                    for (int gi = 0; gi < gm; ++gi) {
-                        const uint4 e = ebuf[g0 + gi];
+#pragma unroll 1
+                for (int g = 0; g < 4; ++g) {
+                    const uint32_t ea = ebuf_s + g * 128;
+                    const uint32_t fg = fm >> (8 * g);
+                    uint32_t tt[RED_G];
+#pragma unroll
+                    for (int i = 0; i < RED_G; ++i) {
+                        const uint2 e = lds64(ea + i * 16 + 8);   // delta bytes + position
                         uint32_t sel[P];
-                        load_sel<K>(col, e.w >> SHIFT, sel);
+                        load_sel<K>(col, e.y >> SHIFT, sel);
+                        uint32_t ti = tbase2;
 #pragma unroll
-                        for (int q = 0; q < P; ++q) rel[q] = __vadd2(rel[q], prmt(e.z, e.w, sel[q]));
-                        double s = 0.0;
-                        int c = 0;
-                        if (e.x & SEG_FLAG) {
-                            uint32_t tt = tbase2;
+                        for (int q = 0; q < P; ++q) {
+                            rel[q] = __vadd2(rel[q], prmt(e.x, e.y, sel[q]));
+                            ti += __vmins2(rel[q], 0x00010001u) * (uint32_t)(TBL_PAT_STRIDE << q);
+                        }
+                        tt[i] = (fg & (1u << i)) ? ti : tzero;
+                    }
+                    if (EPP && small_mask) {   // explicit EPP lists (sorted: the list is in preorder)
 #pragma unroll
-                            for (int q = 0; q < P; ++q) tt += __vmins2(rel[q], 0x00010001u) * (uint32_t)(TBL_PAT_STRIDE << q);
-                            if (p.accumulate) {
-                                const PatEntry a = *reinterpret_cast<const PatEntry*>(smem + (tt & 0xFFFFu));
-                                const PatEntry b = *reinterpret_cast<const PatEntry*>(smem + (tt >> 16));
-                                s = a.w + b.w;
-                                c = a.c + b.c;
-                            }
-                            if (small_mask) {
-                                const uint32_t dd = tt - tbase2;   // per half: pattern * TBL_PAT_STRIDE
-                                const uint32_t hit_lo = ~((dd & 0xFFFFu) / TBL_PAT_STRIDE) & small_lo;
-                                const uint32_t hit_hi = ~((dd >> 16) / TBL_PAT_STRIDE) & small_hi;
-                                if (hit_lo | hit_hi) {  // rare: explicit EPP lists (sorted: the list is in preorder)
+                        for (int i = 0; i < RED_G; ++i) {
+                            const uint32_t dd = tt[i] - tbase2;   // per half: pattern * TBL_PAT_STRIDE
+                            const uint32_t hit_lo = ~((dd & 0xFFFFu) / TBL_PAT_STRIDE) & small_lo;
+                            const uint32_t hit_hi = ~((dd >> 16) / TBL_PAT_STRIDE) & small_hi;
+                            if (hit_lo | hit_hi) {
+                                const uint2 e = lds64(ea + i * 16);   // idx | flag, countable nodes
 #pragma unroll
-                                    for (int q = 0; q < P; ++q) {
-                                        if (hit_lo & (1u << q)) emit_segment(p.epp_nodes, wp[2 * q], e.x & IDX_MASK, e.y, p.mapped);
-                                        if (hit_hi & (1u << q)) emit_segment(p.epp_nodes, wp[2 * q + 1], e.x & IDX_MASK, e.y, p.mapped);
-                                    }
+                                for (int q = 0; q < P; ++q) {
+                                    if (hit_lo & (1u << q)) emit_segment(p.epp_nodes, wp[2 * q], e.x & IDX_MASK, e.y, p.mapped);
+                                    if (hit_hi & (1u << q)) emit_segment(p.epp_nodes, wp[2 * q + 1], e.x & IDX_MASK, e.y, p.mapped);
                                 }
                             }
                         }
-                        if (p.accumulate) {  // stage this lane's partial sums for entry gi
-                            redS[gi * RED_S_STRIDE + lane] = s;
-                            redC[gi * RED_C_STRIDE + lane] = c;
-                        }
                     }
-                    if (p.accumulate) {
-                        // column sums: lane (e = lane/4, part = lane%4) adds 8 of the 32 staged values
-                        __syncwarp();
-                        const int er = lane >> 2, part = lane & 3;
-                        double s = 0.0;
-                        int c = 0;
-                        if (er < gm) {
+                    if (ACC) {
+                        // this lane's partial sums for the 8 entries -> staging, 4 entries at a time
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                s += redS[er * RED_S_STRIDE + part + 4 * k];
-                                c += redC[er * RED_C_STRIDE + part + 4 * k];
+                        for (int h4 = 0; h4 < RED_G; h4 += 4) {
+                            double wa[4], wb[4];
+                            uint32_t ca[4], cb[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint32_t a = tt[h4 + i] & 0xFFFFu, b = tt[h4 + i] >> 16;
+                                wa[i] = lds_f64(a);
+                                ca[i] = lds32(a + 8);
+                                wb[i] = lds_f64(b);
+                                cb[i] = lds32(b + 8);
                             }
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                sts_f64(redS_s + ((h4 + i) * RED_S_STRIDE + lane) * 8, wa[i] + wb[i]);
+                                sts32(redC_s + ((h4 + i) * RED_C_STRIDE + lane) * 4, ca[i] + cb[i]);
+                            }
+                        }
+                        // column sums: lane (er, part) adds 8 of the 32 staged values of entry er
+                        __syncwarp();
+                        double s = 0.0;
+                        uint32_t c = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            s += lds_f64(rS + 4 * k * 8);
+                            c += lds32(rC + 4 * k * 4);
                         }
                         s += __shfl_xor_sync(FULL, s, 1);
                         c += __shfl_xor_sync(FULL, c, 1);
                         s += __shfl_xor_sync(FULL, s, 2);
                         c += __shfl_xor_sync(FULL, c, 2);
-                        if (part == 0 && er < gm) {
-                            if (s != 0.0) atomicAdd(accS + base + g0 + er, s);
-                            if (c != 0) atomicAdd(accC + base + g0 + er, c);
+                        if (part == 0) {   // padded entries stage zeros: nothing is added out of range
+                            if (s != 0.0) atomicAdd(accS + base + g * RED_G + er, s);
+                            if (c != 0) atomicAdd(accC + base + g * RED_G + er, (int)c);
                         }
                         __syncwarp();
                     }
                 }
+                __syncwarp();
             }
         }
     }

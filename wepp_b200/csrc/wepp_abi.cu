@@ -173,21 +173,27 @@ int finalize_plan(wepp_handle* h, wepp_handle::DevPlan& dp) {
     return WEPP_OK;
 }
 
-template <int K>
+template <int K, bool ACC, bool EPP>
 int launch_place(wepp_handle* h, const PlaceParams& pp, int width) {
     PlaceParams p = pp;
     p.smem_per_warp = SMEM_WARP;
     const size_t smem = (size_t)SMEM_CODES + (((size_t)width * 32 * K + 15) & ~(size_t)15);
     if (smem > h->smem_optin || width > MAX_WINDOW)
         return fail(WEPP_E_INVALID, "read window too wide for shared memory (" + std::to_string(width) + " bases)");
-    CU(cudaFuncSetAttribute(place_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(place_kernel<K, ACC, EPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_kernel<K>, PLACE_WARPS * 32, smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_kernel<K, ACC, EPP>, PLACE_WARPS * 32, smem));
     per_sm = std::max(per_sm, 1);
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(p.n_tiles, (int64_t)per_sm * h->n_sms));
-    place_kernel<K><<<grid, PLACE_WARPS * 32, smem, h->stream>>>(p);
+    place_kernel<K, ACC, EPP><<<grid, PLACE_WARPS * 32, smem, h->stream>>>(p);
     CU(cudaGetLastError());
     return WEPP_OK;
+}
+
+template <int K>
+int launch_place_k(wepp_handle* h, const PlaceParams& pp, int width) {
+    if (pp.accumulate) return pp.epp_off ? launch_place<K, true, true>(h, pp, width) : launch_place<K, true, false>(h, pp, width);
+    return launch_place<K, false, true>(h, pp, width);
 }
 
 int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t epp_cap, int64_t epp_capacity) {
@@ -253,9 +259,9 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     CU(cudaEventRecord(h->ev[0], h->stream));
     if (pp.n_tiles > 0) {
         const int k = pl.reads_per_tile / 32;
-        if (k == 8) rc = launch_place<8>(h, pp, pl.max_width);
-        else if (k == 4) rc = launch_place<4>(h, pp, pl.max_width);
-        else rc = launch_place<2>(h, pp, pl.max_width);
+        if (k == 8) rc = launch_place_k<8>(h, pp, pl.max_width);
+        else if (k == 4) rc = launch_place_k<4>(h, pp, pl.max_width);
+        else rc = launch_place_k<2>(h, pp, pl.max_width);
         if (rc) return rc;
         ++launches;
     }
