@@ -144,7 +144,7 @@ struct __align__(16) PatEntry {   // pass-2 pattern table entry
 constexpr int PLACE_WARPS = 8;
 constexpr int RED_G = 8;              // entries reduced together in pass 2
 constexpr int RED_S_STRIDE = 36;      // doubles per staged row: 32 lanes + pad (conflict-free column sums)
-constexpr int RED_C_STRIDE = 33;      // ints per staged row
+constexpr int RED_C_STRIDE = 36;      // ints per staged row (er * 36 + part distinct mod 32: conflict-free column sums)
 constexpr int SMEM_EBUF = 0;                                        // 32 staged entries (512 B)
 constexpr int SMEM_REDS = 512;                                      // double[RED_G][RED_S_STRIDE]
 constexpr int SMEM_REDC = SMEM_REDS + RED_G * RED_S_STRIDE * 8;     // int[RED_G][RED_C_STRIDE]
@@ -374,22 +374,26 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
                 for (int g = 0; g < 4; ++g) {
                     const uint32_t ea = ebuf_s + g * 128;
                     const uint32_t fg = fm >> (8 * g);
+                    // all shared-memory loads of the group are issued before the first branch
+                    uint4 e[8];
+                    uint32_t sel[8][P];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) e[i] = lds128(ea + i * 16);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) load_sel<K>(col, e[i].w >> SHIFT, sel[i]);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        const uint4 e = lds128(ea + i * 16);
-                        uint32_t sel[P];
-                        load_sel<K>(col, e.w >> SHIFT, sel);
 #pragma unroll
-                        for (int q = 0; q < P; ++q) S[q] = __vadd2(S[q], prmt(e.z, e.w, sel[q]));
+                        for (int q = 0; q < P; ++q) S[q] = __vadd2(S[q], prmt(e[i].z, e[i].w, sel[i][q]));
                         if (fg & (1u << i)) {   // warp-uniform: non-empty segment ends here
-                            const int ucnt = (int)e.y;
+                            const int ucnt = (int)e[i].y;
                             uint32_t sum = 0;
 #pragma unroll
                             for (int q = 0; q < P; ++q) {
                                 min_count2(S[q], B[q], cnt[2 * q], cnt[2 * q + 1], ucnt);
                                 sum += B[q];
                             }
-                            if (__any_sync(FULL, sum != bsum)) {  // rare: some read reached a new strict minimum here
+                            if (sum != bsum) {  // rare: some read reached a new strict minimum here
 #pragma unroll
                                 for (int q = 0; q < P; ++q) {   // oB = minima before this entry (they only change here)
                                     if ((S[q] & 0xFFFFu) < (oB[q] & 0xFFFFu)) cnt[2 * q] = ucnt;
