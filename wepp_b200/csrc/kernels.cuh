@@ -599,20 +599,20 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
                         // this lane's partial sums for the 8 entries -> staging, 4 entries at a time
 #pragma unroll
                         for (int h4 = 0; h4 < RED_G; h4 += 4) {
-                            double wa[4], wb[4];
-                            uint32_t ca[4], cb[4];
+                            // one 16-byte load per lookup: a quarter-warp covers all 32 banks (the 8+4-byte
+                            // pair of loads on this 16-byte stride would be 4-way conflicted)
+                            uint4 pa[4], pb[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                const uint32_t a = tt[h4 + i] & 0xFFFFu, b = tt[h4 + i] >> 16;
-                                wa[i] = lds_f64(a);
-                                ca[i] = lds32(a + 8);
-                                wb[i] = lds_f64(b);
-                                cb[i] = lds32(b + 8);
+                                pa[i] = lds128(tt[h4 + i] & 0xFFFFu);
+                                pb[i] = lds128(tt[h4 + i] >> 16);
                             }
 #pragma unroll
                             for (int i = 0; i < 4; ++i) {
-                                sts_f64(redS_s + ((h4 + i) * RED_S_STRIDE + lane) * 8, wa[i] + wb[i]);
-                                sts32(redC_s + ((h4 + i) * RED_C_STRIDE + lane) * 4, ca[i] + cb[i]);
+                                const double wa = __hiloint2double((int)pa[i].y, (int)pa[i].x);
+                                const double wb = __hiloint2double((int)pb[i].y, (int)pb[i].x);
+                                sts_f64(redS_s + ((h4 + i) * RED_S_STRIDE + lane) * 8, wa + wb);
+                                sts32(redC_s + ((h4 + i) * RED_C_STRIDE + lane) * 4, pa[i].z + pb[i].z);
                             }
                         }
                         // column sums: lane (er, part) adds 8 of the 32 staged values of entry er
