@@ -1,9 +1,10 @@
 """numpy emulation of the device algorithm on the HOST-built Euler stripes (test infrastructure).
 
-Checks the product's host logic — signed-delta tables, enter/exit entries, stripe grouping —
-against the oracle without a GPU: per read, gather the stripes its window covers, order by
-preorder index, prefix-sum the deltas selected by the read's allele code, take the min over
-non-empty segments and count unmapped nodes in the argmin segments.
+Checks the product's host logic — signed-delta tables, boundary (enter/exit) and point (leaf)
+entries, stripe grouping — against the oracle without a GPU: per read, gather the stripes its
+window covers, order by sort key, prefix-sum the boundary deltas selected by the read's allele
+code (the state every node inherits), add each leaf's point deltas to that leaf only, take the
+min over nodes and count the unmapped nodes attaining it.
 """
 from __future__ import annotations
 
@@ -66,14 +67,15 @@ def emulate_place(arena, reads, mapped=None, q: int = 32):
             code[p] = CODE[int(c)]
         seed = int(sum(1 for c in reads.rm_nuc[a:b] if c != 15))
         delta = d[np.arange(en.shape[0]), code[en[:, 1]]].astype(np.int64)
-        run = np.concatenate([[seed], seed + np.cumsum(delta)])
-        idx = np.concatenate([[0], en[:, 0].astype(np.int64), [n]])
-        length = idx[1:] - idx[:-1]
-        ok = length > 0
-        m = run[ok].min()
-        sel = ok & (run == m)
-        cnt = (length - (mpre[idx[1:]] - mpre[idx[:-1]]))[sel].sum()
-        best[r], mult[r] = m, cnt
-        nodes = np.concatenate([np.arange(a0, b0) for a0, b0 in zip(idx[:-1][sel], idx[1:][sel])]) if sel.any() else np.zeros(0, np.int64)
-        epps.append(nodes[~mapped[nodes]])
+        idx = (en[:, 0] >> 1).astype(np.int64)
+        point = (en[:, 0] & 1).astype(bool)
+        # boundary entries: difference array over nodes; point entries: that leaf only
+        diff = np.zeros(n + 1, np.int64)
+        np.add.at(diff, idx[~point], delta[~point])
+        score = seed + np.cumsum(diff[:n])
+        np.add.at(score, idx[point], delta[point])
+        m = score.min()
+        nodes = np.flatnonzero((score == m) & ~mapped)
+        best[r], mult[r] = m, nodes.size
+        epps.append(nodes)
     return best, mult, epps

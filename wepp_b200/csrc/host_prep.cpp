@@ -36,7 +36,7 @@ std::string build_euler_stripes(int32_t n_nodes, const int32_t* parent, const in
                                 const int32_t* mut_pos, const uint8_t* mut_ref, const uint8_t* mut_nuc,
                                 int32_t genome_size, int32_t stripe_width, EulerStripes& out) {
     if (n_nodes < 1) return "arena has no nodes";
-    if (n_nodes >= (1 << 30)) return "arena too large (n_nodes must be < 2^30)";
+    if (n_nodes >= (1 << 28)) return "arena too large (n_nodes must be < 2^28)";
     if (genome_size < NUM_RANGE_BINS) return "genome_size must be >= 50";
     if (stripe_width < 1) return "stripe_width must be >= 1";
     if (parent[0] != -1) return "parent[0] must be -1";
@@ -103,20 +103,27 @@ std::string build_euler_stripes(int32_t n_nodes, const int32_t* parent, const in
             }
             if (!any) continue;  // event changes nothing for any read: drop
             ++n_events;
-            raw.push_back(Entry{(uint32_t)v, (uint32_t)mut_pos[k], pack4(d), (uint32_t)(uint8_t)(int8_t)d[4]});
+            if (sub_end[v] == v + 1) {
+                // leaf: one POINT entry — node v's own score is the enclosing state plus this delta;
+                // the running prefix is not changed, so no EXIT entry is needed
+                raw.push_back(Entry{((uint32_t)v << 1) | 1u, (uint32_t)mut_pos[k], pack4(d), (uint32_t)(uint8_t)(int8_t)d[4]});
+                continue;
+            }
+            raw.push_back(Entry{(uint32_t)v << 1, (uint32_t)mut_pos[k], pack4(d), (uint32_t)(uint8_t)(int8_t)d[4]});
             if (sub_end[v] < n_nodes) {
                 int nd[5];
                 for (int c = 0; c < 5; ++c) nd[c] = -d[c];
-                raw.push_back(Entry{(uint32_t)sub_end[v], (uint32_t)mut_pos[k], pack4(nd), (uint32_t)(uint8_t)(int8_t)nd[4]});
+                raw.push_back(Entry{(uint32_t)sub_end[v] << 1, (uint32_t)mut_pos[k], pack4(nd), (uint32_t)(uint8_t)(int8_t)nd[4]});
             }
         }
     }
-    // pass 1: stable counting sort by idx
+    // pass 1: stable counting sort by key = (idx << 1 | point): at one preorder index the
+    // boundary entries (exits of subtrees ending here, the node's own enters) precede its point entries
     std::vector<Entry> by_idx(raw.size());
     {
-        std::vector<int64_t> cnt((size_t)n_nodes + 1, 0);
+        std::vector<int64_t> cnt((size_t)2 * n_nodes + 1, 0);
         for (const Entry& e : raw) ++cnt[e.x + 1];
-        for (int32_t v = 0; v < n_nodes; ++v) cnt[v + 1] += cnt[v];
+        for (int64_t v = 0; v < (int64_t)2 * n_nodes; ++v) cnt[v + 1] += cnt[v];
         for (const Entry& e : raw) by_idx[cnt[e.x]++] = e;
     }
     raw.clear();

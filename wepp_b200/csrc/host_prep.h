@@ -19,11 +19,17 @@
 namespace wepp {
 
 // Device/host shared 16-byte Euler entry.
-//  master (stripe) form : x = preorder idx, y = absolute position, z = delta bytes for codes
-//                         0..3 (ref,A,C,G), w = byte0 delta for code 4 (T), other bytes 0.
-//  bucket-list form     : x = idx | (segment non-empty ? 1u<<31 : 0), y = countable nodes in
-//                         the segment [idx, next idx), z as above, w = byte0 delta T,
-//                         byte1 = 0 (code 5: N / outside), bytes 2..3 = position - bucket start.
+//  master (stripe) form : x = sort key (preorder idx << 1 | point), y = absolute position, z = delta
+//                         bytes for codes 0..3 (ref,A,C,G), w = byte0 delta for code 4 (T), other bytes 0.
+//                         A BOUNDARY entry (point = 0) changes the running prefix from its index on: an
+//                         event of an internal node v is an ENTER at v and an EXIT (negated) at v's
+//                         subtree end.  A POINT entry (point = 1) is an event of a leaf v: v's own score
+//                         is the running prefix plus the deltas of v's point entries; the prefix itself
+//                         is untouched, so leaves cost one entry per event instead of two.
+//  bucket-list form     : x = idx | flags (ENT_EVAL, ENT_POINT, ENT_SKIP, see kernels.cuh), y = countable
+//                         nodes evaluated at this entry (point entries: bits 8.. = preceding entries of
+//                         the same leaf), z as above, w = byte0 delta T, byte1 = 0 (code 5: N / outside),
+//                         bytes 2..3 = position - bucket start.
 struct Entry {
     uint32_t x, y, z, w;
 };

@@ -1,25 +1,29 @@
 // kernels.cuh — sm_100a kernels of the placement path.
 //
 // Data layout in HBM (all built by wepp_set_arena / wepp_set_reads):
-//   stripes      Entry[2E']   Euler entries of all events, grouped by genome stripe
-//                              (pos / stripe_width), preorder index ascending inside a stripe
+//   stripes      Entry[]      Euler entries of all events, grouped by genome stripe
+//                              (pos / stripe_width), sort key ascending inside a stripe.  An event of
+//                              an internal node is a BOUNDARY pair (ENTER at the node, EXIT at its
+//                              subtree end); an event of a leaf is ONE POINT entry (host_prep.h)
 //   lists        Entry[]      one Euler list per distinct read-window stripe range: the k-way
-//                              merge (by preorder index) of the stripes it covers, entry 0 = a
-//                              dummy at index 0; each entry carries its segment's node count
+//                              merge (by key) of the stripes it covers, entry 0 = a dummy boundary
+//                              at index 0; each evaluated entry carries its countable-node count
+//   prev_boundary int32[]     per list entry: the boundary entry whose state encloses it
+//   chunk_start  int32[][W+1] per list: the W scan chunks (each starts on a boundary entry)
 //   reads        SoA          start/end/degree + sparse (pos, code) mutations, bucket-sorted
-//   accS/accC    double/int32 per bucket, per list segment: sum of read weights / degrees whose
-//                              EPP set contains the segment
+//   accS/accC    double/int32 per bucket, per list entry: sum of read weights / degrees whose
+//                              EPP set contains the entry's nodes
 //   diff_lo/hi   uint64[N+1]  128-bit fixed-point difference array for the per-node score
 //   counts       int32[(N+1)*50]  difference array, scanned in place into the result
 //
 // Kernels (reference lines they replace in src/WEPP/initial_filter.cpp):
 //   build_lists_kernel / finalize_lists_kernel   per-window Euler CSR (replaces the range trees,
 //                                                 arena.cpp:68-169)
-//   place_kernel<K>        K1 signed delta (:59-87) + K2 Euler prefix sum (:101-104) + K3
+//   place_kernel<K,ACC,EPP> K1 signed delta (:59-87) + K2 Euler prefix sum (:101-104) + K3
 //                          min / multiplicity / EPP emission (:89-99, :126-134) + K3'
-//                          per-segment weight accumulation (:167-177); one warp = one tile of
-//                          32*K reads in lock step over the list, K reads per lane
-//   expand_kernel + scan kernels   segment accumulators -> per-node score / counts (:199-211)
+//                          per-entry weight accumulation (:167-177); one CTA = one tile of
+//                          32*K reads, its warps split the list, K reads per lane
+//   expand_kernel + scan kernels   entry accumulators -> per-node score / counts (:199-211)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,14 +32,21 @@
 
 namespace wepp {
 
-constexpr uint32_t IDX_MASK = 0x3FFFFFFFu;
-constexpr uint32_t SEG_FLAG = 0x80000000u;
+// bucket-list form of Entry::x
+constexpr uint32_t IDX_MASK = 0x0FFFFFFFu;   // preorder index (n_nodes < 2^28)
+constexpr uint32_t ENT_EVAL = 0x80000000u;   // scores are evaluated here: a boundary entry that owns >= 1 node, or
+                                             // the last point entry of a leaf
+constexpr uint32_t ENT_POINT = 0x40000000u;  // point entry (leaf event)
+constexpr uint32_t ENT_SKIP = 0x20000000u;   // point entry that is not the last of its leaf: applied to the running
+                                             // prefix like a boundary entry and undone once the leaf is evaluated
+constexpr uint32_t KEY_MASK = IDX_MASK | ENT_POINT;
 constexpr int NBINS = 50;
 constexpr int FIX_SHIFT = 80;  // score fixed point: value * 2^80 in a signed 128-bit integer
 
 struct PlaceParams {
     const Entry* lists;
     const ListDesc* list_desc;
+    const int32_t* chunk_start;   // [n_lists][PLACE_WARPS + 1]
     const BucketDesc* buckets;
     const TileDesc* tiles;
     int32_t n_tiles;
@@ -110,8 +121,8 @@ constexpr uint32_t BEST_NONE = 0x3FFFu;
 constexpr uint32_t BEST_NONE2 = 0x3FFF3FFFu;
 constexpr int MAX_WINDOW = 4000;   // widest bucket the 16-bit halves are sized for (|score| < S_BIAS)
 
-// One pair of reads at one non-empty segment (initial_filter.cpp:89-99): b = min(s, b) per half,
-// and where s <= b the segment's countable nodes are added to the read's node count (a strict
+// One pair of reads at one evaluated entry (initial_filter.cpp:89-99): b = min(s, b) per half,
+// and where s <= b the entry's countable nodes are added to the read's node count (a strict
 // decrease is repaired by the caller).  VIMNMX.S16x2 with two predicate outputs + two predicated adds.
 __device__ __forceinline__ void min_count2(uint32_t s, uint32_t& b, int& c_lo, int& c_hi, int ucnt) {
     asm("{\n\t"
@@ -136,10 +147,10 @@ struct __align__(16) PatEntry {   // pass-2 pattern table entry
 };
 
 // Shared-memory layout of place_kernel (one CTA = one tile of 32*K reads, PLACE_WARPS warps).
-//   per warp : 32 staged entries (512 B) + pass-2 reduction staging (double[8][36] + int[8][33])
+//   per warp : 32 staged entries (512 B) + pass-2 reduction staging (double[8][36] + int[8][36])
 //   per CTA  : tile id, EPP write bases, pattern tables, the read-allele selector table
 // The per-warp staging areas double as the exchange buffer for the chunk summaries between
-// pass 1 and pass 2.  The pattern tables must lie below 64 KB (their byte offsets are carried
+// pass 1 and pass 2.  The pattern tables must lie below 64 KB (their addresses are carried
 // in 16-bit halves).
 constexpr int PLACE_WARPS = 8;
 constexpr int RED_G = 8;              // entries reduced together in pass 2
@@ -162,8 +173,8 @@ __device__ __forceinline__ uint4 ld_entry(const Entry* p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// List construction: rank-by-binary-search k-way merge of the stripes a list covers.
-// grid = (chunks, n_lists), one thread per source entry.
+// List construction: rank-by-binary-search k-way merge of the stripes a list covers (stable in
+// (key, stripe) order).  grid = (chunks, n_lists), one thread per source entry.
 __global__ void build_lists_kernel(const Entry* __restrict__ stripes, const int64_t* __restrict__ stripe_off,
                                    const ListDesc* __restrict__ list_desc, Entry* __restrict__ out, int q) {
     const ListDesc ld = list_desc[blockIdx.y];
@@ -179,7 +190,7 @@ __global__ void build_lists_kernel(const Entry* __restrict__ stripes, const int6
             if (t == s) continue;
             int64_t lo = stripe_off[t], hi = stripe_off[t + 1];
             const int64_t base = lo;
-            // stripes before mine: count idx <= mine; after mine: count idx < mine
+            // stripes before mine: count key <= mine; after mine: count key < mine
             const uint32_t key = t < s ? e.x + 1u : e.x;
             while (lo < hi) {
                 const int64_t mid = (lo + hi) >> 1;
@@ -188,7 +199,7 @@ __global__ void build_lists_kernel(const Entry* __restrict__ stripes, const int6
             rank += lo - base;
         }
         Entry o;
-        o.x = e.x;
+        o.x = (e.x >> 1) | ((e.x & 1u) ? ENT_POINT : 0u);
         o.y = 0;
         o.z = e.z;
         o.w = (e.w & 0xFFu) | ((e.y - (uint32_t)ld.b0) << 16);
@@ -196,33 +207,77 @@ __global__ void build_lists_kernel(const Entry* __restrict__ stripes, const int6
     }
 }
 
-// Segment lengths and countable-node counts.  grid = (chunks, n_lists).
-__global__ void finalize_lists_kernel(Entry* __restrict__ lists, const ListDesc* __restrict__ list_desc,
-                                      int n_nodes, const int32_t* __restrict__ mapped_prefix) {
+// Entry kinds, countable-node counts, enclosing boundary entries and scan chunks.
+// grid = (chunks, n_lists).  Threads only ever change the ENT_EVAL / ENT_SKIP bits of x, and
+// neighbours read x through KEY_MASK, so the kernel can be re-run in place when `mapped` changes.
+//   boundary entry i : owns the nodes of [idx_i, idx of the next boundary entry) that are not
+//                      evaluated by point entries in between; y = how many of them are not mapped
+//   point entries    : the last one of a leaf evaluates the leaf (y = 1 - mapped | earlier entries
+//                      of the same leaf << 8); earlier ones are ENT_SKIP
+constexpr int FIN_THREADS = 256;
+
+__global__ void finalize_lists_kernel(Entry* __restrict__ lists, const ListDesc* __restrict__ list_desc, int n_nodes,
+                                      const uint8_t* __restrict__ mapped, const int32_t* __restrict__ mapped_prefix,
+                                      int32_t* __restrict__ prev_boundary, int32_t* __restrict__ chunk_start) {
     const ListDesc ld = list_desc[blockIdx.y];
     Entry* e = lists + ld.off;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ld.n; i += gridDim.x * blockDim.x) {
-        const uint32_t idx = e[i].x & IDX_MASK;
-        const uint32_t nxt = (i + 1 < ld.n) ? (e[i + 1].x & IDX_MASK) : (uint32_t)n_nodes;
-        const uint32_t len = nxt - idx;
-        uint32_t ucnt = len;
-        if (mapped_prefix) ucnt -= (uint32_t)(mapped_prefix[nxt] - mapped_prefix[idx]);
-        e[i].y = ucnt;
-        e[i].x = idx | (len ? SEG_FLAG : 0u);
+    int32_t* pb = prev_boundary + ld.off;
+    const int n = ld.n;
+    if (blockIdx.x == 0 && threadIdx.x <= PLACE_WARPS) {
+        // chunk k nominally starts at k * ceil(n / W); moved forward to a boundary entry so that a
+        // boundary entry and the point entries it encloses are scanned by one warp
+        const int k = threadIdx.x;
+        const int cs = (n + PLACE_WARPS - 1) / PLACE_WARPS;
+        int c = k == PLACE_WARPS ? n : min(n, k * cs);
+        while (c < n && (e[c].x & ENT_POINT)) ++c;
+        chunk_start[blockIdx.y * (PLACE_WARPS + 1) + k] = c;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t x = e[i].x & KEY_MASK;
+        const uint32_t idx = x & IDX_MASK;
+        if (!(x & ENT_POINT)) {
+            int j = i + 1, pts = 0, mpts = 0;
+            while (j < n) {
+                const uint32_t xj = e[j].x & KEY_MASK;
+                if (!(xj & ENT_POINT)) break;
+                const bool last = (j + 1 == n) || ((e[j + 1].x & KEY_MASK) != xj);
+                if (last) {
+                    ++pts;
+                    if (mapped) mpts += mapped[xj & IDX_MASK];
+                }
+                pb[j] = i;
+                ++j;
+            }
+            const uint32_t nidx = j < n ? (e[j].x & IDX_MASK) : (uint32_t)n_nodes;
+            const int own = (int)(nidx - idx) - pts;
+            int ucnt = own;
+            if (mapped_prefix) ucnt -= (mapped_prefix[nidx] - mapped_prefix[idx]) - mpts;
+            int b = i - 1;
+            while (b >= 0 && (e[b].x & ENT_POINT)) --b;
+            pb[i] = b;
+            e[i].y = (uint32_t)ucnt;
+            e[i].x = x | (own > 0 ? ENT_EVAL : 0u);
+        } else {
+            const bool last = (i + 1 == n) || ((e[i + 1].x & KEY_MASK) != x);
+            if (last) {
+                int g = 0;
+                while (i - g - 1 >= 0 && (e[i - g - 1].x & KEY_MASK) == x) ++g;
+                e[i].y = ((mapped && mapped[idx]) ? 0u : 1u) | ((uint32_t)g << 8);
+                e[i].x = x | ENT_EVAL;
+            } else {
+                e[i].y = 0u;
+                e[i].x = x | ENT_SKIP;
+            }
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Out-of-line (rare) EPP list emission: nodes of one argmin segment that are not mapped.
-__device__ __noinline__ void emit_segment(int32_t* __restrict__ out, unsigned long long& wp, uint32_t v, uint32_t u,
-                                          const uint8_t* __restrict__ mapped) {
-    while (u) {
-        if (!mapped || !mapped[v]) {
-            out[wp++] = (int32_t)v;
-            --u;
-        }
-        ++v;
-    }
+// Out-of-line (rare) EPP list emission: nodes of [a, b) that are not mapped.
+__device__ __noinline__ void emit_range(int32_t* __restrict__ out, unsigned long long& wp, uint32_t a, uint32_t b,
+                                        const uint8_t* __restrict__ mapped) {
+    for (uint32_t v = a; v < b; ++v)
+        if (!mapped || !mapped[v]) out[wp++] = (int32_t)v;
 }
 
 // ---- shared-window load/store helpers (32-bit shared addresses; immediate offsets fold into LDS/STS) ----
@@ -252,22 +307,53 @@ __device__ __forceinline__ void sts128(uint32_t a, uint4 v) {
 __device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v)); }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
 
+// Pass-1 state of one lane: K reads as K/2 packed pairs.
+template <int K>
+struct Pass1 {
+    static constexpr int P = K / 2;
+    uint32_t S[P];    // running prefix (biased), boundary entries only
+    uint32_t B[P];    // running minima
+    uint32_t oB[P];   // minima before the last strict decrease (they only change when one happens)
+    uint32_t bsum;    // sum of B: changes iff some minimum strictly decreased
+    int cnt[K];       // countable nodes at the running minimum
+
+    // scores X are evaluated for ucnt countable nodes (initial_filter.cpp:89-99)
+    __device__ __forceinline__ void eval(const uint32_t (&X)[P], int ucnt) {
+        uint32_t sum = 0;
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            min_count2(X[q], B[q], cnt[2 * q], cnt[2 * q + 1], ucnt);
+            sum += B[q];
+        }
+        if (sum != bsum) {  // rare: some read reached a new strict minimum here
+#pragma unroll
+            for (int q = 0; q < P; ++q) {
+                if ((X[q] & 0xFFFFu) < (oB[q] & 0xFFFFu)) cnt[2 * q] = ucnt;
+                if ((X[q] >> 16) < (oB[q] >> 16)) cnt[2 * q + 1] = ucnt;
+                oB[q] = B[q];
+            }
+            bsum = sum;
+        }
+    }
+};
+
 // The placement kernel.  Persistent CTAs; each CTA pulls tiles (32*K reads of one window bucket)
 // from a global counter.  The CTA's PLACE_WARPS warps share the tile's selector table and each
-// scans one contiguous chunk of the bucket's Euler list for ALL reads of the tile (lane = K
-// reads held as K/2 packed s16x2 registers), a two-level Euler-tour scan:
+// scans one chunk of the bucket's Euler list for ALL reads of the tile (lane = K reads held as
+// K/2 packed s16x2 registers), a two-level Euler-tour scan:
 //   pass 1  per chunk: sum of deltas, min prefix, node count at the min  -> shared memory
 //           per entry and pair of reads: PRMT (signed delta pair) + VIADD.16x2 (prefix sum) +
 //           VIMNMX.S16x2 with its two predicates (running min, "<= min") + two predicated adds
 //           (node count); a strict decrease of any minimum is caught once per entry by comparing
 //           the sum of the packed minima and repaired out of line.
 //   combine every warp folds the chunk summaries: global min, multiplicity, its own start offset
-//   pass 2  per chunk: segments attaining the min -> weight/degree sums into the segment
-//           accumulators (staged through shared memory, one atomic per segment per tile) and
+//   pass 2  per chunk: entries attaining the min -> weight/degree sums into the entry
+//           accumulators (staged through shared memory, one atomic per entry per tile) and
 //           explicit EPP lists for reads under the cache cap.
-// Entries are staged 32 at a time through shared memory (zero entries pad the chunk's tail: a
-// zero entry changes nothing and is never a segment end), so both passes run branch-free over
-// whole batches.  ACC = accumulate per-segment weights (wepp_place); EPP = emit explicit lists.
+// A boundary entry moves the running prefix; a point entry (leaf event) is evaluated as prefix +
+// delta and leaves the prefix alone.  Entries are staged 32 at a time through shared memory (zero
+// entries pad the chunk's tail: a zero entry is a boundary entry that changes nothing and is never
+// evaluated).  ACC = accumulate per-entry weights (wepp_place); EPP = emit explicit lists.
 template <int K, bool ACC, bool EPP>
 __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceParams p) {
     using ST = typename Sel<K>::type;
@@ -305,9 +391,9 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
         const ListDesc ld = p.list_desc[bd.list];
         const Entry* ent = p.lists + ld.off;
         const int n = ld.n;
-        // this warp's chunk of the list (multiple of 32 entries)
-        const int cs = (((n + PLACE_WARPS - 1) / PLACE_WARPS) + 31) & ~31;
-        const int c0 = min(n, warp * cs), c1 = min(n, c0 + cs);
+        // this warp's chunk of the list (starts on a boundary entry)
+        const int c0 = p.chunk_start[bd.list * (PLACE_WARPS + 1) + warp];
+        const int c1 = p.chunk_start[bd.list * (PLACE_WARPS + 1) + warp + 1];
 
         // ---- read tile -> shared selector table -------------------------------------------------
         int run0[K];
@@ -353,54 +439,76 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
         // ---- pass 1: chunk-relative prefix sum of signed deltas, min prefix and its node count ----
         int run[K], best[K], cnt[K];
         {
-            uint32_t S[P], B[P], oB[P];
-            uint32_t bsum = (uint32_t)P * BEST_NONE2;
+            Pass1<K> st;
+            st.bsum = (uint32_t)P * BEST_NONE2;
 #pragma unroll
             for (int q = 0; q < P; ++q) {
-                S[q] = S_BIAS2;
-                B[q] = oB[q] = BEST_NONE2;
+                st.S[q] = S_BIAS2;
+                st.B[q] = st.oB[q] = BEST_NONE2;
             }
 #pragma unroll
-            for (int j = 0; j < K; ++j) cnt[j] = 0;
+            for (int j = 0; j < K; ++j) st.cnt[j] = 0;
             uint4 nxt = make_uint4(0, 0, 0, 0);
             if (c0 + lane < c1) nxt = ld_entry(ent + c0 + lane);
             for (int base = c0; base < c1; base += 32) {
                 sts128(ebuf_s + lane * 16, nxt);
-                const uint32_t fm = __ballot_sync(FULL, (nxt.x & SEG_FLAG) != 0u);  // segment ends of this batch
+                const bool is_p = (nxt.x & (ENT_EVAL | ENT_POINT)) == (ENT_EVAL | ENT_POINT);
+                const uint32_t em = __ballot_sync(FULL, (nxt.x & ENT_EVAL) != 0u);   // evaluated entries of this batch
+                const uint32_t pm = __ballot_sync(FULL, is_p);                       // ... of which leaf evaluations
+                const uint32_t mm = __ballot_sync(FULL, is_p && (nxt.y >> 8) != 0u); // ... of multi-event leaves
                 __syncwarp();
                 nxt = make_uint4(0, 0, 0, 0);
                 if (base + 32 + lane < c1) nxt = ld_entry(ent + base + 32 + lane);
 #pragma unroll 1
                 for (int g = 0; g < 4; ++g) {
                     const uint32_t ea = ebuf_s + g * 128;
-                    const uint32_t fg = fm >> (8 * g);
-                    // all shared-memory loads of the group are issued before the first branch
-                    uint4 e[8];
-                    uint32_t sel[8][P];
+                    const uint32_t eg = em >> (8 * g), pg = pm >> (8 * g);
+                    if (((mm >> (8 * g)) & 0xFFu) == 0u) {
+                        // all shared-memory loads of the group are issued before the first branch
+                        uint4 e[8];
+                        uint32_t sel[8][P];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) e[i] = lds128(ea + i * 16);
+                        for (int i = 0; i < 8; ++i) e[i] = lds128(ea + i * 16);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) load_sel<K>(col, e[i].w >> SHIFT, sel[i]);
+                        for (int i = 0; i < 8; ++i) load_sel<K>(col, e[i].w >> SHIFT, sel[i]);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                        for (int i = 0; i < 8; ++i) {
+                            if (pg & (1u << i)) {          // warp-uniform: a leaf is evaluated, the prefix stays
+                                uint32_t X[P];
 #pragma unroll
-                        for (int q = 0; q < P; ++q) S[q] = __vadd2(S[q], prmt(e[i].z, e[i].w, sel[i][q]));
-                        if (fg & (1u << i)) {   // warp-uniform: non-empty segment ends here
-                            const int ucnt = (int)e[i].y;
-                            uint32_t sum = 0;
+                                for (int q = 0; q < P; ++q) X[q] = __vadd2(st.S[q], prmt(e[i].z, e[i].w, sel[i][q]));
+                                st.eval(X, (int)(e[i].y & 0xFFu));
+                            } else {
 #pragma unroll
-                            for (int q = 0; q < P; ++q) {
-                                min_count2(S[q], B[q], cnt[2 * q], cnt[2 * q + 1], ucnt);
-                                sum += B[q];
+                                for (int q = 0; q < P; ++q) st.S[q] = __vadd2(st.S[q], prmt(e[i].z, e[i].w, sel[i][q]));
+                                if (eg & (1u << i)) st.eval(st.S, (int)e[i].y);
                             }
-                            if (sum != bsum) {  // rare: some read reached a new strict minimum here
+                        }
+                    } else {
+                        // rare: the group holds a leaf with several events in this window.  Its earlier
+                        // point entries were applied to the prefix; after the evaluation they are undone.
+#pragma unroll 1
+                        for (int i = 0; i < 8; ++i) {
+                            const uint4 e = lds128(ea + i * 16);
+                            uint32_t sel[P];
+                            load_sel<K>(col, e.w >> SHIFT, sel);
+                            if (pg & (1u << i)) {
+                                uint32_t X[P];
 #pragma unroll
-                                for (int q = 0; q < P; ++q) {   // oB = minima before this entry (they only change here)
-                                    if ((S[q] & 0xFFFFu) < (oB[q] & 0xFFFFu)) cnt[2 * q] = ucnt;
-                                    if ((S[q] >> 16) < (oB[q] >> 16)) cnt[2 * q + 1] = ucnt;
-                                    oB[q] = B[q];
+                                for (int q = 0; q < P; ++q) X[q] = __vadd2(st.S[q], prmt(e.z, e.w, sel[q]));
+                                st.eval(X, (int)(e.y & 0xFFu));
+                                const int64_t at = (int64_t)base + g * 8 + i;
+                                for (int k = 1; k <= (int)(e.y >> 8); ++k) {
+                                    const uint4 u = ld_entry(ent + at - k);
+                                    uint32_t us[P];
+                                    load_sel<K>(col, u.w >> SHIFT, us);
+#pragma unroll
+                                    for (int q = 0; q < P; ++q) st.S[q] = __vsub2(st.S[q], prmt(u.z, u.w, us[q]));
                                 }
-                                bsum = sum;
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < P; ++q) st.S[q] = __vadd2(st.S[q], prmt(e.z, e.w, sel[q]));
+                                if (eg & (1u << i)) st.eval(st.S, (int)e.y);
                             }
                         }
                     }
@@ -409,12 +517,14 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
             }
 #pragma unroll
             for (int q = 0; q < P; ++q) {
-                run[2 * q] = (int)(S[q] & 0xFFFFu) - (int)S_BIAS;
-                run[2 * q + 1] = (int)(S[q] >> 16) - (int)S_BIAS;
-                const uint32_t bl = B[q] & 0xFFFFu, bh = B[q] >> 16;
+                run[2 * q] = (int)(st.S[q] & 0xFFFFu) - (int)S_BIAS;
+                run[2 * q + 1] = (int)(st.S[q] >> 16) - (int)S_BIAS;
+                const uint32_t bl = st.B[q] & 0xFFFFu, bh = st.B[q] >> 16;
                 best[2 * q] = bl == BEST_NONE ? 0x3FFFFFFF : (int)bl - (int)S_BIAS;
                 best[2 * q + 1] = bh == BEST_NONE ? 0x3FFFFFFF : (int)bh - (int)S_BIAS;
             }
+#pragma unroll
+            for (int j = 0; j < K; ++j) cnt[j] = st.cnt[j];
         }
         // ---- exchange chunk summaries, fold them ------------------------------------------------
         __syncthreads();  // all warps are done with their staging areas
@@ -536,13 +646,14 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
         }
         __syncthreads();
 
-        // ---- pass 2: which segments attain the min -> weights into the segment accumulators,
+        // ---- pass 2: which entries attain the min -> weights into the entry accumulators,
         //      EPP node lists for reads under the cache cap.  rel = running score - min >= 0 at
-        //      every non-empty segment, so min(rel, 1) is the read's NOT-at-min bit. ---------------
+        //      every evaluated entry, so min(rel, 1) is the read's NOT-at-min bit. ------------------
         double* accS = p.accS + bd.acc_off;
         int32_t* accC = p.accC + bd.acc_off;
         uint32_t rel[P];
         uint32_t small_lo = 0, small_hi = 0;
+        uint32_t enc_lo = 0, enc_hi = 0;   // EPP: reads at their min in the enclosing boundary entry's state
 #pragma unroll
         for (int q = 0; q < P; ++q) {
             rel[q] = ((uint32_t)(run[2 * q] - best[2 * q]) & 0xFFFFu) | ((uint32_t)(run[2 * q + 1] - best[2 * q + 1]) << 16);
@@ -557,40 +668,92 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
             if (c0 + lane < c1) nxt = ld_entry(ent + c0 + lane);
             for (int base = c0; base < c1; base += 32) {
                 sts128(ebuf_s + lane * 16, nxt);
-                const uint32_t fm = __ballot_sync(FULL, (nxt.x & SEG_FLAG) != 0u);
+                const bool is_p = (nxt.x & (ENT_EVAL | ENT_POINT)) == (ENT_EVAL | ENT_POINT);
+                const uint32_t em = __ballot_sync(FULL, (nxt.x & ENT_EVAL) != 0u);
+                const uint32_t pm = __ballot_sync(FULL, is_p);
+                const uint32_t mm = __ballot_sync(FULL, is_p && (nxt.y >> 8) != 0u);
+                const uint32_t qm = EPP ? __ballot_sync(FULL, (nxt.x & ENT_POINT) != 0u) : 0u;   // any point entry
                 __syncwarp();
                 nxt = make_uint4(0, 0, 0, 0);
                 if (base + 32 + lane < c1) nxt = ld_entry(ent + base + 32 + lane);
 #pragma unroll 1
                 for (int g = 0; g < 4; ++g) {
                     const uint32_t ea = ebuf_s + g * 128;
-                    const uint32_t fg = fm >> (8 * g);
+                    const uint32_t eg = em >> (8 * g), pg = pm >> (8 * g);
                     uint32_t tt[RED_G];
-#pragma unroll
-                    for (int i = 0; i < RED_G; ++i) {
-                        const uint2 e = lds64(ea + i * 16 + 8);   // delta bytes + position
-                        uint32_t sel[P];
-                        load_sel<K>(col, e.y >> SHIFT, sel);
-                        uint32_t ti = tbase2;
-#pragma unroll
-                        for (int q = 0; q < P; ++q) {
-                            rel[q] = __vadd2(rel[q], prmt(e.x, e.y, sel[q]));
-                            ti += __vmins2(rel[q], 0x00010001u) * (uint32_t)(TBL_PAT_STRIDE << q);
-                        }
-                        tt[i] = (fg & (1u << i)) ? ti : tzero;
-                    }
-                    if (EPP && small_mask) {   // explicit EPP lists (sorted: the list is in preorder)
+                    if (((mm >> (8 * g)) & 0xFFu) == 0u) {
 #pragma unroll
                         for (int i = 0; i < RED_G; ++i) {
-                            const uint32_t dd = tt[i] - tbase2;   // per half: pattern * TBL_PAT_STRIDE
+                            const uint2 e = lds64(ea + i * 16 + 8);   // delta bytes + position
+                            uint32_t sel[P];
+                            load_sel<K>(col, e.y >> SHIFT, sel);
+                            uint32_t ti = tbase2;
+                            const bool pt = (pg & (1u << i)) != 0u;
+#pragma unroll
+                            for (int q = 0; q < P; ++q) {
+                                const uint32_t x = __vadd2(rel[q], prmt(e.x, e.y, sel[q]));
+                                ti += __vmins2(x, 0x00010001u) * (uint32_t)(TBL_PAT_STRIDE << q);
+                                rel[q] = pt ? rel[q] : x;   // a leaf evaluation leaves the prefix alone
+                            }
+                            tt[i] = (eg & (1u << i)) ? ti : tzero;
+                        }
+                    } else {
+                        // rare: a leaf with several events in this window (see pass 1)
+#pragma unroll
+                        for (int i = 0; i < RED_G; ++i) {
+                            const uint4 e = lds128(ea + i * 16);
+                            uint32_t sel[P];
+                            load_sel<K>(col, e.w >> SHIFT, sel);
+                            uint32_t ti = tbase2;
+                            const bool pt = (pg & (1u << i)) != 0u;
+#pragma unroll
+                            for (int q = 0; q < P; ++q) {
+                                const uint32_t x = __vadd2(rel[q], prmt(e.z, e.w, sel[q]));
+                                ti += __vmins2(x, 0x00010001u) * (uint32_t)(TBL_PAT_STRIDE << q);
+                                rel[q] = pt ? rel[q] : x;
+                            }
+                            tt[i] = (eg & (1u << i)) ? ti : tzero;
+                            if (pt && (e.y >> 8) != 0u) {
+                                const int64_t at = (int64_t)base + g * 8 + i;
+                                for (int k = 1; k <= (int)(e.y >> 8); ++k) {
+                                    const uint4 u = ld_entry(ent + at - k);
+                                    uint32_t us[P];
+                                    load_sel<K>(col, u.w >> SHIFT, us);
+#pragma unroll
+                                    for (int q = 0; q < P; ++q) rel[q] = __vsub2(rel[q], prmt(u.z, u.w, us[q]));
+                                }
+                            }
+                        }
+                    }
+                    if (EPP && small_mask) {   // explicit EPP lists (sorted: the list is in preorder)
+#pragma unroll 1
+                        for (int i = 0; i < RED_G; ++i) {
+                            uint32_t tti = tt[0];
+#pragma unroll
+                            for (int k = 1; k < RED_G; ++k) tti = (i == k) ? tt[k] : tti;
+                            const uint32_t dd = tti - tbase2;   // per half: pattern * TBL_PAT_STRIDE
                             const uint32_t hit_lo = ~((dd & 0xFFFFu) / TBL_PAT_STRIDE) & small_lo;
                             const uint32_t hit_hi = ~((dd >> 16) / TBL_PAT_STRIDE) & small_hi;
-                            if (hit_lo | hit_hi) {
-                                const uint2 e = lds64(ea + i * 16);   // idx | flag, countable nodes
+                            const bool any_point = ((qm >> (8 * g + i)) & 1u) != 0u;
+                            if (!any_point) {   // boundary entry: its state encloses the following point entries
+                                enc_lo = hit_lo;
+                                enc_hi = hit_hi;
+                            }
+                            if (hit_lo | hit_hi | (any_point ? (enc_lo | enc_hi) : 0u)) {
+                                const int64_t at = (int64_t)base + g * 8 + i;
+                                const uint32_t v = __ldg(&ent[at].x) & IDX_MASK;
+                                const uint32_t vn = at + 1 < n ? (__ldg(&ent[at + 1].x) & IDX_MASK) : (uint32_t)p.n_nodes;
 #pragma unroll
                                 for (int q = 0; q < P; ++q) {
-                                    if (hit_lo & (1u << q)) emit_segment(p.epp_nodes, wp[2 * q], e.x & IDX_MASK, e.y, p.mapped);
-                                    if (hit_hi & (1u << q)) emit_segment(p.epp_nodes, wp[2 * q + 1], e.x & IDX_MASK, e.y, p.mapped);
+                                    if (!any_point) {
+                                        if (hit_lo & (1u << q)) emit_range(p.epp_nodes, wp[2 * q], v, vn, p.mapped);
+                                        if (hit_hi & (1u << q)) emit_range(p.epp_nodes, wp[2 * q + 1], v, vn, p.mapped);
+                                    } else {   // the leaf itself, then the enclosing state's nodes up to the next entry
+                                        if (hit_lo & (1u << q)) emit_range(p.epp_nodes, wp[2 * q], v, v + 1, p.mapped);
+                                        if (enc_lo & (1u << q)) emit_range(p.epp_nodes, wp[2 * q], v + 1, vn, p.mapped);
+                                        if (hit_hi & (1u << q)) emit_range(p.epp_nodes, wp[2 * q + 1], v, v + 1, p.mapped);
+                                        if (enc_hi & (1u << q)) emit_range(p.epp_nodes, wp[2 * q + 1], v + 1, vn, p.mapped);
+                                    }
                                 }
                             }
                         }
@@ -642,7 +805,10 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
 }
 
 // ---------------------------------------------------------------------------------------------
-// Segment accumulators -> per-node difference arrays.  grid = (chunks, n_buckets).
+// Entry accumulators -> per-node difference arrays.  grid = (chunks, n_buckets).
+//   boundary entry: its nodes' value differs from the previous boundary entry's by (cur - prv)
+//                   from its index on (an entry that owns no node has value 0);
+//   point entry   : the leaf's value differs from the enclosing boundary entry's at exactly one node.
 __device__ __forceinline__ void dbl_to_fix(double d, unsigned long long& lo, long long& hi) {
     lo = 0;
     hi = 0;
@@ -672,19 +838,25 @@ __device__ __forceinline__ void atomic_add128(unsigned long long* dlo, unsigned 
 }
 
 __global__ void expand_kernel(const Entry* __restrict__ lists, const ListDesc* __restrict__ list_desc,
-                              const BucketDesc* __restrict__ buckets, const double* __restrict__ accS,
-                              const int32_t* __restrict__ accC, unsigned long long* __restrict__ diff_lo,
-                              unsigned long long* __restrict__ diff_hi, int32_t* __restrict__ counts) {
+                              const BucketDesc* __restrict__ buckets, const int32_t* __restrict__ prev_boundary,
+                              const double* __restrict__ accS, const int32_t* __restrict__ accC,
+                              unsigned long long* __restrict__ diff_lo, unsigned long long* __restrict__ diff_hi,
+                              int32_t* __restrict__ counts) {
     const BucketDesc bd = buckets[blockIdx.y];
     const ListDesc ld = list_desc[bd.list];
     const Entry* e = lists + ld.off;
+    const int32_t* pb = prev_boundary + ld.off;
     const double* s = accS + bd.acc_off;
     const int32_t* c = accC + bd.acc_off;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ld.n; i += gridDim.x * blockDim.x) {
-        const double cur = s[i], prv = i ? s[i - 1] : 0.0;
-        const int32_t ccur = c[i], cprv = i ? c[i - 1] : 0;
+        const uint32_t x = __ldg(&e[i].x);
+        if (x & ENT_SKIP) continue;
+        const int pi = pb[i];
+        const double cur = s[i], prv = pi >= 0 ? s[pi] : 0.0;
+        const int32_t ccur = c[i], cprv = pi >= 0 ? c[pi] : 0;
         if (cur == prv && ccur == cprv) continue;
-        const uint32_t idx = __ldg(&e[i].x) & IDX_MASK;
+        const uint32_t idx = x & IDX_MASK;
+        const bool point = (x & ENT_POINT) != 0u;
         if (cur != prv) {
             unsigned long long alo, blo;
             long long ahi, bhi;
@@ -693,8 +865,16 @@ __global__ void expand_kernel(const Entry* __restrict__ lists, const ListDesc* _
             const unsigned long long lo = alo - blo;
             const long long hi = ahi - bhi - (alo < blo ? 1 : 0);
             atomic_add128(diff_lo + idx, diff_hi + idx, lo, hi);
+            if (point) {   // back to the enclosing value right after the leaf
+                const unsigned long long nlo = 0ull - lo;
+                const long long nhi = ~hi + (lo == 0ull ? 1 : 0);
+                atomic_add128(diff_lo + idx + 1, diff_hi + idx + 1, nlo, nhi);
+            }
         }
-        if (ccur != cprv) atomicAdd(counts + (size_t)idx * NBINS + bd.bin, ccur - cprv);
+        if (ccur != cprv) {
+            atomicAdd(counts + (size_t)idx * NBINS + bd.bin, ccur - cprv);
+            if (point) atomicAdd(counts + (size_t)(idx + 1) * NBINS + bd.bin, cprv - ccur);
+        }
     }
 }
 

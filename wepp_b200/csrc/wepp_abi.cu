@@ -98,10 +98,13 @@ struct wepp_handle {
         DevBuf<BucketDesc> buckets;
         DevBuf<TileDesc> tiles;
         DevBuf<Entry> entries;
+        DevBuf<int32_t> prev_boundary;   // per list entry: enclosing / previous boundary entry
+        DevBuf<int32_t> chunk_start;     // [n_lists][PLACE_WARPS + 1]
         bool final_for_mask = false;
         void release() {
             start.release(); end.release(); degree.release(); rm_pos.release(); rm_off.release(); perm.release();
             rm_code.release(); lists.release(); buckets.release(); tiles.release(); entries.release();
+            prev_boundary.release(); chunk_start.release();
         }
     };
     DevPlan full, sub;
@@ -149,6 +152,8 @@ int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp) {
     CU(upload(dp.buckets, pl.buckets, h->stream));
     CU(upload(dp.tiles, pl.tiles, h->stream));
     CU(dp.entries.ensure((size_t)pl.list_entries_total));
+    CU(dp.prev_boundary.ensure((size_t)pl.list_entries_total));
+    CU(dp.chunk_start.ensure(pl.lists.size() * (PLACE_WARPS + 1)));
     if (!pl.lists.empty()) {
         int max_n = 0;
         for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
@@ -166,8 +171,10 @@ int finalize_plan(wepp_handle* h, wepp_handle::DevPlan& dp) {
     int max_n = 0;
     for (const ListDesc& l : dp.plan.lists) max_n = std::max(max_n, l.n);
     dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)dp.plan.lists.size());
-    finalize_lists_kernel<<<grid, 256, 0, h->stream>>>(dp.entries.p, dp.lists.p, h->n_nodes,
-                                                       h->has_mask ? h->d_mapped_prefix.p : nullptr);
+    finalize_lists_kernel<<<grid, FIN_THREADS, 0, h->stream>>>(dp.entries.p, dp.lists.p, h->n_nodes,
+                                                               h->has_mask ? h->d_mapped.p : nullptr,
+                                                               h->has_mask ? h->d_mapped_prefix.p : nullptr,
+                                                               dp.prev_boundary.p, dp.chunk_start.p);
     CU(cudaGetLastError());
     dp.final_for_mask = true;
     return WEPP_OK;
@@ -232,6 +239,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     PlaceParams pp = {};
     pp.lists = dp.entries.p;
     pp.list_desc = dp.lists.p;
+    pp.chunk_start = dp.chunk_start.p;
     pp.buckets = dp.buckets.p;
     pp.tiles = dp.tiles.p;
     pp.n_tiles = (int32_t)pl.tiles.size();
@@ -271,8 +279,9 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
             int max_n = 0;
             for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
             dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
-            expand_kernel<<<grid, 256, 0, h->stream>>>(dp.entries.p, dp.lists.p, dp.buckets.p, h->d_accS.p,
-                                                       h->d_accC.p, h->d_diff_lo.p, h->d_diff_hi.p, h->d_counts.p);
+            expand_kernel<<<grid, 256, 0, h->stream>>>(dp.entries.p, dp.lists.p, dp.buckets.p, dp.prev_boundary.p,
+                                                       h->d_accS.p, h->d_accC.p, h->d_diff_lo.p, h->d_diff_hi.p,
+                                                       h->d_counts.p);
             CU(cudaGetLastError());
             ++launches;
         }
