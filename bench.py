@@ -273,40 +273,57 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     value = reads_total / (ms_per_step / 1e3)
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------
-    e2e = None
+    # One reference-facing cartesian_map per step: host reads in (packing, H2D, per-window Euler
+    # lists), placement, NCCL merge, results out to pinned host memory.  "e2e" returns what the
+    # reference's later stages read (per-read min parsimony / multiplicity, per-node score and
+    # dist_divergence); "e2e_full_counts" also brings back the 200-byte-per-node
+    # mapped_read_counts matrix that the reference keeps in haplotype but never reads again.
+    e2e = e2e_full = None
     if not args.no_e2e:
         n, r = arena.n_nodes, reads.n_reads
         mp = torch.empty(r, dtype=torch.int32, pin_memory=True).numpy()
         mu = torch.empty(r, dtype=torch.int32, pin_memory=True).numpy()
         sc = torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
+        dv = torch.empty(n, dtype=torch.float64, pin_memory=True).numpy()
         ct = torch.empty((n, 50), dtype=torch.int32, pin_memory=True).numpy()
         from wepp_b200._lib import check, ptr
 
-        def e2e_step():
+        def e2e_step(full: bool):
             p.set_reads(reads)          # host packing + H2D + per-window Euler list build
             p.set_mapped(None)
             p.place(0, 0, sync=False)
             allreduce_nodes()
             check(p.lib.wepp_get_read_results(p.h, ptr(mp), ptr(mu)))
             if rank == 0 or world == 1:
-                check(p.lib.wepp_get_node_results(p.h, ptr(sc), ptr(ct)))
+                if full:
+                    check(p.lib.wepp_get_node_results(p.h, ptr(sc), ptr(ct)))
+                else:
+                    check(p.lib.wepp_get_node_summary(p.h, ptr(sc), ptr(dv)))
 
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        k_e2e = max(1, min(args.steps, 3))
-        for _ in range(k_e2e):
-            e2e_step()
-        barrier()
-        dt = (time.perf_counter() - t0) / k_e2e
-        if world > 1:
-            t = torch.tensor([dt], device=f"cuda:{dev}")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        def time_e2e(full: bool):
+            e2e_step(full)
+            barrier()
+            t0 = time.perf_counter()
+            k_e2e = max(1, min(args.steps, 3))
+            for _ in range(k_e2e):
+                e2e_step(full)
+            barrier()
+            dt = (time.perf_counter() - t0) / k_e2e
+            if world > 1:
+                t = torch.tensor([dt], device=f"cuda:{dev}")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return dt
+
         h2d = int(r * (12 + 8 + 8) + reads.rm_pos.shape[0] * 5 + st["n_tiles"] * 16 + st["n_lists"] * 32)
-        d2h = int(r * 8 + n * (8 + 200))
-        e2e = {"value": reads_total / dt, "unit": "reads/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-               "ms_per_step": dt * 1e3}
+        dt = time_e2e(False)
+        e2e = {"value": reads_total / dt, "unit": "reads/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(r * 8 + n * 16), "ms_per_step": dt * 1e3,
+               "outputs": "max_parsimony, multiplicity per read; score, dist_divergence per node"}
+        dt = time_e2e(True)
+        e2e_full = {"value": reads_total / dt, "unit": "reads/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(r * 8 + n * (8 + 200)), "ms_per_step": dt * 1e3,
+                    "outputs": "as e2e, with mapped_read_counts[N][50] instead of dist_divergence"}
 
     if rank != 0:
         return
@@ -315,13 +332,24 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # algorithmic bytes of the placement kernel alone: two passes over each tile's Euler list
     # (16-B entries), one 12-B accumulator update per (tile, entry), packed reads in, results out
     alg = (st["scanned_entries"] * (16 * 2 + 12) + reads.n_reads * (12 + 8 + 8 + 8) + reads.rm_pos.shape[0] * 5)
-    traffic = None
+    # ncu counters of the same kernel on the same workload (profiles/traffic.json, captured with
+    # `ncu --set full`): DRAM bytes, executed warp instructions and shared-memory wavefronts per
+    # launch.  Divided by the live kernel time they say which unit the kernel is actually bound by.
+    traffic, bottleneck = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         try:
             tj = json.load(open(tpath))
             if tj.get("nodes") == arena.n_nodes and tj.get("reads_per_gpu") == reads.n_reads:
                 traffic = tj.get("dram_bytes_per_launch")
+                sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+                cyc = k_ms * 1e-3 * sm_hz * 1e6
+                bottleneck = {
+                    "issue_slots_frac": tj["warp_instructions_per_launch"] / (cyc * 148 * 4),
+                    "smem_wavefronts_frac": tj["smem_wavefronts_per_launch"] / (cyc * 148),
+                    "source": tj.get("source"),
+                    "note": "fractions of the SM issue rate (1 warp-instruction/cycle/sub-partition) and of the "
+                            "shared-memory pipe (1 wavefront/cycle/SM) at the live kernel time"}
         except Exception:
             pass
     achieved = alg / (k_ms / 1e3) / 1e9
@@ -331,11 +359,14 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config_dict(arena, reads, args),
         "read_x_node_scores_per_s": value * arena.n_nodes,
         "touched_read_entries_per_s": st["scanned_read_entries"] * 2 * world / (ms_per_step / 1e3),
-        "e2e": e2e, "gpu_launches": int(st["kernel_launches"] * args.steps),
+        "e2e": e2e, "e2e_full_counts": e2e_full, "gpu_launches": int(st["kernel_launches"] * args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "place_kernel", "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": int(alg), "peak_source": peak_src,
-                     "note": "issue-bound tile scan: lists are L2-resident, see DESIGN.md"},
+                     "note": "not HBM-bound: the per-window Euler lists are L2-resident and every tile re-reads them; "
+                             "the kernel is co-limited by warp-instruction issue and shared-memory wavefronts "
+                             "(see bottleneck and DESIGN.md section 3)",
+                     "bottleneck": bottleneck},
         "clocks": clocks,
         "setup_s": {"flatten_tree": t_arena, "pack_reads_and_build_lists": t_reads},
         "stats": {k: st[k] for k in ("n_tiles", "n_lists", "n_buckets", "reads_per_tile", "stripe_width",

@@ -104,6 +104,14 @@ int wepp_get_read_results(wepp_handle* h, int32_t* max_parsimony, int32_t* multi
 int wepp_get_node_results(wepp_handle* h, double* score, int32_t* counts);
 int wepp_get_epp(wepp_handle* h, int64_t* epp_off, int32_t* epp_nodes, int64_t capacity, int64_t* n_epp);
 
+/* What the later stages actually read from the per-node state: score[N] and dist_divergence[N]
+ * (src/WEPP/initial_filter.cpp:214-231 — the share of the 50 read-count bins in which the node
+ * collects more than READ_DIST_FACTOR_THRESHOLD = 0.5 % of the sample's degree-weighted reads,
+ * arena::read_counts(), src/WEPP/arena.cpp:138-151).  Computed on the device from the counts
+ * matrix, so the 200-byte-per-node matrix itself need not cross PCIe (mapped_read_counts has no
+ * reader after cartesian_map in the reference).  Either pointer may be NULL.  */
+int wepp_get_node_summary(wepp_handle* h, double* score, double* dist_divergence);
+
 /* The whole reference call in one go with host buffers in and out
  * (set_reads + set_mapped + place + get_*): what the cgo/ctypes/C++ binding calls.  */
 int wepp_cartesian_map(wepp_handle* h, int64_t n_reads, const int32_t* start, const int32_t* end,

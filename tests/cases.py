@@ -74,3 +74,42 @@ def small_case(seed: int = 7, n_nodes: int = 3000, n_reads: int = 700, genome: i
     reads = synth.make_reads(arena, n_reads, seed, amplicons=amps, read_len=100, jitter=8, n_templates=50,
                              err=0.01, n_rate=0.02)
     return arena, reads
+
+
+def star_case(seed: int = 0, n_leaves: int = 900, genome: int = 400, n_reads: int = 120):
+    """A few internal nodes with hundreds of leaf children each, 1-3 events per leaf inside a
+    small genome: long runs of point entries (some leaves with several events in one window)
+    between boundary entries, so scan chunks must be cut at boundary entries."""
+    rng = np.random.default_rng(seed)
+    ref = np.zeros(genome + 1, np.uint8)
+    ref[1:] = synth.ONE_HOT[rng.integers(0, 4, genome)]
+    parent = [-1]
+    hubs = [0]
+    n_hubs = 4
+    per = n_leaves // n_hubs
+    for h in range(n_hubs):
+        if h > 0:
+            parent.append(hubs[int(rng.integers(0, len(hubs)))] if rng.random() < 0.5 else 0)
+            # preorder needs the parent on the rightmost path: attach to the root or the previous hub chain
+            parent[-1] = 0
+            hubs.append(len(parent) - 1)
+        hub = hubs[-1]
+        for _ in range(per):
+            parent.append(hub)
+    parent = np.array(parent, np.int32)
+    n_nodes = parent.shape[0]
+    pos_l, ref_l, nuc_l, off = [], [], [], [0]
+    for v in range(n_nodes):
+        k = int(rng.integers(1, 4)) if v > 0 else 0
+        ps = np.sort(rng.choice(np.arange(1, genome + 1), size=k, replace=False))
+        for p in ps:
+            alts = [int(c) for c in synth.ONE_HOT if c != ref[p]]
+            pos_l.append(int(p)); ref_l.append(int(ref[p])); nuc_l.append(alts[int(rng.integers(0, 3))])
+        off.append(len(pos_l))
+    arena = Arena(genome, ref, parent, np.array(off, np.int64), np.array(pos_l, np.int32),
+                  np.array(ref_l, np.uint8), np.array(nuc_l, np.uint8))
+    amps = synth.amplicon_scheme(genome, 3, 150, 200, seed)
+    reads = synth.make_reads(arena, n_reads, seed, amplicons=amps, read_len=120, jitter=6, n_templates=40,
+                             err=0.01, n_rate=0.02)
+    mapped = (rng.random(n_nodes) < 0.15).astype(np.uint8)
+    return arena, reads, mapped

@@ -56,6 +56,14 @@ def test_small_case_with_mask_and_cap():
     _check(arena, reads, mapped, 32, 0, epp_cap=64)
 
 
+@pytest.mark.parametrize("seed,k", [(0, 8), (1, 0), (2, 2)])
+def test_star_tree_long_point_runs(seed, k):
+    """Polytomies: hundreds of consecutive leaf (point) entries, multi-event leaves, mask, EPP lists."""
+    arena, reads, mapped = cases.star_case(seed)
+    _check(arena, reads, None, 32, k)
+    _check(arena, reads, mapped, 16, k, epp_cap=200)
+
+
 def test_empty_and_ragged_inputs():
     arena, reads = cases.small_case(seed=3, n_reads=70)
     # zero reads
@@ -135,6 +143,11 @@ def test_cartesian_map_host_call_and_filter_mirror():
     off, nodes = f.epp_positions_cache
     assert np.array_equal(off, o["epp_off"]) and np.array_equal(nodes, o["epp_nodes"])
     assert f.dist_divergence.shape == (arena.n_nodes,)
+    # the device-side summary (wepp_get_node_summary) restates initial_filter.cpp:214-231 exactly
+    sc2, dv = p.node_summary()
+    assert np.array_equal(sc2, f.score)
+    assert np.array_equal(dv, f.dist_divergence)
+    assert 0.0 < dv.max() <= 1.0
     p.close()
 
 

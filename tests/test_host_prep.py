@@ -37,6 +37,32 @@ def test_emulated_scan_matches_oracle_small():
         assert np.array_equal(epps[r], o["epp_nodes"][o["epp_off"][r]:o["epp_off"][r + 1]])
 
 
+def test_emulated_scan_matches_oracle_star_tree():
+    arena, reads, mapped = cases.star_case(1)
+    for m in (None, mapped):
+        o = oracle.cartesian_map(arena, reads, m, n_threads=4, epp_cap=arena.n_nodes)
+        best, mult, epps = emulate.emulate_place(arena, reads, m, q=16)
+        assert np.array_equal(best, o["max_parsimony"])
+        assert np.array_equal(mult, o["multiplicity"])
+        for r in range(0, reads.n_reads, 7):
+            assert np.array_equal(epps[r], o["epp_nodes"][o["epp_off"][r]:o["epp_off"][r + 1]])
+
+
+def test_leaf_events_are_single_point_entries():
+    """A leaf's event is one POINT entry (key bit 0 set) at the leaf's index; an internal node's event is
+    an ENTER/EXIT boundary pair."""
+    arena, _, _ = cases.star_case(2)
+    ent, off = emulate.host_stripes(arena, 16)
+    n = arena.n_nodes
+    children = np.bincount(arena.parent[1:], minlength=n)
+    point = (ent[:, 0] & 1).astype(bool)
+    idx = (ent[:, 0] >> 1).astype(np.int64)
+    assert np.all(children[idx[point]] == 0)
+    n_leaf_events = int(np.diff(arena.mut_off)[children == 0].sum())
+    assert int(point.sum()) <= n_leaf_events and int(point.sum()) > 0.9 * n_leaf_events
+    assert ent.shape[0] < 2 * int(arena.mut_off[-1])
+
+
 def test_stripes_are_grouped_and_sorted():
     arena, _ = cases.small_case()
     ent, off = emulate.host_stripes(arena, 32)

@@ -46,6 +46,7 @@ SIGNATURES = {
     "wepp_place_subset": (C.c_int, [VP, C.c_int64, VP, C.c_int32, C.c_int64]),
     "wepp_get_read_results": (C.c_int, [VP, VP, VP]),
     "wepp_get_node_results": (C.c_int, [VP, VP, VP]),
+    "wepp_get_node_summary": (C.c_int, [VP, VP, VP]),
     "wepp_get_epp": (C.c_int, [VP, VP, VP, C.c_int64, C.POINTER(C.c_int64)]),
     "wepp_cartesian_map": (C.c_int, [VP, C.c_int64] + [VP] * 11),
     "wepp_rescore": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, C.c_int64]),

@@ -18,7 +18,7 @@ ORACLE_LIB = os.path.join(ROOT, "oracle", "libwepp_oracle.so")
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libwepp_ref.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O3", "-shared"]
+              "-Xcompiler", "-fPIC,-O3,-pthread", "-shared"]
 
 
 def _newer(target: str, sources: list[str]) -> bool:

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <unordered_map>
 
 namespace wepp {
@@ -143,6 +144,25 @@ std::string build_euler_stripes(int32_t n_nodes, const int32_t* parent, const in
     return "";
 }
 
+// Blocked-range parallel loop over [0, n) on the host (the reference uses TBB for its loaders).
+template <typename F>
+static void parallel_for(int64_t n, F&& body) {
+    int nt = (int)std::min<int64_t>(std::max(1u, std::thread::hardware_concurrency()), 32);
+    if (n < (1 << 15)) nt = 1;
+    if (nt == 1) {
+        body(0, n, 0);
+        return;
+    }
+    std::vector<std::thread> th;
+    const int64_t step = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        const int64_t a = t * step, b = std::min(n, a + step);
+        if (a >= b) break;
+        th.emplace_back([&, a, b, t] { body(a, b, t); });
+    }
+    for (auto& x : th) x.join();
+}
+
 std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t n_reads, const int32_t* start,
                             const int32_t* end, const int32_t* degree, const int64_t* rm_off, const int32_t* rm_pos,
                             const uint8_t* rm_nuc, int32_t reads_per_lane, const int64_t* subset, int64_t n_subset,
@@ -153,33 +173,58 @@ std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t
     out = ReadPlan();
     out.n_reads = n_sel;
 
-    // bucket key per selected read
+    // validation and window keys, in parallel
     std::vector<int32_t> bucket_of((size_t)n_sel);
-    std::unordered_map<uint64_t, int32_t> bucket_id, list_id;
+    std::vector<int32_t> key_qs((size_t)n_sel), key_qe((size_t)n_sel);
+    std::vector<uint8_t> key_bin((size_t)n_sel);
+    std::vector<const char*> errs(64, nullptr);
+    parallel_for(n_sel, [&](int64_t a, int64_t b, int t) {
+        for (int64_t i = a; i < b; ++i) {
+            const int64_t r = subset ? subset[i] : i;
+            if (r < 0 || r >= n_reads) { errs[t] = "read index out of range"; return; }
+            const int32_t s = start[r], e = end[r];
+            if (s < 1 || s > genome_size || e > genome_size || e < s - 1) {
+                errs[t] = "read window must satisfy 1 <= start <= genome_size, start-1 <= end <= genome_size";
+                return;
+            }
+            if (degree[r] < 0) { errs[t] = "read degree must be >= 0"; return; }
+            if (rm_off[r + 1] < rm_off[r]) { errs[t] = "rm_off must be non-decreasing"; return; }
+            int32_t prev = s - 1;
+            for (int64_t k = rm_off[r]; k < rm_off[r + 1]; ++k) {
+                if (rm_pos[k] <= prev || rm_pos[k] > e) {
+                    errs[t] = "read mutations must be sorted, unique and inside [start,end]";
+                    return;
+                }
+                prev = rm_pos[k];
+                const uint8_t c = rm_nuc[k];
+                if (!(c == 1 || c == 2 || c == 4 || c == 8 || c == 15)) {
+                    errs[t] = "read allele code must be one of 1,2,4,8,15";
+                    return;
+                }
+            }
+            key_qs[i] = s / q;
+            key_qe[i] = std::max(e, s) / q;
+            key_bin[i] = (uint8_t)std::min(s / bin_size, NUM_RANGE_BINS - 1);
+        }
+    });
+    for (const char* e : errs)
+        if (e) return e;
+
+    // list and bucket ids in first-appearance order (flat tables: one short vector of (qe, list) per qs)
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> lists_of_qs((size_t)es.n_stripes + 1);
+    std::vector<int32_t> bucket_id;   // [list * NUM_RANGE_BINS + bin]
     std::vector<int64_t> bucket_count;
     for (int64_t i = 0; i < n_sel; ++i) {
-        const int64_t r = subset ? subset[i] : i;
-        if (r < 0 || r >= n_reads) return "read index out of range";
-        const int32_t s = start[r], e = end[r];
-        if (s < 1 || s > genome_size || e > genome_size || e < s - 1)
-            return "read window must satisfy 1 <= start <= genome_size, start-1 <= end <= genome_size";
-        if (degree[r] < 0) return "read degree must be >= 0";
-        if (rm_off[r + 1] < rm_off[r]) return "rm_off must be non-decreasing";
-        int32_t prev = s - 1;
-        for (int64_t k = rm_off[r]; k < rm_off[r + 1]; ++k) {
-            if (rm_pos[k] <= prev || rm_pos[k] > e) return "read mutations must be sorted, unique and inside [start,end]";
-            prev = rm_pos[k];
-            const uint8_t c = rm_nuc[k];
-            if (!(c == 1 || c == 2 || c == 4 || c == 8 || c == 15)) return "read allele code must be one of 1,2,4,8,15";
-        }
-        const int32_t qs = s / q, qe = std::max(e, s) / q;
-        const int32_t bin = std::min(s / bin_size, NUM_RANGE_BINS - 1);
-        const uint64_t lkey = ((uint64_t)qs << 32) | (uint32_t)qe;
-        auto li = list_id.find(lkey);
-        int32_t l;
-        if (li == list_id.end()) {
+        const int32_t qs = key_qs[i], qe = key_qe[i];
+        int32_t l = -1;
+        for (const auto& pr : lists_of_qs[qs])
+            if (pr.first == qe) {
+                l = pr.second;
+                break;
+            }
+        if (l < 0) {
             l = (int32_t)out.lists.size();
-            list_id.emplace(lkey, l);
+            lists_of_qs[qs].emplace_back(qe, l);
             ListDesc ld;
             ld.qs = qs;
             ld.qe = qe;
@@ -189,19 +234,13 @@ std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t
             ld.off = 0;
             ld.pad = 0;
             out.lists.push_back(ld);
-        } else {
-            l = li->second;
+            bucket_id.resize(out.lists.size() * NUM_RANGE_BINS, -1);
         }
-        const uint64_t bkey = ((uint64_t)l << 8) | (uint32_t)bin;
-        auto bi = bucket_id.find(bkey);
-        int32_t b;
-        if (bi == bucket_id.end()) {
+        int32_t& b = bucket_id[(size_t)l * NUM_RANGE_BINS + key_bin[i]];
+        if (b < 0) {
             b = (int32_t)out.buckets.size();
-            bucket_id.emplace(bkey, b);
-            out.buckets.push_back(BucketDesc{0, l, bin});
+            out.buckets.push_back(BucketDesc{0, l, (int32_t)key_bin[i]});
             bucket_count.push_back(0);
-        } else {
-            b = bi->second;
         }
         bucket_of[i] = b;
         ++bucket_count[b];
@@ -256,22 +295,24 @@ std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t
     out.rm_off.assign((size_t)n_sel + 1, 0);
     for (int64_t i = 0; i < n_sel; ++i) {
         const int64_t r = out.perm[i];
-        out.start[i] = start[r];
-        out.end[i] = end[r];
-        out.degree[i] = degree[r];
         out.rm_off[i + 1] = out.rm_off[i] + (rm_off[r + 1] - rm_off[r]);
     }
     out.rm_pos.resize((size_t)out.rm_off[n_sel]);
     out.rm_code.resize((size_t)out.rm_off[n_sel]);
-    for (int64_t i = 0; i < n_sel; ++i) {
-        const int64_t r = out.perm[i];
-        int64_t o = out.rm_off[i];
-        for (int64_t kk = rm_off[r]; kk < rm_off[r + 1]; ++kk, ++o) {
-            out.rm_pos[o] = rm_pos[kk];
-            const uint8_t c = rm_nuc[kk];
-            out.rm_code[o] = c == 1 ? 1 : c == 2 ? 2 : c == 4 ? 3 : c == 8 ? 4 : 5;
+    parallel_for(n_sel, [&](int64_t a, int64_t b, int) {
+        for (int64_t i = a; i < b; ++i) {
+            const int64_t r = out.perm[i];
+            out.start[i] = start[r];
+            out.end[i] = end[r];
+            out.degree[i] = degree[r];
+            int64_t o = out.rm_off[i];
+            for (int64_t kk = rm_off[r]; kk < rm_off[r + 1]; ++kk, ++o) {
+                out.rm_pos[o] = rm_pos[kk];
+                const uint8_t c = rm_nuc[kk];
+                out.rm_code[o] = c == 1 ? 1 : c == 2 ? 2 : c == 4 ? 3 : c == 8 ? 4 : 5;
+            }
         }
-    }
+    });
     // tiles, longest lists first (LPT order for the persistent-warp scheduler)
     for (size_t b = 0; b < nb; ++b) {
         const int64_t c = bucket_count[b];

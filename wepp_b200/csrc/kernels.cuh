@@ -1026,4 +1026,24 @@ __global__ void __launch_bounds__(64) counts_apply_kernel(int32_t* __restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// dist_divergence (initial_filter.cpp:214-231): the share of read-count bins in which the node
+// collects more than READ_DIST_FACTOR_THRESHOLD of the sample's reads.  One thread per node.
+struct BinCounts {
+    int32_t v[NBINS];
+};
+__global__ void divergence_kernel(const int32_t* __restrict__ counts, int n, BinCounts true_counts, int bins_active,
+                                  double threshold, double* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int32_t* row = counts + (size_t)v * NBINS;
+    int divergence = 0;
+#pragma unroll 10
+    for (int j = 0; j < NBINS; ++j) {
+        const double proportion = (double)row[j] / (double)true_counts.v[j];   // 0/0 = NaN compares false, as on the host
+        divergence += proportion > threshold;
+    }
+    out[v] = (double)divergence / (double)bins_active;
+}
+
 }  // namespace wepp

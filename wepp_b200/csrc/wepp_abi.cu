@@ -113,8 +113,9 @@ struct wepp_handle {
     DevBuf<double> d_accS;
     DevBuf<int32_t> d_accC;
     DevBuf<int32_t> d_maxpars, d_mult;
-    DevBuf<double> d_score;
+    DevBuf<double> d_score, d_divergence;
     DevBuf<int32_t> d_counts;
+    int32_t true_counts[NBINS] = {};   // arena::true_read_counts, src/WEPP/arena.cpp:138-151
     DevBuf<unsigned long long> d_diff_lo, d_diff_hi;
     DevBuf<U128> d_chunk128;
     DevBuf<int32_t> d_cchunk_tot, d_cchunk_off;
@@ -381,7 +382,7 @@ void wepp_destroy(wepp_handle* h) {
     h->d_stripes.release(); h->d_stripe_off.release(); h->d_mapped.release(); h->d_mapped_prefix.release();
     h->full.release(); h->sub.release();
     h->d_accS.release(); h->d_accC.release(); h->d_maxpars.release(); h->d_mult.release(); h->d_score.release();
-    h->d_counts.release(); h->d_diff_lo.release(); h->d_diff_hi.release(); h->d_chunk128.release();
+    h->d_counts.release(); h->d_divergence.release(); h->d_diff_lo.release(); h->d_diff_hi.release(); h->d_chunk128.release();
     h->d_cchunk_tot.release(); h->d_cchunk_off.release(); h->d_epp_off.release(); h->d_epp_nodes.release();
     h->d_epp_total.release(); h->d_tile_counter.release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
@@ -447,6 +448,12 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
     const int64_t nm = rm_off[n_reads];
     h->r_pos.assign(rm_pos, rm_pos + nm);
     h->r_nuc.assign(rm_nuc, rm_nuc + nm);
+    {   // degree-weighted reads per start bin (arena.cpp:138-151)
+        const int32_t bin_size = h->genome / NBINS;
+        int64_t tc[NBINS] = {};
+        for (int64_t r = 0; r < n_reads; ++r) tc[std::min(start[r] / bin_size, NBINS - 1)] += degree[r];
+        for (int j = 0; j < NBINS; ++j) h->true_counts[j] = (int32_t)tc[j];
+    }
     int rc = upload_plan(h, h->full);
     if (rc) return rc;
     CU(cudaStreamSynchronize(h->stream));
@@ -518,6 +525,29 @@ int wepp_get_node_results(wepp_handle* h, double* score, int32_t* counts) {
     CU(cudaSetDevice(h->device));
     if (score) CU(cudaMemcpyAsync(score, h->d_score.p, (size_t)h->n_nodes * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (counts) CU(cudaMemcpyAsync(counts, h->d_counts.p, (size_t)h->n_nodes * NBINS * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return WEPP_OK;
+}
+
+int wepp_get_node_summary(wepp_handle* h, double* score, double* dist_divergence) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (!h->has_results || !h->d_score.p) return fail(WEPP_E_STATE, "no per-node results yet (call wepp_place)");
+    CU(cudaSetDevice(h->device));
+    const int n = h->n_nodes;
+    if (dist_divergence) {
+        CU(h->d_divergence.ensure((size_t)n));
+        BinCounts tc;
+        int active = 0;
+        for (int j = 0; j < NBINS; ++j) {
+            tc.v[j] = h->true_counts[j];
+            active += tc.v[j] != 0;
+        }
+        divergence_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_counts.p, n, tc, active, 0.5 / 100,
+                                                                  h->d_divergence.p);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(dist_divergence, h->d_divergence.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (score) CU(cudaMemcpyAsync(score, h->d_score.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return WEPP_OK;
 }

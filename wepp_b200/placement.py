@@ -99,6 +99,13 @@ class Placer:
         check(self.lib.wepp_get_node_results(self.h, ptr(sc), ptr(ct)))
         return sc, ct
 
+    def node_summary(self):
+        """score[N] and dist_divergence[N] (initial_filter.cpp:214-231), the divergence computed on the device."""
+        sc = np.empty(self.n_nodes, np.float64)
+        dv = np.empty(self.n_nodes, np.float64)
+        check(self.lib.wepp_get_node_summary(self.h, ptr(sc), ptr(dv)))
+        return sc, dv
+
     def epp(self):
         off = np.empty(self.n_reads + 1, np.int64)
         n = C.c_int64(0)
