@@ -53,6 +53,12 @@ __global__ void k(int* out, long long* cyc, int a0, int b0) {
                 x |= nb ^ bb[j];
                 bb[j] = nb;
             }
+            if (OP == 18) r[j] = __viaddmin_s16x2(r[j], b, c + i);                                      // VIADDMNMX.S16x2
+            if (OP == 19) r[j] = __umulhi(r[j], 0x10000u) + b;                                           // IMAD.HI (shift by 16 on the FMA pipe)
+            if (OP == 20) asm volatile("{.reg .pred p; setp.eq.s32 p, %1, 0x7fffffff; @p prmt.b32 %0, %0, %1, %2; @p prmt.b32 %0, %0, %2, %1; @p prmt.b32 %0, %1, %0, %2; @p prmt.b32 %0, %2, %0, %1;}" : "+r"(r[j]) : "r"(b), "r"(c));  // 4 predicated-off PRMT
+            if (OP == 21) asm volatile("{.reg .pred p; setp.ne.s32 p, %1, 3; selp.b32 %0, %0, %2, p;}" : "+r"(r[j]) : "r"(b), "r"(c));   // SEL
+            if (OP == 22) asm volatile("prmt.b32 %0, %0, %1, %2; min.s16x2 %0, %0, %1;" : "+r"(r[j]) : "r"(b), "r"(c));   // PRMT + VIMNMX pair
+            if (OP == 23) asm volatile("prmt.b32 %0, %0, %1, %2; mad.lo.s32 %0, %0, %1, %2;" : "+r"(r[j]) : "r"(b), "r"(c));   // PRMT + IMAD pair
             if (OP == 17) asm volatile("{.reg .pred ph, pl; .reg .u16 a0, a1, m0, m1; .reg .b32 t;\n\t"
                              "min.s16x2 t, %0, %2;\n\t"
                              "mov.b32 {m0, m1}, t; mov.b32 {a0, a1}, %0;\n\t"
@@ -110,6 +116,12 @@ int main() {
     run<11>("add.u16x2", 1);
     run<12>("min.s16x2", 1);
     run<15>("LOP+POPC+IADD", 3);
+    run<18>("VIADDMNMX.S16x2", 1);
+    run<19>("IMAD.HI + IADD", 2);
+    run<20>("ISETP + 4 pred-off PRMT", 5);
+    run<21>("ISETP + SEL", 2);
+    run<22>("PRMT + VIMNMX", 2);
+    run<23>("PRMT + IMAD", 2);
     run<17>("VIMNMX.S16x2+P,2x@IADD", 3);
     run<16>("packed pass-1 pair step", 6);
     return 0;

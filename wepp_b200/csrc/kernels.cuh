@@ -154,6 +154,7 @@ struct __align__(16) PatEntry {   // pass-2 pattern table entry
 // in 16-bit halves).
 constexpr int PLACE_WARPS = 8;
 constexpr int RED_G = 8;              // entries reduced together in pass 2
+constexpr int G1 = 8;                 // entries per pass-1 group (their shared loads are issued together)
 constexpr int RED_S_STRIDE = 36;      // doubles per staged row: 32 lanes + pad (conflict-free column sums)
 constexpr int RED_C_STRIDE = 36;      // ints per staged row (er * 36 + part distinct mod 32: conflict-free column sums)
 constexpr int SMEM_EBUF = 0;                                        // 32 staged entries (512 B)
@@ -460,19 +461,19 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
                 nxt = make_uint4(0, 0, 0, 0);
                 if (base + 32 + lane < c1) nxt = ld_entry(ent + base + 32 + lane);
 #pragma unroll 1
-                for (int g = 0; g < 4; ++g) {
-                    const uint32_t ea = ebuf_s + g * 128;
-                    const uint32_t eg = em >> (8 * g), pg = pm >> (8 * g);
-                    if (((mm >> (8 * g)) & 0xFFu) == 0u) {
+                for (int g = 0; g < 32 / G1; ++g) {
+                    const uint32_t ea = ebuf_s + g * (G1 * 16);
+                    const uint32_t eg = em >> (G1 * g), pg = pm >> (G1 * g);
+                    if (((mm >> (G1 * g)) & ((1u << G1) - 1u)) == 0u) {
                         // all shared-memory loads of the group are issued before the first branch
-                        uint4 e[8];
-                        uint32_t sel[8][P];
+                        uint4 e[G1];
+                        uint32_t sel[G1][P];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) e[i] = lds128(ea + i * 16);
+                        for (int i = 0; i < G1; ++i) e[i] = lds128(ea + i * 16);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) load_sel<K>(col, e[i].w >> SHIFT, sel[i]);
+                        for (int i = 0; i < G1; ++i) load_sel<K>(col, e[i].w >> SHIFT, sel[i]);
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
+                        for (int i = 0; i < G1; ++i) {
                             if (pg & (1u << i)) {          // warp-uniform: a leaf is evaluated, the prefix stays
                                 uint32_t X[P];
 #pragma unroll
@@ -488,7 +489,7 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
                         // rare: the group holds a leaf with several events in this window.  Its earlier
                         // point entries were applied to the prefix; after the evaluation they are undone.
 #pragma unroll 1
-                        for (int i = 0; i < 8; ++i) {
+                        for (int i = 0; i < G1; ++i) {
                             const uint4 e = lds128(ea + i * 16);
                             uint32_t sel[P];
                             load_sel<K>(col, e.w >> SHIFT, sel);
@@ -497,7 +498,7 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
 #pragma unroll
                                 for (int q = 0; q < P; ++q) X[q] = __vadd2(st.S[q], prmt(e.z, e.w, sel[q]));
                                 st.eval(X, (int)(e.y & 0xFFu));
-                                const int64_t at = (int64_t)base + g * 8 + i;
+                                const int64_t at = (int64_t)base + g * G1 + i;
                                 for (int k = 1; k <= (int)(e.y >> 8); ++k) {
                                     const uint4 u = ld_entry(ent + at - k);
                                     uint32_t us[P];
@@ -780,13 +781,16 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
                         }
                         // column sums: lane (er, part) adds 8 of the 32 staged values of entry er
                         __syncwarp();
-                        double s = 0.0;
-                        uint32_t c = 0;
+                        double sv[8];
+                        uint32_t cv[8];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            s += lds_f64(rS + 4 * k * 8);
-                            c += lds32(rC + 4 * k * 4);
+                            sv[k] = lds_f64(rS + 4 * k * 8);
+                            cv[k] = lds32(rC + 4 * k * 4);
                         }
+                        // pairwise tree: three dependent adds instead of eight
+                        double s = ((sv[0] + sv[1]) + (sv[2] + sv[3])) + ((sv[4] + sv[5]) + (sv[6] + sv[7]));
+                        uint32_t c = ((cv[0] + cv[1]) + (cv[2] + cv[3])) + ((cv[4] + cv[5]) + (cv[6] + cv[7]));
                         s += __shfl_xor_sync(FULL, s, 1);
                         c += __shfl_xor_sync(FULL, c, 1);
                         s += __shfl_xor_sync(FULL, s, 2);
