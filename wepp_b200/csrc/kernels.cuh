@@ -990,8 +990,11 @@ __global__ void __launch_bounds__(SCAN_THREADS) score_apply_kernel(const unsigne
 }
 
 // ---------------------------------------------------------------------------------------------
-// counts: in-place inclusive prefix along nodes of int32[(N+1)][50].
-constexpr int CNT_CHUNK = 1024;  // nodes per block
+// counts: in-place inclusive prefix along nodes of int32[(N+1)][50] (HBM streaming: the matrix is
+// read twice and written once).  A block owns CNT_CHUNK consecutive nodes; thread b < 50 owns bin b
+// (a warp reads 200 contiguous bytes per node) and keeps CNT_BATCH independent loads in flight.
+constexpr int CNT_CHUNK = 512;   // nodes per block
+constexpr int CNT_BATCH = 16;    // rows loaded together
 
 __global__ void __launch_bounds__(64) counts_chunk_sum_kernel(const int32_t* __restrict__ counts, int n,
                                                                int32_t* __restrict__ chunk_tot) {
@@ -999,19 +1002,40 @@ __global__ void __launch_bounds__(64) counts_chunk_sum_kernel(const int32_t* __r
     if (b >= NBINS) return;
     const int v0 = blockIdx.x * CNT_CHUNK, v1 = min(n, v0 + CNT_CHUNK);
     int32_t acc = 0;
-#pragma unroll 8
-    for (int v = v0; v < v1; ++v) acc += counts[(size_t)v * NBINS + b];
+    for (int v = v0; v < v1; v += CNT_BATCH) {
+        int32_t x[CNT_BATCH];
+#pragma unroll
+        for (int k = 0; k < CNT_BATCH; ++k) x[k] = (v + k < v1) ? __ldg(counts + (size_t)(v + k) * NBINS + b) : 0;
+#pragma unroll
+        for (int k = 0; k < CNT_BATCH; ++k) acc += x[k];
+    }
     chunk_tot[(size_t)blockIdx.x * NBINS + b] = acc;
 }
 
-// exclusive scan over chunks, one thread per bin (out of place so the loads pipeline)
-__global__ void counts_chunk_scan_kernel(const int32_t* __restrict__ chunk_tot, int32_t* __restrict__ chunk_off,
-                                         int n_chunks) {
-    const int b = threadIdx.x;
-    if (b >= NBINS) return;
+// exclusive scan over chunks: one block per bin, each thread sums a contiguous run of chunks,
+// the run totals are scanned through shared memory
+constexpr int CSCAN_THREADS = 256;
+__global__ void __launch_bounds__(CSCAN_THREADS) counts_chunk_scan_kernel(const int32_t* __restrict__ chunk_tot,
+                                                                           int32_t* __restrict__ chunk_off, int n_chunks) {
+    __shared__ int32_t run_tot[CSCAN_THREADS];
+    const int b = blockIdx.x;
+    const int per = (n_chunks + CSCAN_THREADS - 1) / CSCAN_THREADS;
+    const int c0 = min(n_chunks, (int)threadIdx.x * per), c1 = min(n_chunks, c0 + per);
     int32_t acc = 0;
-#pragma unroll 8
-    for (int c = 0; c < n_chunks; ++c) {
+    for (int c = c0; c < c1; ++c) acc += chunk_tot[(size_t)c * NBINS + b];
+    run_tot[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t run = 0;
+        for (int t = 0; t < CSCAN_THREADS; ++t) {
+            const int32_t x = run_tot[t];
+            run_tot[t] = run;
+            run += x;
+        }
+    }
+    __syncthreads();
+    acc = run_tot[threadIdx.x];
+    for (int c = c0; c < c1; ++c) {
         chunk_off[(size_t)c * NBINS + b] = acc;
         acc += chunk_tot[(size_t)c * NBINS + b];
     }
@@ -1024,9 +1048,19 @@ __global__ void __launch_bounds__(64) counts_apply_kernel(int32_t* __restrict__ 
     if (b >= NBINS) return;
     const int v0 = blockIdx.x * CNT_CHUNK, v1 = min(n, v0 + CNT_CHUNK);
     int32_t acc = chunk_off[(size_t)blockIdx.x * NBINS + b];
-    for (int v = v0; v < v1; ++v) {
-        acc += counts[(size_t)v * NBINS + b];
-        counts[(size_t)v * NBINS + b] = (mapped && mapped[v]) ? 0 : acc;
+    for (int v = v0; v < v1; v += CNT_BATCH) {
+        int32_t x[CNT_BATCH];
+        uint8_t m[CNT_BATCH];
+#pragma unroll
+        for (int k = 0; k < CNT_BATCH; ++k) {
+            x[k] = (v + k < v1) ? counts[(size_t)(v + k) * NBINS + b] : 0;
+            m[k] = (mapped && v + k < v1) ? mapped[v + k] : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < CNT_BATCH; ++k) {
+            acc += x[k];
+            if (v + k < v1) counts[(size_t)(v + k) * NBINS + b] = m[k] ? 0 : acc;
+        }
     }
 }
 

@@ -299,7 +299,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         CU(h->d_cchunk_tot.ensure((size_t)c_chunks * NBINS));
         CU(h->d_cchunk_off.ensure((size_t)c_chunks * NBINS));
         counts_chunk_sum_kernel<<<c_chunks, 64, 0, h->stream>>>(h->d_counts.p, n, h->d_cchunk_tot.p);
-        counts_chunk_scan_kernel<<<1, 64, 0, h->stream>>>(h->d_cchunk_tot.p, h->d_cchunk_off.p, c_chunks);
+        counts_chunk_scan_kernel<<<NBINS, CSCAN_THREADS, 0, h->stream>>>(h->d_cchunk_tot.p, h->d_cchunk_off.p, c_chunks);
         counts_apply_kernel<<<c_chunks, 64, 0, h->stream>>>(h->d_counts.p, n, h->d_cchunk_off.p,
                                                             h->has_mask ? h->d_mapped.p : nullptr);
         CU(cudaGetLastError());
