@@ -14,6 +14,8 @@
  *                            (which calls single_read_tree, :41-135, for every read)
  *   wepp_place_subset     <- single_read_tree on chosen reads under the current `mapped`
  *                            mask, as wepp_filter::remove_read does, :298-302
+ *   wepp_filter_peaks     <- wepp_filter::filter, src/WEPP/initial_filter.cpp:455-506 (the peak loop
+ *                            :284-453 and the neighbour expansion :476-503)
  *   wepp_rescore          <- haplotype::mutation_distance(const raw_read&),
  *                            src/WEPP/haplotype.hpp:123-177, over a candidate set with the
  *                            min / argmin idiom of src/WEPP/arena.cpp:614-625 and :846-857
@@ -125,6 +127,20 @@ int wepp_cartesian_map(wepp_handle* h, int64_t n_reads, const int32_t* start, co
  * candidate list, in candidate order; capacity am_capacity).  */
 int wepp_rescore(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, int32_t* min_dist, int32_t* dist,
                  int64_t* am_off, int32_t* am_idx, int64_t am_capacity);
+
+/* The whole initial filter: wepp_filter::filter (src/WEPP/initial_filter.cpp:455-506) — cartesian_map over
+ * the current reads with nothing mapped, then the greedy peak loop (step / clear_neighbors / singular_step /
+ * find_correspondents / remove_read, :241-453: pick the top full_score = score * sqrt(dist_divergence) nodes
+ * (ties within SCORE_EPSILON by leaf_count, then id), map their radius-MAX_PEAK_PEAK_MUTATION neighbourhoods,
+ * take the reads they explain out of every node's score, until MAX_PEAKS peaks or no reads / scores are left)
+ * and the neighbour expansion (:476-503).  The per-read work runs on the GPU: correspondents are found with the
+ * mutation-distance kernel, their weights are re-accumulated by the placement kernel and subtracted.
+ * leaf_count[N] is haplotype::leaf_count, id_rank[N] the rank of haplotype::id in ascending std::string order
+ * (the comparator's last tie-break, src/WEPP/arena.hpp:16-31).  out_nodes receives the peaks (ascending arena
+ * index) followed by the chosen neighbours (ascending), as the reference returns them; *n_peaks / *n_out their
+ * numbers.  On return the per-node score / counts are those of the cartesian_map (recover_haplotype_state).  */
+int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, const int32_t* id_rank, int32_t* out_nodes,
+                      int32_t capacity, int32_t* n_peaks, int32_t* n_out);
 
 /* Device-resident views for callers that keep results on the GPU (NCCL all-reduce of the
  * per-node arrays in the multi-GPU driver).  Pointers stay valid until the next

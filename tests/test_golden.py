@@ -69,6 +69,47 @@ def test_oracle_matches_reference_masked_single_read_tree_and_distances(name):
     assert np.array_equal(sn, g["arena_st_nuc"])
 
 
+def hap_ids(source):
+    """The reference's haplotype ids are its MAT node identifiers, "n<index>" in the fixture trees
+    (oracle/ref_driver.cpp); the comparator's last tie-break compares them as strings (arena.hpp:29)."""
+    ids = ["n%d" % int(s) for s in source]
+    order = sorted(range(len(ids)), key=lambda i: ids[i])
+    rank = np.zeros(len(ids), np.int32)
+    rank[order] = np.arange(len(ids), dtype=np.int32)
+    return ids, rank
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_restated_peak_loop_matches_reference_filter(name):
+    """wepp_filter::filter (initial_filter.cpp:455-506) of the reference's object code vs oracle/peaks.py."""
+    from oracle import peaks
+    g, tree, reads, _ = load(name)
+    arena, mreads = golden_arena(g, tree, reads)
+    ids, _ = hap_ids(g["arena_source"])
+    pk, nb = peaks.filter_peaks(arena, mreads, g["arena_leaf_count"], ids)
+    assert pk.size > 0
+    assert np.array_equal(np.sort(np.concatenate([pk, nb])), np.sort(g["filter_selected"]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_peak_loop_matches_reference_filter(name):
+    from wepp_b200.placement import Placer
+    g, tree, reads, masked = load(name)
+    arena, mreads, info = build_arena(tree, reads, masked)
+    _, rank = hap_ids(info["source"])
+    p = Placer(0)
+    p.set_arena(arena)
+    p.set_reads(mreads)
+    pk, nb = p.filter_peaks(info["leaf_count"], rank)
+    assert np.array_equal(np.sort(np.concatenate([pk, nb])), np.sort(g["filter_selected"]))
+    # the cartesian_map state is restored afterwards (recover_haplotype_state)
+    sc, ct = p.node_results()
+    assert np.array_equal(ct, g["cm_counts"])
+    np.testing.assert_allclose(sc, g["cm_score"], rtol=1e-9, atol=1e-15)
+    p.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", NAMES)
 def test_cuda_matches_reference_fixtures(name):

@@ -165,6 +165,27 @@ def test_rescore_matches_oracle():
     p.close()
 
 
+@pytest.mark.parametrize("seed,n_nodes,n_reads", [(41, 1500, 500), (42, 3000, 900)])
+def test_peak_loop_matches_restated_filter(seed, n_nodes, n_reads):
+    """wepp_filter_peaks (GPU-driven peak loop) vs oracle/peaks.py, itself pinned on the reference's object code."""
+    from oracle import peaks
+    arena, reads = cases.small_case(seed=seed, n_nodes=n_nodes, n_reads=n_reads)
+    rng = np.random.default_rng(seed)
+    leaf_count = rng.integers(1, 6, arena.n_nodes).astype(np.int32)
+    ids = ["n%d" % v for v in range(arena.n_nodes)]
+    order = sorted(range(arena.n_nodes), key=lambda i: ids[i])
+    rank = np.zeros(arena.n_nodes, np.int32)
+    rank[order] = np.arange(arena.n_nodes, dtype=np.int32)
+    opk, onb = peaks.filter_peaks(arena, reads, leaf_count, ids)
+    p = Placer(0)
+    p.set_arena(arena)
+    p.set_reads(reads)
+    pk, nb = p.filter_peaks(leaf_count, rank)
+    assert np.array_equal(pk, opk)
+    assert np.array_equal(nb, onb)
+    p.close()
+
+
 def test_full_size_properties():
     """Size-independent properties at a size the oracle cannot finish: (1) degrees are
     conserved — sum over nodes of counts[v][b] == sum over reads in bin b of degree*multiplicity;

@@ -49,6 +49,7 @@ SIGNATURES = {
     "wepp_get_node_summary": (C.c_int, [VP, VP, VP]),
     "wepp_get_epp": (C.c_int, [VP, VP, VP, C.c_int64, C.POINTER(C.c_int64)]),
     "wepp_cartesian_map": (C.c_int, [VP, C.c_int64] + [VP] * 11),
+    "wepp_filter_peaks": (C.c_int, [VP, VP, VP, VP, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "wepp_rescore": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, C.c_int64]),
     "wepp_device_buffer": (C.c_int, [VP, C.c_int32, C.POINTER(VP), C.POINTER(C.c_int64)]),
     "wepp_get_stats": (C.c_int, [VP, C.POINTER(WeppStats)]),

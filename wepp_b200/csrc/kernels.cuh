@@ -875,7 +875,7 @@ __global__ void expand_kernel(const Entry* __restrict__ lists, const ListDesc* _
                 atomic_add128(diff_lo + idx + 1, diff_hi + idx + 1, nlo, nhi);
             }
         }
-        if (ccur != cprv) {
+        if (counts && ccur != cprv) {
             atomicAdd(counts + (size_t)idx * NBINS + bd.bin, ccur - cprv);
             if (point) atomicAdd(counts + (size_t)(idx + 1) * NBINS + bd.bin, cprv - ccur);
         }

@@ -3,7 +3,10 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cmath>
 #include <cstring>
+#include <set>
+#include <unordered_map>
 #include <string>
 #include <vector>
 
@@ -12,6 +15,7 @@
 #include "host_prep.h"
 #include "kernels.cuh"
 #include "rescore.cuh"
+#include "peaks.cuh"
 
 using namespace wepp;
 
@@ -204,7 +208,8 @@ int launch_place_k(wepp_handle* h, const PlaceParams& pp, int width) {
     return launch_place<K, false, true>(h, pp, width);
 }
 
-int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t epp_cap, int64_t epp_capacity) {
+int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t epp_cap, int64_t epp_capacity,
+              bool with_counts = true, double* score_out = nullptr) {
     ReadPlan& pl = dp.plan;
     int rc = finalize_plan(h, dp);
     if (rc) return rc;
@@ -232,7 +237,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         CU(h->d_counts.ensure(((size_t)n + 1) * NBINS));
         CU(h->d_diff_lo.ensure((size_t)n + 1));
         CU(h->d_diff_hi.ensure((size_t)n + 1));
-        CU(cudaMemsetAsync(h->d_counts.p, 0, ((size_t)n + 1) * NBINS * sizeof(int32_t), h->stream));
+        if (with_counts) CU(cudaMemsetAsync(h->d_counts.p, 0, ((size_t)n + 1) * NBINS * sizeof(int32_t), h->stream));
         CU(cudaMemsetAsync(h->d_diff_lo.p, 0, ((size_t)n + 1) * sizeof(unsigned long long), h->stream));
         CU(cudaMemsetAsync(h->d_diff_hi.p, 0, ((size_t)n + 1) * sizeof(unsigned long long), h->stream));
     }
@@ -282,7 +287,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
             dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
             expand_kernel<<<grid, 256, 0, h->stream>>>(dp.entries.p, dp.lists.p, dp.buckets.p, dp.prev_boundary.p,
                                                        h->d_accS.p, h->d_accC.p, h->d_diff_lo.p, h->d_diff_hi.p,
-                                                       h->d_counts.p);
+                                                       with_counts ? h->d_counts.p : nullptr);
             CU(cudaGetLastError());
             ++launches;
         }
@@ -294,16 +299,19 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         score_apply_kernel<<<n_chunks, SCAN_THREADS, 0, h->stream>>>(h->d_diff_lo.p, h->d_diff_hi.p, n,
                                                                      h->d_chunk128.p,
                                                                      h->has_mask ? h->d_mapped.p : nullptr,
-                                                                     h->d_score.p);
-        const int c_chunks = (n + CNT_CHUNK - 1) / CNT_CHUNK;
-        CU(h->d_cchunk_tot.ensure((size_t)c_chunks * NBINS));
-        CU(h->d_cchunk_off.ensure((size_t)c_chunks * NBINS));
-        counts_chunk_sum_kernel<<<c_chunks, 64, 0, h->stream>>>(h->d_counts.p, n, h->d_cchunk_tot.p);
-        counts_chunk_scan_kernel<<<NBINS, CSCAN_THREADS, 0, h->stream>>>(h->d_cchunk_tot.p, h->d_cchunk_off.p, c_chunks);
-        counts_apply_kernel<<<c_chunks, 64, 0, h->stream>>>(h->d_counts.p, n, h->d_cchunk_off.p,
-                                                            h->has_mask ? h->d_mapped.p : nullptr);
+                                                                     score_out ? score_out : h->d_score.p);
+        launches += 3;
+        if (with_counts) {
+            const int c_chunks = (n + CNT_CHUNK - 1) / CNT_CHUNK;
+            CU(h->d_cchunk_tot.ensure((size_t)c_chunks * NBINS));
+            CU(h->d_cchunk_off.ensure((size_t)c_chunks * NBINS));
+            counts_chunk_sum_kernel<<<c_chunks, 64, 0, h->stream>>>(h->d_counts.p, n, h->d_cchunk_tot.p);
+            counts_chunk_scan_kernel<<<NBINS, CSCAN_THREADS, 0, h->stream>>>(h->d_cchunk_tot.p, h->d_cchunk_off.p, c_chunks);
+            counts_apply_kernel<<<c_chunks, 64, 0, h->stream>>>(h->d_counts.p, n, h->d_cchunk_off.p,
+                                                                h->has_mask ? h->d_mapped.p : nullptr);
+            launches += 3;
+        }
         CU(cudaGetLastError());
-        launches += 6;
     }
     CU(cudaEventRecord(h->ev[2], h->stream));
     h->stats_pending = true;
@@ -770,3 +778,308 @@ int wepp_rescore(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, int3
 }
 
 }  // extern "C"
+
+// ---- greedy peak selection (wepp_filter::filter, initial_filter.cpp:455-506) ---------------------
+namespace {
+
+constexpr int MAX_PEAK_PEAK_MUTATION = 2;   // src/WEPP/config.hpp:19
+constexpr int FREYJA_PEAKS_LIMIT = 5000;    // :20
+constexpr int TOP_N = 10;                   // :21
+constexpr int MAX_PEAKS = 300;              // :22
+constexpr int MAX_NEIGHBORS_WEPP = 50;      // :23
+
+// Host view of the arena for the haplotype-to-haplotype work of the peak loop.
+struct PeakHost {
+    const wepp_handle* h;
+    std::vector<int64_t> child_off;
+    std::vector<int32_t> child;
+    std::unordered_map<int32_t, std::vector<std::pair<int32_t, uint8_t>>> cache;
+    std::vector<int64_t> last;
+
+    explicit PeakHost(const wepp_handle* hh) : h(hh) {
+        const int32_t n = h->n_nodes;
+        child_off.assign((size_t)n + 1, 0);
+        for (int32_t v = 1; v < n; ++v) ++child_off[h->parent[v] + 1];
+        for (int32_t v = 0; v < n; ++v) child_off[v + 1] += child_off[v];
+        child.resize((size_t)std::max(n - 1, 0));
+        std::vector<int64_t> cur(child_off.begin(), child_off.end() - 1);
+        for (int32_t v = 1; v < n; ++v) child[cur[h->parent[v]]++] = v;   // preorder = the reference's creation order
+        last.assign((size_t)h->genome + 1, -1);
+    }
+
+    // haplotype::stack_muts (arena.cpp:18-46): the last event per position on the root path, kept when it differs
+    // from the reference allele, sorted by position
+    const std::vector<std::pair<int32_t, uint8_t>>& stack(int32_t v) {
+        auto it = cache.find(v);
+        if (it != cache.end()) return it->second;
+        std::vector<int32_t> path, touched;
+        for (int32_t u = v; u >= 0; u = h->parent[u]) path.push_back(u);
+        for (auto p = path.rbegin(); p != path.rend(); ++p)
+            for (int64_t k = h->mut_off[*p]; k < h->mut_off[*p + 1]; ++k) {
+                if (last[h->mut_pos[k]] < 0) touched.push_back(h->mut_pos[k]);
+                last[h->mut_pos[k]] = k;
+            }
+        std::sort(touched.begin(), touched.end());
+        std::vector<std::pair<int32_t, uint8_t>> st;
+        for (int32_t pos : touched) {
+            const int64_t k = last[pos];
+            if (h->mut_ref[k] != h->mut_nuc[k]) st.emplace_back(pos, h->mut_nuc[k]);
+            last[pos] = -1;
+        }
+        return cache.emplace(v, std::move(st)).first->second;
+    }
+
+    // a->mutation_distance(b) (haplotype.hpp:123-181 with comp = b->stack_muts, [0, INT_MAX])
+    int dist(int32_t a, int32_t b) {
+        const auto& A = stack(a);
+        const auto B = stack(b);   // copy: stack(a) may rehash the cache
+        const auto& A2 = stack(a);
+        size_t i = 0, j = 0;
+        int m = 0;
+        while (i < A2.size() || j < B.size()) {
+            if (i == A2.size()) { m += B[j].second != 15; ++j; }
+            else if (j == B.size()) { ++m; ++i; }
+            else if (A2[i].first < B[j].first) { ++m; ++i; }
+            else if (A2[i].first > B[j].first) { m += B[j].second != 15; ++j; }
+            else { m += (A2[i].second != B[j].second) && (B[j].second != 15); ++i; ++j; }
+        }
+        (void)A;
+        return m;
+    }
+
+    // arena::highest_scoring_neighbors(pivot, include_mapped = false, radius, INT_MAX) (arena.cpp:209-249),
+    // in the order the reference's recursion inserts them
+    void neighbors(int32_t pivot, int radius, const std::vector<uint8_t>& mapped, std::vector<int32_t>& out) {
+        out.clear();
+        int32_t curr = pivot;
+        while (h->parent[curr] >= 0 && dist(pivot, h->parent[curr]) <= radius) curr = h->parent[curr];
+        std::vector<int32_t> st{curr};
+        while (!st.empty()) {
+            const int32_t v = st.back();
+            st.pop_back();
+            if (dist(pivot, v) > radius) continue;
+            if (!mapped[v]) out.push_back(v);
+            for (int64_t k = child_off[v + 1] - 1; k >= child_off[v]; --k) st.push_back(child[k]);
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, const int32_t* id_rank, int32_t* out_nodes,
+                                 int32_t capacity, int32_t* n_peaks_out, int32_t* n_out) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (!h->has_reads) return fail(WEPP_E_STATE, "wepp_set_reads must be called first");
+    if (!leaf_count || !id_rank || !n_out) return fail(WEPP_E_INVALID, "NULL argument");
+    CU(cudaSetDevice(h->device));
+    const int n = h->n_nodes;
+    const int64_t R = h->n_reads;
+    cudaStream_t st = h->stream;
+
+    // reset_haplotype_state + cartesian_map (initial_filter.cpp:458-466)
+    h->has_mask = false;
+    h->full.final_for_mask = false;
+    h->sub.final_for_mask = false;
+    int rc = run_place(h, h->full, true, 0, 0);
+    if (rc) return rc;
+    CU(h->d_divergence.ensure((size_t)n));
+    {
+        BinCounts tc;
+        int active = 0;
+        for (int j = 0; j < NBINS; ++j) {
+            tc.v[j] = h->true_counts[j];
+            active += tc.v[j] != 0;
+        }
+        divergence_kernel<<<(n + 255) / 256, 256, 0, st>>>(h->d_counts.p, n, tc, active, 0.5 / 100, h->d_divergence.p);
+        CU(cudaGetLastError());
+    }
+    DevBuf<double> d_cur, d_orig, d_contrib, d_fulls;
+    DevBuf<uint8_t> d_pmapped, d_removed, d_rnuc, d_stnuc;
+    DevBuf<int32_t> d_rstart, d_rend, d_rpos, d_nodes, d_stpos, d_marks;
+    DevBuf<int64_t> d_roff, d_list, d_stoff;
+    DevBuf<unsigned long long> d_max;
+    DevBuf<int> d_count;
+    auto release = [&]() {
+        d_cur.release(); d_orig.release(); d_contrib.release(); d_fulls.release(); d_pmapped.release();
+        d_removed.release(); d_rnuc.release(); d_stnuc.release(); d_rstart.release(); d_rend.release();
+        d_rpos.release(); d_nodes.release(); d_stpos.release(); d_marks.release(); d_roff.release();
+        d_list.release(); d_stoff.release(); d_max.release(); d_count.release();
+    };
+#define FCU(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            release();                                                                             \
+            return fail(WEPP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));         \
+        }                                                                                          \
+    } while (0)
+    const int CAND_CAP = 1 << 20;
+    FCU(d_cur.ensure((size_t)n)); FCU(d_orig.ensure((size_t)n)); FCU(d_contrib.ensure((size_t)n));
+    FCU(d_pmapped.ensure((size_t)n)); FCU(d_removed.ensure((size_t)std::max<int64_t>(R, 1)));
+    FCU(d_nodes.ensure(CAND_CAP)); FCU(d_fulls.ensure(CAND_CAP)); FCU(d_max.ensure(1)); FCU(d_count.ensure(1));
+    FCU(d_list.ensure((size_t)std::max<int64_t>(R, 1)));
+    FCU(cudaMemcpyAsync(d_cur.p, h->d_score.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    FCU(cudaMemcpyAsync(d_orig.p, h->d_score.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    FCU(cudaMemsetAsync(d_pmapped.p, 0, (size_t)n, st));
+    FCU(cudaMemsetAsync(d_removed.p, 0, (size_t)std::max<int64_t>(R, 1), st));
+    // the reads in caller order for find_correspondents
+    FCU(upload(d_rstart, h->r_start, st)); FCU(upload(d_rend, h->r_end, st)); FCU(upload(d_roff, h->r_off, st));
+    FCU(upload(d_rpos, h->r_pos, st)); FCU(upload(d_rnuc, h->r_nuc, st));
+
+    PeakHost ph(h);
+    std::vector<uint8_t> mapped((size_t)n, 0);
+    std::set<int32_t> peaks;
+    int64_t remaining = R;
+    auto cmp_tie = [&](int32_t l, int32_t r) {   // score_comparator's tie-breaks (arena.hpp:24-29)
+        if (leaf_count[l] != leaf_count[r]) return leaf_count[l] > leaf_count[r];
+        return id_rank[l] > id_rank[r];
+    };
+
+    std::vector<int32_t> cand_nodes, consideration, nb, marks;
+    std::vector<double> cand_full;
+    std::vector<int64_t> removed_now;
+    while (remaining > 0 && (int)peaks.size() < MAX_PEAKS) {
+        // ---- the head of the sorted `current` list (initial_filter.cpp:396-417) -------------------
+        FCU(cudaMemsetAsync(d_max.p, 0, 8, st));
+        peak_max_kernel<<<1184, 256, 0, st>>>(d_cur.p, h->d_divergence.p, d_pmapped.p, n, d_max.p);
+        unsigned long long top_bits = 0;
+        FCU(cudaMemcpyAsync(&top_bits, d_max.p, 8, cudaMemcpyDeviceToHost, st));
+        FCU(cudaStreamSynchronize(st));
+        double top;
+        std::memcpy(&top, &top_bits, 8);
+        if (!(top >= PEAK_SCORE_EPSILON)) break;   // no available peaks (:401-404) / current is empty
+        FCU(cudaMemsetAsync(d_count.p, 0, sizeof(int), st));
+        peak_collect_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_cur.p, h->d_divergence.p, d_pmapped.p, n, top, d_count.p,
+                                                             d_nodes.p, d_fulls.p, CAND_CAP);
+        int n_cand = 0;
+        FCU(cudaMemcpyAsync(&n_cand, d_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FCU(cudaStreamSynchronize(st));
+        if (n_cand > CAND_CAP) {
+            release();
+            return fail(WEPP_E_CAPACITY, "more than 2^20 nodes tie for the top score");
+        }
+        cand_nodes.resize((size_t)n_cand);
+        cand_full.resize((size_t)n_cand);
+        FCU(cudaMemcpyAsync(cand_nodes.data(), d_nodes.p, (size_t)n_cand * 4, cudaMemcpyDeviceToHost, st));
+        FCU(cudaMemcpyAsync(cand_full.data(), d_fulls.p, (size_t)n_cand * 8, cudaMemcpyDeviceToHost, st));
+        FCU(cudaStreamSynchronize(st));
+        // all candidates are within SCORE_EPSILON of the maximum, hence of each other: the comparator orders
+        // them by leaf_count, then id (descending)
+        std::vector<int32_t> order(cand_nodes.begin(), cand_nodes.end());
+        std::sort(order.begin(), order.end(), cmp_tie);
+
+        consideration.clear();
+        marks.clear();
+        for (int32_t v : order) {
+            if ((int)consideration.size() >= TOP_N || (int)consideration.size() + (int)peaks.size() >= MAX_PEAKS) break;
+            bool valid = true;
+            for (int32_t old : consideration)
+                if (!(ph.dist(old, v) > MAX_PEAK_PEAK_MUTATION)) valid = false;   // valid_two_tops
+            if (valid) {
+                consideration.push_back(v);
+                mapped[v] = 1;
+                marks.push_back(v);
+            }
+        }
+        // ---- clear_neighbors (:368-385) ------------------------------------------------------------
+        for (int32_t pivot : consideration) {
+            peaks.insert(pivot);
+            ph.neighbors(pivot, MAX_PEAK_PEAK_MUTATION, mapped, nb);
+            for (int32_t v : nb) {
+                mapped[v] = 1;
+                marks.push_back(v);
+            }
+        }
+        FCU(upload(d_marks, marks, st));
+        if (!marks.empty()) mark_kernel<<<((int)marks.size() + 255) / 256, 256, 0, st>>>(d_pmapped.p, d_marks.p, (int)marks.size());
+        // ---- singular_step for every chosen peak (:344-366): correspondents, then their removal -----
+        std::vector<int64_t> so{0};
+        std::vector<int32_t> sp;
+        std::vector<uint8_t> sn;
+        for (int32_t pivot : consideration) {
+            for (const auto& m : ph.stack(pivot)) {
+                sp.push_back(m.first);
+                sn.push_back(m.second);
+            }
+            so.push_back((int64_t)sp.size());
+        }
+        FCU(upload(d_stoff, so, st)); FCU(upload(d_stpos, sp, st)); FCU(upload(d_stnuc, sn, st));
+        FCU(cudaMemsetAsync(d_count.p, 0, sizeof(int), st));
+        CorrespondParams cp = {};
+        cp.n_reads = R; cp.start = d_rstart.p; cp.end = d_rend.p; cp.rm_off = d_roff.p; cp.rm_pos = d_rpos.p;
+        cp.rm_nuc = d_rnuc.p; cp.max_pars = h->d_maxpars.p; cp.removed = d_removed.p;
+        cp.n_cand = (int32_t)consideration.size(); cp.st_off = d_stoff.p; cp.st_pos = d_stpos.p; cp.st_nuc = d_stnuc.p;
+        cp.count = d_count.p; cp.list = d_list.p;
+        if (R > 0 && !consideration.empty()) correspond_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(cp);
+        int n_rem = 0;
+        FCU(cudaMemcpyAsync(&n_rem, d_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FCU(cudaStreamSynchronize(st));
+        if (n_rem > 0) {
+            removed_now.resize((size_t)n_rem);
+            FCU(cudaMemcpyAsync(removed_now.data(), d_list.p, (size_t)n_rem * 8, cudaMemcpyDeviceToHost, st));
+            FCU(cudaStreamSynchronize(st));
+            std::sort(removed_now.begin(), removed_now.end());
+            std::string err = build_read_plan(h->es, h->genome, h->n_reads, h->r_start.data(), h->r_end.data(),
+                                              h->r_degree.data(), h->r_off.data(), h->r_pos.data(), h->r_nuc.data(),
+                                              h->opt_k, removed_now.data(), n_rem, h->sub.plan);
+            if (!err.empty()) {
+                release();
+                return fail(WEPP_E_INVALID, err);
+            }
+            rc = upload_plan(h, h->sub);
+            if (!rc) rc = run_place(h, h->sub, true, 0, 0, /*with_counts*/ false, d_contrib.p);
+            if (rc) {
+                release();
+                return rc;
+            }
+            subtract_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_cur.p, d_contrib.p, n);
+            remaining -= n_rem;
+        }
+        if (consideration.empty()) break;   // nothing selectable: the reference would spin on the same head
+    }
+
+    // ---- neighbours of the peaks (:476-503) ---------------------------------------------------------
+    std::vector<double> full((size_t)n), dv((size_t)n);
+    FCU(cudaMemcpyAsync(full.data(), d_orig.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    FCU(cudaMemcpyAsync(dv.data(), h->d_divergence.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    FCU(cudaMemcpyAsync(h->d_score.p, d_orig.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));   // recover_state
+    FCU(cudaStreamSynchronize(st));
+    for (int v = 0; v < n; ++v) full[v] = full[v] * std::sqrt(dv[v]);   // haplotype::full_score with score = orig_score
+    auto cmp = [&](int32_t l, int32_t r) {   // score_comparator (arena.hpp:16-31)
+        if (std::fabs(full[l] - full[r]) > PEAK_SCORE_EPSILON) return full[l] > full[r];
+        return cmp_tie(l, r);
+    };
+    std::set<int32_t> nbrs;
+    for (int k = 0; k < 5; ++k) {
+        std::fill(mapped.begin(), mapped.end(), 0);
+        std::set<int32_t> curr;
+        for (int32_t pivot : peaks) {
+            ph.neighbors(pivot, MAX_PEAK_PEAK_MUTATION + k, mapped, nb);
+            std::set<int32_t, decltype(cmp)> ordered(cmp);
+            for (int32_t v : nb) ordered.insert(v);
+            int i = 0;
+            for (int32_t v : ordered) {
+                if (peaks.count(v) || curr.count(v)) continue;
+                mapped[v] = 1;
+                curr.insert(v);
+                if (++i == MAX_NEIGHBORS_WEPP) break;
+            }
+        }
+        if (std::abs(FREYJA_PEAKS_LIMIT - ((int)curr.size() + (int)peaks.size())) <
+            std::abs(FREYJA_PEAKS_LIMIT - ((int)nbrs.size() + (int)peaks.size())))
+            nbrs = curr;
+    }
+    release();
+#undef FCU
+    const int total = (int)peaks.size() + (int)nbrs.size();
+    if (n_peaks_out) *n_peaks_out = (int32_t)peaks.size();
+    *n_out = total;
+    if (out_nodes) {
+        if (capacity < total) return fail(WEPP_E_CAPACITY, "out_nodes capacity too small");
+        int i = 0;
+        for (int32_t v : peaks) out_nodes[i++] = v;
+        for (int32_t v : nbrs) out_nodes[i++] = v;
+    }
+    h->has_results = true;
+    return WEPP_OK;
+}

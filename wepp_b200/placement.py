@@ -106,6 +106,14 @@ class Placer:
         check(self.lib.wepp_get_node_summary(self.h, ptr(sc), ptr(dv)))
         return sc, dv
 
+    def filter_peaks(self, leaf_count, id_rank):
+        """wepp_filter::filter (initial_filter.cpp:455-506): returns (peaks, neighbours) as arena indices."""
+        lc, ir = _c(leaf_count, np.int32), _c(id_rank, np.int32)
+        out = np.empty(self.n_nodes, np.int32)
+        npk, nout = C.c_int32(0), C.c_int32(0)
+        check(self.lib.wepp_filter_peaks(self.h, ptr(lc), ptr(ir), ptr(out), out.shape[0], C.byref(npk), C.byref(nout)))
+        return out[: npk.value].copy(), out[npk.value: nout.value].copy()
+
     def epp(self):
         off = np.empty(self.n_reads + 1, np.int64)
         n = C.c_int64(0)
