@@ -189,6 +189,46 @@ int  wepp_arena_get(const wepp_arena* a, int32_t* parent, int32_t* source, int32
 int  wepp_arena_get_reads(const wepp_arena* a, int64_t* rm_off, int32_t* rm_pos, uint8_t* rm_nuc);
 int  wepp_set_arena_from(wepp_handle* h, const wepp_arena* a);
 
+/* ---- File formats either side of the path (host side; no GPU needed) ---------------------------
+ * The MAT loader replaces MAT::load_mutation_annotated_tree + Tree::uncondense_leaves as dataset::mat()
+ * calls them (src/WEPP/dataset.hpp:213-220; src/mutation_annotated_tree.cpp:415-508 Newick, :522-612
+ * protobuf `Parsimony::data` with gzip detected by a ".gz" in the file name, :720-746 add_mutation,
+ * :1224-1272 uncondense).  Nodes come back in creation order (Newick preorder, then un-condensed
+ * leaves): parent[v] < v, children of a node = its nodes in index order — exactly the input
+ * wepp_arena_build takes.  Mutations keep the loader's 4-bit ids; a negative position is a masked
+ * mutation.  Strings are returned as one character pool plus offsets (n + 1 entries).  */
+typedef struct wepp_mat wepp_mat;
+int  wepp_mat_load(const char* path, int32_t uncondense, wepp_mat** out);
+int  wepp_mat_parse(const void* pb_bytes, int64_t n_bytes, int32_t uncondense, wepp_mat** out);
+void wepp_mat_free(wepp_mat* m);
+int  wepp_mat_dims(const wepp_mat* m, int32_t* n_nodes, int64_t* n_muts, int32_t* n_annotations, int64_t* id_chars,
+                   int64_t* clade_chars);
+int  wepp_mat_get(const wepp_mat* m, int32_t* parent, int64_t* mut_off, int32_t* mut_pos, uint8_t* mut_ref,
+                  uint8_t* mut_par, uint8_t* mut_nuc, int64_t* id_off, char* id_chars);
+/* clade_annotations: entry v * n_annotations + k (src/mutation_annotated_tree.cpp:560-564) */
+int  wepp_mat_get_clades(const wepp_mat* m, int64_t* clade_off, char* clade_chars);
+/* Parsimony::data bytes of a tree given as flat arrays (leaf names = ids of childless nodes; internal
+ * nodes are renamed node_<k> by any loader).  Returns the size; writes at most `capacity` bytes.  */
+int64_t wepp_mat_serialize(int32_t n_nodes, const int32_t* parent, const int64_t* mut_off, const int32_t* mut_pos,
+                           const uint8_t* mut_ref, const uint8_t* mut_par, const uint8_t* mut_nuc, const int64_t* id_off,
+                           const char* id_chars, void* out, int64_t capacity);
+
+/* The collapsed reads: load_reads_from_proto (src/WEPP/sam2pb.cpp:489-549) over `Sam::sam`
+ * (sam.proto:4-18).  A read's mutations are the positions where its content differs from the reference
+ * and is not '_' (N included, id 15); end = start + len - 1.  reverse columns: key k owns values
+ * rev_off[k] .. rev_off[k+1].  */
+typedef struct wepp_readset wepp_readset;
+int  wepp_reads_load(const char* path, const char* ref_seq, int64_t ref_len, int32_t n_threads, wepp_readset** out);
+int  wepp_reads_parse(const void* pb_bytes, int64_t n_bytes, const char* ref_seq, int64_t ref_len, int32_t n_threads,
+                      wepp_readset** out);
+void wepp_reads_free(wepp_readset* r);
+int  wepp_reads_dims(const wepp_readset* r, int64_t* n_reads, int64_t* n_muts, int64_t* name_chars, int64_t* n_rev_keys,
+                     int64_t* n_rev_vals, int64_t* rev_key_chars, int64_t* rev_val_chars);
+int  wepp_reads_get(const wepp_readset* r, int32_t* start, int32_t* end, int32_t* degree, int64_t* rm_off,
+                    int32_t* rm_pos, uint8_t* rm_nuc, int64_t* name_off, char* name_chars);
+int  wepp_reads_get_reverse(const wepp_readset* r, int64_t* key_off, char* key_chars, int64_t* rev_off,
+                            int64_t* val_off, char* val_chars);
+
 /* Host-only introspection (no GPU needed; used by the CPU test-suite): the Euler-tour event
  * stripes built from an arena (4 x uint32 per entry: preorder idx, position, signed-delta bytes
  * for read allele ref/A/C/G, delta byte for T) and the read bucketing plan.  Both return a

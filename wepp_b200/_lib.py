@@ -59,6 +59,19 @@ SIGNATURES = {
     "wepp_arena_get": (C.c_int, [VP] * 10),
     "wepp_arena_get_reads": (C.c_int, [VP] * 4),
     "wepp_set_arena_from": (C.c_int, [VP, VP]),
+    "wepp_mat_load": (C.c_int, [C.c_char_p, C.c_int32, C.POINTER(VP)]),
+    "wepp_mat_parse": (C.c_int, [C.c_char_p, C.c_int64, C.c_int32, C.POINTER(VP)]),
+    "wepp_mat_free": (None, [VP]),
+    "wepp_mat_dims": (C.c_int, [VP, C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "wepp_mat_get": (C.c_int, [VP] * 9),
+    "wepp_mat_get_clades": (C.c_int, [VP] * 3),
+    "wepp_mat_serialize": (C.c_int64, [C.c_int32] + [VP] * 9 + [C.c_int64]),
+    "wepp_reads_load": (C.c_int, [C.c_char_p, C.c_char_p, C.c_int64, C.c_int32, C.POINTER(VP)]),
+    "wepp_reads_parse": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int32, C.POINTER(VP)]),
+    "wepp_reads_free": (None, [VP]),
+    "wepp_reads_dims": (C.c_int, [VP] + [C.POINTER(C.c_int64)] * 7),
+    "wepp_reads_get": (C.c_int, [VP] * 9),
+    "wepp_reads_get_reverse": (C.c_int, [VP] * 6),
     "wepp_host_euler_stripes": (C.c_int64, [C.c_int32, VP, VP, VP, VP, VP, C.c_int32, C.c_int32, VP, C.c_int64, VP, C.c_int32]),
     "wepp_host_read_plan": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [VP] * 10 + [C.POINTER(C.c_int32)]),
 }

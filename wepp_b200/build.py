@@ -17,8 +17,8 @@ ORACLE_SRC = os.path.join(ROOT, "oracle", "wepp_oracle.cpp")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "libwepp_oracle.so")
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libwepp_ref.so")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC,-O3,-pthread", "-shared"]
+NVCC_OBJ_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                  "-Xcompiler", "-fPIC,-O3,-pthread"]
 
 
 def _newer(target: str, sources: list[str]) -> bool:
@@ -35,13 +35,29 @@ def _run(cmd: list[str]) -> None:
         raise RuntimeError("build failed: " + " ".join(cmd))
 
 
+HOST_SRCS = ["host_prep.cpp", "host_arena.cpp", "host_io.cpp", "wepp_abi_io.cpp"]
+OBJ_DIR = os.path.join(ROOT, "wepp_b200", "build")
+
+
 def build_cuda(force: bool = False) -> str:
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [os.path.join(ROOT, "include", "wepp_b200.h")]
-    if not force and _newer(LIB, srcs):
-        return LIB
+    """wepp_abi.cu (all kernels) is compiled by nvcc for sm_100a, the host translation units by g++,
+    each into its own object (rebuilt only when it or a header changed), then linked into one library."""
+    headers = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(ROOT, "include", "wepp_b200.h"))
+    os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    _run([nvcc, *NVCC_FLAGS, os.path.join(CSRC, "wepp_abi.cu"), os.path.join(CSRC, "host_prep.cpp"),
-          os.path.join(CSRC, "host_arena.cpp"), "-o", LIB])
+    objs = []
+    cu, cu_o = os.path.join(CSRC, "wepp_abi.cu"), os.path.join(OBJ_DIR, "wepp_abi.o")
+    if force or not _newer(cu_o, [cu] + headers):
+        _run([nvcc, *NVCC_OBJ_FLAGS, "-c", cu, "-o", cu_o])
+    objs.append(cu_o)
+    for f in HOST_SRCS:
+        src, obj = os.path.join(CSRC, f), os.path.join(OBJ_DIR, f[:-4] + ".o")
+        if force or not _newer(obj, [src] + headers):
+            _run(["g++", "-O3", "-std=c++17", "-fPIC", "-pthread", "-c", src, "-o", obj])
+        objs.append(obj)
+    if force or not _newer(LIB, objs):
+        _run([nvcc, "-shared", "-Xcompiler", "-pthread", *objs, "-lz", "-o", LIB])
     return LIB
 
 

@@ -27,6 +27,13 @@ int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
 }
+}  // namespace
+
+namespace wepp {
+int abi_fail(int code, const std::string& msg) { return fail(code, msg); }   // for the other ABI translation units
+}
+
+namespace {
 
 #define CU(call)                                                                                        \
     do {                                                                                                \
