@@ -173,19 +173,34 @@ class queuing_rw_mutex {
     std::shared_mutex m_;
 };
 
-// concurrent_unordered_{map,set}: single-lock wrappers are enough for the code paths exercised
+// concurrent_unordered_{map,set}: std containers whose inserting members take a lock (element references of
+// the node-based std containers stay valid across rehashing, as TBB's do), so the reference's concurrent
+// emplace / operator[] from inside parallel_for (src/mutation_annotated_tree.cpp:598-610) is safe.
 template <typename K, typename V, typename H = std::hash<K>, typename E = std::equal_to<K>>
 class concurrent_unordered_map : public std::unordered_map<K, V, H, E> {
   public:
     using base = std::unordered_map<K, V, H, E>;
-    using base::base;
+    concurrent_unordered_map() {}
+    concurrent_unordered_map(const concurrent_unordered_map& o) : base(o) {}
+    concurrent_unordered_map& operator=(const concurrent_unordered_map& o) { base::operator=(o); return *this; }
+    template <typename... A> auto emplace(A&&... a) { std::lock_guard<std::mutex> g(m_); return base::emplace(std::forward<A>(a)...); }
+    template <typename A> auto insert(A&& a) { std::lock_guard<std::mutex> g(m_); return base::insert(std::forward<A>(a)); }
+    V& operator[](const K& k) { std::lock_guard<std::mutex> g(m_); return base::operator[](k); }
     void unsafe_erase(const K& k) { this->erase(k); }
+  private:
+    std::mutex m_;
 };
 template <typename K, typename H = std::hash<K>, typename E = std::equal_to<K>>
 class concurrent_unordered_set : public std::unordered_set<K, H, E> {
   public:
     using base = std::unordered_set<K, H, E>;
-    using base::base;
+    concurrent_unordered_set() {}
+    concurrent_unordered_set(const concurrent_unordered_set& o) : base(o) {}
+    concurrent_unordered_set& operator=(const concurrent_unordered_set& o) { base::operator=(o); return *this; }
+    template <typename... A> auto emplace(A&&... a) { std::lock_guard<std::mutex> g(m_); return base::emplace(std::forward<A>(a)...); }
+    template <typename A> auto insert(A&& a) { std::lock_guard<std::mutex> g(m_); return base::insert(std::forward<A>(a)); }
+  private:
+    std::mutex m_;
 };
 
 template <typename K, typename V>
@@ -290,8 +305,16 @@ class task_group {
     void wait() {}
 };
 
+// flow graph: only has to compile (MAT::read_vcf, src/mutation_annotated_tree.cpp:1962-2031, is never run)
+class flow_control { public: void stop() {} };
 namespace flow {
 class graph { public: void wait_for_all() {} };
+enum { unlimited = 0, serial = 1 };
+template <typename In, typename Out>
+class function_node { public: template <typename B> function_node(graph&, int, B) {} };
+template <typename T>
+class input_node { public: template <typename B> input_node(graph&, B) {} void activate() {} };
+template <typename A, typename B> void make_edge(A&, B&) {}
 }  // namespace flow
 
 }  // namespace tbb

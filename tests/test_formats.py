@@ -210,3 +210,70 @@ def test_reads_loader_errors(tmp_path):
         wio.parse_reads(pb, ref[:50])          # reads beyond the reference
     with pytest.raises(WeppError):
         wio.parse_reads(pb[:-7], ref)
+
+
+# ---- pinned on the reference's own loader object code (oracle/_ref/wepp_ref, see oracle/Makefile) ----
+import os
+import subprocess
+
+REF_CLI = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "wepp_ref")
+needs_ref_cli = pytest.mark.skipif(not os.path.exists(REF_CLI), reason="oracle/_ref/wepp_ref not built (no /root/reference here)")
+
+
+def _ref_loadmat(path, uncondense):
+    out = subprocess.run([REF_CLI, "loadmat", str(path), "1" if uncondense else "0"], capture_output=True, text=True,
+                         check=True).stdout
+    nodes = {}
+    order = []
+    for line in out.splitlines():
+        ident, par, muts, clades = line.split("\t")
+        m = [tuple(int(x) for x in t.split(":")) for t in muts.split(",") if t]
+        nodes[ident] = (par, m, clades.split("|")[:-1])
+        order.append(ident)
+    return nodes, order
+
+
+@needs_ref_cli
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("uncondense", [False, True])
+def test_reference_loader_builds_the_same_tree(seed, uncondense, tmp_path):
+    """MAT::load_mutation_annotated_tree + uncondense_leaves, the reference's object code, on a gzipped
+    file written by the real protobuf runtime.  The reference expands condensed nodes in hash-map order, so
+    the comparison is by node id (parent id, mutations, annotations) and the fixture holds at most one
+    condensed node that gets a fresh node_<k> id."""
+    rng = np.random.default_rng(100 + seed)
+    pb = _random_mat(100 + seed, n_leaves=25 + 5 * seed, meta=seed != 3, condensed=False, with_len=seed % 2 == 0,
+                     with_labels=seed == 1)
+    data = formats.ParsimonyData()
+    data.ParseFromString(pb)
+    parent, ids, _, _ = formats.parse_newick(data.newick)
+    kids = {p for p in parent if p >= 0}
+    leaves = [v for v in range(len(parent)) if v not in kids]
+    with_muts = [v for v in leaves if len(data.node_mutations[v].mutation) > 0 and
+                 formats.load_mat(pb, False)["muts"][v]]
+    without = [v for v in leaves if not formats.load_mat(pb, False)["muts"][v]]
+    chosen = []
+    if with_muts:
+        chosen.append((with_muts[0], 3))                 # renamed node_<k>, three new children
+        chosen += [(v, 1) for v in with_muts[1:4]]       # single sample: plain rename
+    chosen += [(v, int(rng.integers(1, 4))) for v in without[:3]]   # siblings appended to the parent
+    for v, k in chosen:
+        cn = data.condensed_nodes.add()
+        cn.node_name = ids[v]
+        cn.condensed_leaves.extend([f"{ids[v]}_c{j}" for j in range(k)])
+    pb = data.SerializeToString()
+    path = tmp_path / "tree.pb.gz"
+    with gzip.open(path, "wb") as f:
+        f.write(pb)
+    ref_nodes, ref_order = _ref_loadmat(path, uncondense)
+    got = wio.load_mat(str(path), uncondense)
+    assert sorted(got.ids) == sorted(ref_nodes)
+    for v, ident in enumerate(got.ids):
+        par, muts, clades = ref_nodes[ident]
+        assert (got.ids[got.parent[v]] if got.parent[v] >= 0 else "") == par, ident
+        a, b = int(got.mut_off[v]), int(got.mut_off[v + 1])
+        mine = [(int(got.mut_pos[k]), int(got.mut_ref[k]), int(got.mut_par[k]), int(got.mut_nuc[k])) for k in range(a, b)]
+        assert mine == [tuple(np.int8(x) if i else x for i, x in enumerate(t)) for t in muts], ident
+        assert [c for c in got.clades[v]] == (clades + [""] * got.n_annotations)[: got.n_annotations], ident
+    if not uncondense:   # without condensed-node expansion the preorder itself is defined
+        assert got.ids == ref_order

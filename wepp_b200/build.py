@@ -74,7 +74,7 @@ def build_ref(force: bool = False) -> str | None:
     mk = os.path.join(ROOT, "oracle", "Makefile")
     if not os.path.isdir("/root/reference/src/WEPP") or not os.path.exists(mk):
         return REF_LIB if os.path.exists(REF_LIB) else None
-    _run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref"] + (["-B"] if force else []))
+    _run(["make", "-s", "-j4", "-C", os.path.join(ROOT, "oracle"), "ref", "refcli"] + (["-B"] if force else []))
     return REF_LIB
 
 
