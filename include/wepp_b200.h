@@ -128,6 +128,13 @@ int wepp_cartesian_map(wepp_handle* h, int64_t n_reads, const int32_t* start, co
 int wepp_rescore(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, int32_t* min_dist, int32_t* dist,
                  int64_t* am_off, int32_t* am_idx, int64_t am_capacity);
 
+/* The same over reads handed in directly (not the set_reads ones): the result writers score copies of
+ * the reads whose residual alleles were masked to N (arena::resolve_unaccounted_mutations,
+ * src/WEPP/arena.cpp:736-785, :846-857).  Needs only wepp_set_arena.  */
+int wepp_rescore_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const int32_t* end, const int64_t* rm_off,
+                       const int32_t* rm_pos, const uint8_t* rm_nuc, int32_t n_cand, const int32_t* cand_nodes,
+                       int32_t* min_dist, int32_t* dist, int64_t* am_off, int32_t* am_idx, int64_t am_capacity);
+
 /* The whole initial filter: wepp_filter::filter (src/WEPP/initial_filter.cpp:455-506) — cartesian_map over
  * the current reads with nothing mapped, then the greedy peak loop (step / clear_neighbors / singular_step /
  * find_correspondents / remove_read, :241-453: pick the top full_score = score * sqrt(dist_divergence) nodes
@@ -228,6 +235,15 @@ int  wepp_reads_get(const wepp_readset* r, int32_t* start, int32_t* end, int32_t
                     int32_t* rm_pos, uint8_t* rm_nuc, int64_t* name_off, char* name_chars);
 int  wepp_reads_get_reverse(const wepp_readset* r, int64_t* key_off, char* key_chars, int64_t* rev_off,
                             int64_t* val_off, char* val_chars);
+
+/* ---- The `wepp` command line (process boundary) -----------------------------------------
+ * Everything `build/wepp <command> ...` does, argv as main() gets it: `detectPeaks` (src/WEPP/main.cpp:47-49,
+ * pipeline.cpp:5-80: loaders -> arena -> initial filter on the GPU -> <P>_checkpoint.txt -> iterative Freyja
+ * post filter -> the result files of src/WEPP/arena.cpp:446-931), `sam2PB` (main.cpp:50-52, sam2pb.cpp:54-109),
+ * `help`.  Same flags and defaults as src/WEPP/util.cpp:145-158, same files, same exit codes (0; 1 on a fatal
+ * error or an invalid command; 0 for help / no command, main.cpp:36-45).  The executable built at build/wepp
+ * is a three-line main() around this call.  */
+int wepp_cli_main(int argc, const char* const* argv);
 
 /* Host-only introspection (no GPU needed; used by the CPU test-suite): the Euler-tour event
  * stripes built from an arena (4 x uint32 per entry: preorder idx, position, signed-delta bytes

@@ -35,7 +35,8 @@ def _run(cmd: list[str]) -> None:
         raise RuntimeError("build failed: " + " ".join(cmd))
 
 
-HOST_SRCS = ["host_prep.cpp", "host_arena.cpp", "host_io.cpp", "wepp_abi_io.cpp"]
+HOST_SRCS = ["host_prep.cpp", "host_arena.cpp", "host_io.cpp", "wepp_abi_io.cpp", "pipeline.cpp", "writers.cpp", "sam2pb.cpp"]
+CLI = os.path.join(ROOT, "build", "wepp")   # where the Snakemake rules expect the binary (workflow/rules/filter.smk:3)
 OBJ_DIR = os.path.join(ROOT, "wepp_b200", "build")
 
 
@@ -58,6 +59,11 @@ def build_cuda(force: bool = False) -> str:
         objs.append(obj)
     if force or not _newer(LIB, objs):
         _run([nvcc, "-shared", "-Xcompiler", "-pthread", *objs, "-lz", "-o", LIB])
+    main_src = os.path.join(CSRC, "wepp_main.cpp")
+    if force or not _newer(CLI, [main_src, LIB]):
+        os.makedirs(os.path.dirname(CLI), exist_ok=True)
+        _run(["g++", "-O2", "-std=c++17", main_src, "-o", CLI, "-L" + os.path.dirname(LIB), "-lwepp_b200",
+              "-Wl,-rpath,$ORIGIN/../wepp_b200", "-pthread"])
     return LIB
 
 

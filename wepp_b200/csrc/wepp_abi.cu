@@ -784,6 +784,23 @@ int wepp_rescore(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, int3
     return WEPP_OK;
 }
 
+int wepp_rescore_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const int32_t* end, const int64_t* rm_off,
+                       const int32_t* rm_pos, const uint8_t* rm_nuc, int32_t n_cand, const int32_t* cand_nodes,
+                       int32_t* min_dist, int32_t* dist, int64_t* am_off, int32_t* am_idx, int64_t am_capacity) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (!h->has_arena) return fail(WEPP_E_STATE, "wepp_set_arena must be called first");
+    if (n_reads < 0 || (n_reads > 0 && (!start || !end || !rm_off))) return fail(WEPP_E_INVALID, "bad read arrays");
+    if (n_cand < 1 || !cand_nodes || !min_dist) return fail(WEPP_E_INVALID, "bad candidate set / min_dist is NULL");
+    CU(cudaSetDevice(h->device));
+    static const int64_t zero_off[1] = {0};
+    std::string err;
+    int rc = rescore_run(h->device, h->stream, h->n_nodes, h->genome, h->parent.data(), h->mut_off.data(), h->mut_pos.data(),
+                         h->mut_ref.data(), h->mut_nuc.data(), n_reads, start, end, n_reads ? rm_off : zero_off, rm_pos, rm_nuc,
+                         n_cand, cand_nodes, min_dist, dist, am_off, am_idx, am_capacity, err);
+    if (rc) return fail(rc, err);
+    return WEPP_OK;
+}
+
 }  // extern "C"
 
 // ---- greedy peak selection (wepp_filter::filter, initial_filter.cpp:455-506) ---------------------
