@@ -51,6 +51,8 @@ SIGNATURES = {
     "wepp_cartesian_map": (C.c_int, [VP, C.c_int64] + [VP] * 11),
     "wepp_filter_peaks": (C.c_int, [VP, VP, VP, VP, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "wepp_rescore": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, C.c_int64]),
+    "wepp_rescore_reads": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, C.c_int32, VP, VP, VP, VP, VP, C.c_int64]),
+    "wepp_cli_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "wepp_device_buffer": (C.c_int, [VP, C.c_int32, C.POINTER(VP), C.POINTER(C.c_int64)]),
     "wepp_get_stats": (C.c_int, [VP, C.POINTER(WeppStats)]),
     "wepp_arena_build": (C.c_int, [C.c_int32, VP, VP, VP, VP, VP, C.c_int32, C.c_int32, VP, C.c_int64, VP, VP, VP, VP, VP, C.POINTER(VP)]),
