@@ -83,6 +83,38 @@ def test_empty_and_ragged_inputs():
     _check(one, reads, None)
 
 
+def test_device_and_host_keying_agree_and_validate_reads():
+    """wepp_set_reads keys the reads on the device (validation, bucket histogram, scatter); stripe
+    geometries whose cell table would be too large are keyed on the host.  Both must give the
+    oracle's results, and both must reject malformed reads with the same messages."""
+    from wepp_b200._lib import WeppError
+    arena, reads = cases.small_case(seed=7, n_reads=200)
+    _check(arena, reads, None, 1, 0)      # stripe width 1 on a 2,000-base genome: 8M cells -> host keying
+    _check(arena, reads, None, 32, 0)     # device keying
+    for q in (1, 32):
+        p = Placer(0, stripe_width=q)
+        p.set_arena(arena)
+
+        def bad(**kw):
+            r = synth.Reads(reads.start.copy(), reads.end.copy(), reads.degree.copy(), reads.rm_off.copy(),
+                            reads.rm_pos.copy(), reads.rm_nuc.copy())
+            for name, (i, v) in kw.items():
+                getattr(r, name)[i] = v
+            return r
+        has_mut = int(np.flatnonzero(np.diff(reads.rm_off) > 0)[0])
+        k = int(reads.rm_off[has_mut])
+        for r, msg in [(bad(start=(3, 0)), "read window"), (bad(end=(5, arena.genome_size + 1)), "read window"),
+                       (bad(degree=(0, -1)), "degree"), (bad(rm_nuc=(k, 3)), "allele code"),
+                       (bad(rm_pos=(k, int(reads.start[has_mut]) - 1)), "sorted, unique and inside")]:
+            with pytest.raises(WeppError, match=msg):
+                p.set_reads(r)
+        p.set_reads(reads)                # the handle is usable again after a rejected set
+        p.place(0, 0)
+        mp, _ = p.read_results()
+        assert np.array_equal(mp, oracle.cartesian_map(arena, reads, None, n_threads=4)["max_parsimony"])
+        p.close()
+
+
 def test_everything_mapped_gives_zero_multiplicity():
     arena, reads = cases.small_case(seed=5, n_reads=100)
     mapped = np.ones(arena.n_nodes, np.uint8)

@@ -163,95 +163,16 @@ static void parallel_for(int64_t n, F&& body) {
     for (auto& x : th) x.join();
 }
 
-std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t n_reads, const int32_t* start,
-                            const int32_t* end, const int32_t* degree, const int64_t* rm_off, const int32_t* rm_pos,
-                            const uint8_t* rm_nuc, int32_t reads_per_lane, const int64_t* subset, int64_t n_subset,
-                            ReadPlan& out) {
-    const int32_t q = es.stripe_width;
-    const int32_t bin_size = genome_size / NUM_RANGE_BINS;
-    const int64_t n_sel = subset ? n_subset : n_reads;
-    out = ReadPlan();
-    out.n_reads = n_sel;
-
-    // validation and window keys, in parallel
-    std::vector<int32_t> bucket_of((size_t)n_sel);
-    std::vector<int32_t> key_qs((size_t)n_sel), key_qe((size_t)n_sel);
-    std::vector<uint8_t> key_bin((size_t)n_sel);
-    std::vector<const char*> errs(64, nullptr);
-    parallel_for(n_sel, [&](int64_t a, int64_t b, int t) {
-        for (int64_t i = a; i < b; ++i) {
-            const int64_t r = subset ? subset[i] : i;
-            if (r < 0 || r >= n_reads) { errs[t] = "read index out of range"; return; }
-            const int32_t s = start[r], e = end[r];
-            if (s < 1 || s > genome_size || e > genome_size || e < s - 1) {
-                errs[t] = "read window must satisfy 1 <= start <= genome_size, start-1 <= end <= genome_size";
-                return;
-            }
-            if (degree[r] < 0) { errs[t] = "read degree must be >= 0"; return; }
-            if (rm_off[r + 1] < rm_off[r]) { errs[t] = "rm_off must be non-decreasing"; return; }
-            int32_t prev = s - 1;
-            for (int64_t k = rm_off[r]; k < rm_off[r + 1]; ++k) {
-                if (rm_pos[k] <= prev || rm_pos[k] > e) {
-                    errs[t] = "read mutations must be sorted, unique and inside [start,end]";
-                    return;
-                }
-                prev = rm_pos[k];
-                const uint8_t c = rm_nuc[k];
-                if (!(c == 1 || c == 2 || c == 4 || c == 8 || c == 15)) {
-                    errs[t] = "read allele code must be one of 1,2,4,8,15";
-                    return;
-                }
-            }
-            key_qs[i] = s / q;
-            key_qe[i] = std::max(e, s) / q;
-            key_bin[i] = (uint8_t)std::min(s / bin_size, NUM_RANGE_BINS - 1);
-        }
-    });
-    for (const char* e : errs)
-        if (e) return e;
-
-    // list and bucket ids in first-appearance order (flat tables: one short vector of (qe, list) per qs)
-    std::vector<std::vector<std::pair<int32_t, int32_t>>> lists_of_qs((size_t)es.n_stripes + 1);
-    std::vector<int32_t> bucket_id;   // [list * NUM_RANGE_BINS + bin]
-    std::vector<int64_t> bucket_count;
-    for (int64_t i = 0; i < n_sel; ++i) {
-        const int32_t qs = key_qs[i], qe = key_qe[i];
-        int32_t l = -1;
-        for (const auto& pr : lists_of_qs[qs])
-            if (pr.first == qe) {
-                l = pr.second;
-                break;
-            }
-        if (l < 0) {
-            l = (int32_t)out.lists.size();
-            lists_of_qs[qs].emplace_back(qe, l);
-            ListDesc ld;
-            ld.qs = qs;
-            ld.qe = qe;
-            ld.b0 = qs * q;
-            ld.width = (qe - qs + 1) * q;
-            ld.n = (int32_t)(1 + es.stripe_off[qe + 1] - es.stripe_off[qs]);
-            ld.off = 0;
-            ld.pad = 0;
-            out.lists.push_back(ld);
-            bucket_id.resize(out.lists.size() * NUM_RANGE_BINS, -1);
-        }
-        int32_t& b = bucket_id[(size_t)l * NUM_RANGE_BINS + key_bin[i]];
-        if (b < 0) {
-            b = (int32_t)out.buckets.size();
-            out.buckets.push_back(BucketDesc{0, l, (int32_t)key_bin[i]});
-            bucket_count.push_back(0);
-        }
-        bucket_of[i] = b;
-        ++bucket_count[b];
+// Lists, accumulator offsets, reads per tile and tiles from per-bucket read counts (shared by the
+// host keying below and the device keying of wepp_set_reads).  `first` gets nb + 1 offsets into
+// the bucket-sorted read order.
+std::string finish_read_plan(const EulerStripes& es, int32_t reads_per_lane, const std::vector<int64_t>& bucket_count,
+                             ReadPlan& out, std::vector<int64_t>& first) {
+    for (const ListDesc& l : out.lists) {
+        if (l.width > 65535) return "read window wider than 65535 bases is not supported";
+        out.max_width = std::max(out.max_width, l.width);
     }
-    if (out.lists.size() > 0) {
-        for (const ListDesc& l : out.lists) {
-            if (l.width > 65535) return "read window wider than 65535 bases is not supported";
-            out.max_width = std::max(out.max_width, l.width);
-        }
-    }
-    // offsets
+    (void)es;
     int64_t off = 0;
     for (ListDesc& l : out.lists) {
         l.off = off;
@@ -280,40 +201,10 @@ std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t
     }
     out.reads_per_tile = 32 * k;
 
-    // counting sort of the selected reads by bucket
     const size_t nb = out.buckets.size();
-    std::vector<int64_t> first(nb + 1, 0);
+    first.assign(nb + 1, 0);
     for (size_t b = 0; b < nb; ++b) first[b + 1] = first[b] + bucket_count[b];
-    out.perm.resize((size_t)n_sel);
-    {
-        std::vector<int64_t> cur(first.begin(), first.end() - 1);
-        for (int64_t i = 0; i < n_sel; ++i) out.perm[cur[bucket_of[i]]++] = subset ? subset[i] : i;
-    }
-    out.start.resize((size_t)n_sel);
-    out.end.resize((size_t)n_sel);
-    out.degree.resize((size_t)n_sel);
-    out.rm_off.assign((size_t)n_sel + 1, 0);
-    for (int64_t i = 0; i < n_sel; ++i) {
-        const int64_t r = out.perm[i];
-        out.rm_off[i + 1] = out.rm_off[i] + (rm_off[r + 1] - rm_off[r]);
-    }
-    out.rm_pos.resize((size_t)out.rm_off[n_sel]);
-    out.rm_code.resize((size_t)out.rm_off[n_sel]);
-    parallel_for(n_sel, [&](int64_t a, int64_t b, int) {
-        for (int64_t i = a; i < b; ++i) {
-            const int64_t r = out.perm[i];
-            out.start[i] = start[r];
-            out.end[i] = end[r];
-            out.degree[i] = degree[r];
-            int64_t o = out.rm_off[i];
-            for (int64_t kk = rm_off[r]; kk < rm_off[r + 1]; ++kk, ++o) {
-                out.rm_pos[o] = rm_pos[kk];
-                const uint8_t c = rm_nuc[kk];
-                out.rm_code[o] = c == 1 ? 1 : c == 2 ? 2 : c == 4 ? 3 : c == 8 ? 4 : 5;
-            }
-        }
-    });
-    // tiles, longest lists first (LPT order for the persistent-warp scheduler)
+    // tiles, longest lists first (LPT order for the persistent-CTA scheduler)
     for (size_t b = 0; b < nb; ++b) {
         const int64_t c = bucket_count[b];
         for (int64_t o = 0; o < c; o += out.reads_per_tile) {
@@ -330,6 +221,122 @@ std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t
         return out.lists[out.buckets[a.bucket].list].n > out.lists[out.buckets[b.bucket].list].n;
     });
     return "";
+}
+
+ListDesc make_list_desc(const EulerStripes& es, int32_t qs, int32_t qe) {
+    const int32_t q = es.stripe_width;
+    ListDesc ld;
+    ld.qs = qs;
+    ld.qe = qe;
+    ld.b0 = qs * q;
+    ld.width = (qe - qs + 1) * q;
+    ld.n = (int32_t)(1 + es.stripe_off[qe + 1] - es.stripe_off[qs]);
+    ld.off = 0;
+    ld.pad = 0;
+    return ld;
+}
+
+std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t n_reads, const int32_t* start,
+                            const int32_t* end, const int32_t* degree, const int64_t* rm_off, const int32_t* rm_pos,
+                            const uint8_t* rm_nuc, int32_t reads_per_lane, const int64_t* subset, int64_t n_subset,
+                            ReadPlan& out) {
+    const int32_t q = es.stripe_width;
+    const int32_t bin_size = genome_size / NUM_RANGE_BINS;
+    const int64_t n_sel = subset ? n_subset : n_reads;
+    out = ReadPlan();
+    out.n_reads = n_sel;
+
+    // validation and window keys, in parallel
+    std::vector<int32_t> bucket_of((size_t)n_sel);
+    std::vector<int32_t> key_qs((size_t)n_sel), key_qe((size_t)n_sel);
+    std::vector<uint8_t> key_bin((size_t)n_sel);
+    std::vector<const char*> errs(64, nullptr);
+    std::vector<int64_t> n_mut(64, 0);
+    parallel_for(n_sel, [&](int64_t a, int64_t b, int t) {
+        for (int64_t i = a; i < b; ++i) {
+            const int64_t r = subset ? subset[i] : i;
+            if (r < 0 || r >= n_reads) { errs[t] = "read index out of range"; return; }
+            const int32_t s = start[r], e = end[r];
+            if (s < 1 || s > genome_size || e > genome_size || e < s - 1) {
+                errs[t] = read_plan_error(RP_ERR_WINDOW);
+                return;
+            }
+            if (degree[r] < 0) { errs[t] = read_plan_error(RP_ERR_DEGREE); return; }
+            if (rm_off[r + 1] < rm_off[r]) { errs[t] = read_plan_error(RP_ERR_OFFSETS); return; }
+            int32_t prev = s - 1;
+            for (int64_t k = rm_off[r]; k < rm_off[r + 1]; ++k) {
+                if (rm_pos[k] <= prev || rm_pos[k] > e) {
+                    errs[t] = read_plan_error(RP_ERR_MUT_ORDER);
+                    return;
+                }
+                prev = rm_pos[k];
+                const uint8_t c = rm_nuc[k];
+                if (!(c == 1 || c == 2 || c == 4 || c == 8 || c == 15)) {
+                    errs[t] = read_plan_error(RP_ERR_MUT_CODE);
+                    return;
+                }
+            }
+            n_mut[t] += rm_off[r + 1] - rm_off[r];
+            key_qs[i] = s / q;
+            key_qe[i] = std::max(e, s) / q;
+            key_bin[i] = (uint8_t)std::min(s / bin_size, NUM_RANGE_BINS - 1);
+        }
+    });
+    for (const char* e : errs)
+        if (e) return e;
+    for (int64_t m : n_mut) out.n_read_muts += m;
+
+    // list and bucket ids in first-appearance order (flat tables: one short vector of (qe, list) per qs)
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> lists_of_qs((size_t)es.n_stripes + 1);
+    std::vector<int32_t> bucket_id;   // [list * NUM_RANGE_BINS + bin]
+    std::vector<int64_t> bucket_count;
+    for (int64_t i = 0; i < n_sel; ++i) {
+        const int32_t qs = key_qs[i], qe = key_qe[i];
+        int32_t l = -1;
+        for (const auto& pr : lists_of_qs[qs])
+            if (pr.first == qe) {
+                l = pr.second;
+                break;
+            }
+        if (l < 0) {
+            l = (int32_t)out.lists.size();
+            lists_of_qs[qs].emplace_back(qe, l);
+            out.lists.push_back(make_list_desc(es, qs, qe));
+            bucket_id.resize(out.lists.size() * NUM_RANGE_BINS, -1);
+        }
+        int32_t& b = bucket_id[(size_t)l * NUM_RANGE_BINS + key_bin[i]];
+        if (b < 0) {
+            b = (int32_t)out.buckets.size();
+            out.buckets.push_back(BucketDesc{0, l, (int32_t)key_bin[i]});
+            bucket_count.push_back(0);
+        }
+        bucket_of[i] = b;
+        ++bucket_count[b];
+    }
+    std::vector<int64_t> first;
+    std::string err = finish_read_plan(es, reads_per_lane, bucket_count, out, first);
+    if (!err.empty()) return err;
+
+    // stable counting sort of the selected reads by bucket: sorted position -> caller's index.  The
+    // reads themselves stay where they are (the device keeps them in caller order and the placement
+    // kernel goes through this permutation).
+    out.perm.resize((size_t)n_sel);
+    {
+        std::vector<int64_t> cur(first.begin(), first.end() - 1);
+        for (int64_t i = 0; i < n_sel; ++i) out.perm[cur[bucket_of[i]]++] = subset ? subset[i] : i;
+    }
+    return "";
+}
+
+const char* read_plan_error(int code) {
+    switch (code) {
+        case RP_ERR_WINDOW: return "read window must satisfy 1 <= start <= genome_size, start-1 <= end <= genome_size";
+        case RP_ERR_DEGREE: return "read degree must be >= 0";
+        case RP_ERR_OFFSETS: return "rm_off must be non-decreasing";
+        case RP_ERR_MUT_ORDER: return "read mutations must be sorted, unique and inside [start,end]";
+        case RP_ERR_MUT_CODE: return "read allele code must be one of 1,2,4,8,15";
+        default: return "invalid reads";
+    }
 }
 
 }  // namespace wepp

@@ -68,14 +68,10 @@ struct TileDesc {
 
 struct ReadPlan {
     int64_t n_reads = 0;
+    int64_t n_read_muts = 0;        // mutations of the selected reads
     int32_t reads_per_tile = 256;
     int32_t max_width = 0;
-    // reads in bucket-sorted order
-    std::vector<int32_t> start, end, degree;
-    std::vector<int64_t> rm_off;
-    std::vector<int32_t> rm_pos;
-    std::vector<uint8_t> rm_code;   // 1..4 = A,C,G,T ; 5 = N
-    std::vector<int64_t> perm;      // sorted index -> caller's index
+    std::vector<int64_t> perm;      // bucket-sorted position -> caller's read index (the reads stay in caller order)
     std::vector<ListDesc> lists;
     std::vector<BucketDesc> buckets;
     std::vector<TileDesc> tiles;    // longest lists first
@@ -85,10 +81,21 @@ struct ReadPlan {
     int64_t scanned_read_entries = 0;  // sum over reads of list length
 };
 
+// Read validation errors (shared by the host keying and the device keying kernel).
+enum { RP_OK = 0, RP_ERR_WINDOW = 1, RP_ERR_DEGREE = 2, RP_ERR_OFFSETS = 3, RP_ERR_MUT_ORDER = 4, RP_ERR_MUT_CODE = 5 };
+const char* read_plan_error(int code);
+
+// Host keying (place_subset, the peak loop, and the fallback of wepp_set_reads): validates the
+// reads, keys them by (stripe range, count bin) and produces the permutation + descriptors.
 // reads_per_lane: 0 = pick from the widest bucket, else 2/4/8.
 std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t n_reads, const int32_t* start,
                             const int32_t* end, const int32_t* degree, const int64_t* rm_off, const int32_t* rm_pos,
                             const uint8_t* rm_nuc, int32_t reads_per_lane, const int64_t* subset, int64_t n_subset,
                             ReadPlan& out);
+
+// Descriptor half of the plan, from per-bucket read counts (out.lists / out.buckets already filled).
+ListDesc make_list_desc(const EulerStripes& es, int32_t qs, int32_t qe);
+std::string finish_read_plan(const EulerStripes& es, int32_t reads_per_lane, const std::vector<int64_t>& bucket_count,
+                             ReadPlan& out, std::vector<int64_t>& first);
 
 }  // namespace wepp

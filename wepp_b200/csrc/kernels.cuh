@@ -10,7 +10,8 @@
 //                              at index 0; each evaluated entry carries its countable-node count
 //   prev_boundary int32[]     per list entry: the boundary entry whose state encloses it
 //   chunk_start  int32[][W+1] per list: the W scan chunks (each starts on a boundary entry)
-//   reads        SoA          start/end/degree + sparse (pos, code) mutations, bucket-sorted
+//   reads        SoA          start/end/degree + sparse (pos, class) mutations in caller order, and the
+//                              bucket-sorted permutation `perm` the tiles index
 //   accS/accC    double/int32 per bucket, per list entry: sum of read weights / degrees whose
 //                              EPP set contains the entry's nodes
 //   diff_lo/hi   uint64[N+1]  128-bit fixed-point difference array for the per-node score
@@ -52,13 +53,13 @@ struct PlaceParams {
     int32_t n_tiles;
     int32_t n_nodes;
     int* tile_counter;
-    // reads (bucket-sorted)
+    // reads, in caller order; perm = bucket-sorted position -> caller's read index
     const int32_t* start;
     const int32_t* end;
     const int32_t* degree;
     const int64_t* rm_off;
     const int32_t* rm_pos;
-    const uint8_t* rm_code;
+    const uint8_t* rm_code;   // allele class 1..4 = A,C,G,T ; 5 = N
     const int64_t* perm;
     // mask
     const uint8_t* mapped;  // may be null
@@ -274,6 +275,84 @@ __global__ void finalize_lists_kernel(Entry* __restrict__ lists, const ListDesc*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Read keying on the device (wepp_set_reads): the reads are uploaded once, in caller order, and
+// stay there; these two kernels validate them, translate the allele codes, count the reads of
+// every (stripe range, count bin) cell and scatter the read indices into bucket order.  The
+// host only turns the (small) cell histogram into list / bucket / tile descriptors in between.
+//   cell = (qs * span_cap + (qe - qs)) * bins_per_stripe + (bin - first bin of stripe qs)
+struct ReadKeyParams {
+    int64_t n_reads, n_muts;
+    int32_t genome, q, bin_size, span_cap, bins_per_stripe;
+    const int32_t* start;
+    const int32_t* end;
+    const int32_t* degree;
+    const int64_t* rm_off;
+    const int32_t* rm_pos;
+    const uint8_t* rm_nuc;           // 1,2,4,8 = A,C,G,T ; 15 = N (mutation_annotated_tree.cpp:19-74)
+    uint8_t* rm_code;                // out: 1..5
+    int32_t* cell;                   // out: per read
+    int32_t* table;                  // out: reads per cell (zeroed by the caller)
+    unsigned long long* true_counts; // out: degree-weighted reads per count bin (arena.cpp:138-151)
+    int* status;                     // out: [0] = max RP_ERR_* code seen, [1] = 1 if a window exceeds span_cap
+};
+
+__global__ void read_keys_kernel(const ReadKeyParams p) {
+    __shared__ unsigned long long tc[NBINS];
+    for (int j = threadIdx.x; j < NBINS; j += blockDim.x) tc[j] = 0ull;
+    __syncthreads();
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < p.n_reads; r += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t s = p.start[r], e = p.end[r], d = p.degree[r];
+        const int64_t a = p.rm_off[r], b = p.rm_off[r + 1];
+        int err = RP_OK;
+        if (s < 1 || s > p.genome || e > p.genome || e < s - 1) err = RP_ERR_WINDOW;
+        else if (d < 0) err = RP_ERR_DEGREE;
+        else if (a < 0 || b < a || b > p.n_muts) err = RP_ERR_OFFSETS;
+        else {
+            int32_t prev = s - 1;
+            for (int64_t k = a; k < b; ++k) {
+                const int32_t pos = p.rm_pos[k];
+                const uint32_t c = p.rm_nuc[k];
+                if (pos <= prev || pos > e) err = max(err, (int)RP_ERR_MUT_ORDER);
+                prev = pos;
+                if (!(c == 1u || c == 2u || c == 4u || c == 8u || c == 15u)) err = max(err, (int)RP_ERR_MUT_CODE);
+                p.rm_code[k] = (uint8_t)(c == 15u ? 5u : (uint32_t)__ffs((int)c));
+            }
+        }
+        if (err != RP_OK) {
+            atomicMax(&p.status[0], err);
+            p.cell[r] = -1;
+            continue;
+        }
+        const int32_t qs = s / p.q, qe = max(e, s) / p.q;
+        const int32_t bin = min(s / p.bin_size, NBINS - 1);
+        const int32_t bin0 = min((qs * p.q) / p.bin_size, NBINS - 1);
+        atomicAdd(&tc[bin], (unsigned long long)d);
+        if (qe - qs >= p.span_cap || bin - bin0 >= p.bins_per_stripe) {   // not in the table: the host keys this set
+            p.status[1] = 1;
+            p.cell[r] = -1;
+            continue;
+        }
+        const int32_t cell = (qs * p.span_cap + (qe - qs)) * p.bins_per_stripe + (bin - bin0);
+        p.cell[r] = cell;
+        atomicAdd(&p.table[cell], 1);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < NBINS; j += blockDim.x)
+        if (tc[j]) atomicAdd(&p.true_counts[j], tc[j]);
+}
+
+// cursor[b] starts at the bucket's first sorted position.  The order inside a bucket is the order
+// the atomics land in: it only decides which reads share a tile, never a result.
+__global__ void read_scatter_kernel(int64_t n_reads, const int32_t* __restrict__ cell,
+                                    const int32_t* __restrict__ bucket_of_cell, unsigned long long* __restrict__ cursor,
+                                    int64_t* __restrict__ perm) {
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_reads; r += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t b = bucket_of_cell[cell[r]];
+        perm[atomicAdd(&cursor[b], 1ull)] = r;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Out-of-line (rare) EPP list emission: nodes of [a, b) that are not mapped.
 __device__ __noinline__ void emit_range(int32_t* __restrict__ out, unsigned long long& wp, uint32_t a, uint32_t b,
                                         const uint8_t* __restrict__ mapped) {
@@ -405,7 +484,7 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
             for (int j = 0; j < K; ++j) {
                 const int ti = lane * K + j;
                 const bool valid = ti < td.count;
-                rid[j] = valid ? td.first + ti : -1;
+                rid[j] = valid ? p.perm[td.first + ti] : -1;   // caller's read index
                 s_rel[j] = valid ? p.start[rid[j]] - ld.b0 : 1;
                 e_rel[j] = valid ? p.end[rid[j]] - ld.b0 : 0;
                 run0[j] = 0;
@@ -584,7 +663,7 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) place_kernel(const PlaceP
                     deg[j] = d;
                 }
                 if (warp == 0) {
-                    const int64_t orig = p.perm[rid[j]];
+                    const int64_t orig = rid[j];
                     p.max_pars[orig] = best[j];
                     p.mult[orig] = cnt[j];
                     if (EPP && p.epp_off) {

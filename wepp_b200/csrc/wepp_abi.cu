@@ -92,19 +92,28 @@ struct wepp_handle {
     DevBuf<int32_t> d_mapped_prefix;
     bool lists_final = false;
 
-    // reads (caller copy kept for subset plans and rescore)
+    // reads: resident on the device in caller order (uploaded once by wepp_set_reads); the host copy is
+    // fetched back only when a host-side consumer needs it (subset plans, rescore) — ensure_host_reads()
     bool has_reads = false;
-    int64_t n_reads = 0;
+    bool host_reads = false;
+    int64_t n_reads = 0, n_read_muts = 0;
     std::vector<int32_t> r_start, r_end, r_degree;
     std::vector<int64_t> r_off;
     std::vector<int32_t> r_pos;
     std::vector<uint8_t> r_nuc;
+    DevBuf<int32_t> d_rstart, d_rend, d_rdegree, d_rpos;
+    DevBuf<int64_t> d_roff;
+    DevBuf<uint8_t> d_rnuc, d_rcode;
+    // device keying scratch (wepp_set_reads)
+    DevBuf<int32_t> d_cell, d_table, d_bucket_of_cell;
+    DevBuf<unsigned long long> d_cursor, d_true_counts;
+    DevBuf<int> d_key_status;
+    void* h_stage = nullptr;   // pinned: key status + true counts + cell table
+    size_t h_stage_cap = 0;
 
     struct DevPlan {
         ReadPlan plan;
-        DevBuf<int32_t> start, end, degree, rm_pos;
-        DevBuf<int64_t> rm_off, perm;
-        DevBuf<uint8_t> rm_code;
+        DevBuf<int64_t> perm;
         DevBuf<ListDesc> lists;
         DevBuf<BucketDesc> buckets;
         DevBuf<TileDesc> tiles;
@@ -113,8 +122,7 @@ struct wepp_handle {
         DevBuf<int32_t> chunk_start;     // [n_lists][PLACE_WARPS + 1]
         bool final_for_mask = false;
         void release() {
-            start.release(); end.release(); degree.release(); rm_pos.release(); rm_off.release(); perm.release();
-            rm_code.release(); lists.release(); buckets.release(); tiles.release(); entries.release();
+            perm.release(); lists.release(); buckets.release(); tiles.release(); entries.release();
             prev_boundary.release(); chunk_start.release();
         }
     };
@@ -151,15 +159,11 @@ cudaError_t upload(DevBuf<T>& b, const std::vector<T>& v, cudaStream_t s) {
     return cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
 }
 
-int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp) {
+// Descriptors (and, for a host-keyed plan, the permutation) to the device, then the per-window
+// Euler lists.  A device-keyed plan has already written dp.perm itself.
+int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp, bool host_perm) {
     ReadPlan& pl = dp.plan;
-    CU(upload(dp.start, pl.start, h->stream));
-    CU(upload(dp.end, pl.end, h->stream));
-    CU(upload(dp.degree, pl.degree, h->stream));
-    CU(upload(dp.rm_off, pl.rm_off, h->stream));
-    CU(upload(dp.rm_pos, pl.rm_pos, h->stream));
-    CU(upload(dp.rm_code, pl.rm_code, h->stream));
-    CU(upload(dp.perm, pl.perm, h->stream));
+    if (host_perm) CU(upload(dp.perm, pl.perm, h->stream));
     CU(upload(dp.lists, pl.lists, h->stream));
     CU(upload(dp.buckets, pl.buckets, h->stream));
     CU(upload(dp.tiles, pl.tiles, h->stream));
@@ -175,6 +179,27 @@ int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp) {
         CU(cudaGetLastError());
     }
     dp.final_for_mask = false;
+    return WEPP_OK;
+}
+
+// Host copy of the resident reads, for the host-side consumers (subset plans, rescore).
+int ensure_host_reads(wepp_handle* h) {
+    if (h->host_reads) return WEPP_OK;
+    const size_t n = (size_t)h->n_reads, nm = (size_t)h->n_read_muts;
+    h->r_start.resize(n); h->r_end.resize(n); h->r_degree.resize(n); h->r_off.resize(n + 1);
+    h->r_pos.resize(nm); h->r_nuc.resize(nm);
+    if (n) {
+        CU(cudaMemcpyAsync(h->r_start.data(), h->d_rstart.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->r_end.data(), h->d_rend.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->r_degree.data(), h->d_rdegree.p, n * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaMemcpyAsync(h->r_off.data(), h->d_roff.p, (n + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (nm) {
+        CU(cudaMemcpyAsync(h->r_pos.data(), h->d_rpos.p, nm * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->r_nuc.data(), h->d_rnuc.p, nm, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    h->host_reads = true;
     return WEPP_OK;
 }
 
@@ -258,12 +283,12 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     pp.n_tiles = (int32_t)pl.tiles.size();
     pp.n_nodes = n;
     pp.tile_counter = h->d_tile_counter.p;
-    pp.start = dp.start.p;
-    pp.end = dp.end.p;
-    pp.degree = dp.degree.p;
-    pp.rm_off = dp.rm_off.p;
-    pp.rm_pos = dp.rm_pos.p;
-    pp.rm_code = dp.rm_code.p;
+    pp.start = h->d_rstart.p;
+    pp.end = h->d_rend.p;
+    pp.degree = h->d_rdegree.p;
+    pp.rm_off = h->d_roff.p;
+    pp.rm_pos = h->d_rpos.p;
+    pp.rm_code = h->d_rcode.p;
     pp.perm = dp.perm.p;
     pp.mapped = h->has_mask ? h->d_mapped.p : nullptr;
     pp.max_pars = h->d_maxpars.p;
@@ -339,7 +364,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     // Algorithmic bytes of one place (DESIGN.md "Roofline"): two passes over each tile's Euler
     // list (16 B entries), the packed reads once, per-read results, the segment accumulators
     // written and read once, and the per-node difference arrays / results written and scanned.
-    const int64_t rm = pl.rm_off.empty() ? 0 : pl.rm_off.back();
+    const int64_t rm = pl.n_read_muts;
     int64_t bytes = pl.scanned_entries * 16 * (accumulate ? 2 : 1);
     bytes += pl.n_reads * (12 + 8 + 8) + rm * 5;
     bytes += pl.n_reads * 8;
@@ -396,6 +421,10 @@ void wepp_destroy(wepp_handle* h) {
     cudaStreamSynchronize(h->stream);
     h->d_stripes.release(); h->d_stripe_off.release(); h->d_mapped.release(); h->d_mapped_prefix.release();
     h->full.release(); h->sub.release();
+    h->d_rstart.release(); h->d_rend.release(); h->d_rdegree.release(); h->d_rpos.release(); h->d_roff.release();
+    h->d_rnuc.release(); h->d_rcode.release(); h->d_cell.release(); h->d_table.release(); h->d_bucket_of_cell.release();
+    h->d_cursor.release(); h->d_true_counts.release(); h->d_key_status.release();
+    if (h->h_stage) cudaFreeHost(h->h_stage);
     h->d_accS.release(); h->d_accC.release(); h->d_maxpars.release(); h->d_mult.release(); h->d_score.release();
     h->d_counts.release(); h->d_divergence.release(); h->d_diff_lo.release(); h->d_diff_hi.release(); h->d_chunk128.release();
     h->d_cchunk_tot.release(); h->d_cchunk_off.release(); h->d_epp_off.release(); h->d_epp_nodes.release();
@@ -452,28 +481,120 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
     CU(cudaSetDevice(h->device));
     static const int64_t zero_off[1] = {0};
     if (n_reads == 0) rm_off = zero_off;
-    std::string err = build_read_plan(h->es, h->genome, n_reads, start, end, degree, rm_off, rm_pos, rm_nuc, h->opt_k,
-                                      nullptr, 0, h->full.plan);
-    if (!err.empty()) return fail(WEPP_E_INVALID, err);
-    h->n_reads = n_reads;
-    h->r_start.assign(start, start + n_reads);
-    h->r_end.assign(end, end + n_reads);
-    h->r_degree.assign(degree, degree + n_reads);
-    h->r_off.assign(rm_off, rm_off + n_reads + 1);
     const int64_t nm = rm_off[n_reads];
-    h->r_pos.assign(rm_pos, rm_pos + nm);
-    h->r_nuc.assign(rm_nuc, rm_nuc + nm);
-    {   // degree-weighted reads per start bin (arena.cpp:138-151)
-        const int32_t bin_size = h->genome / NBINS;
-        int64_t tc[NBINS] = {};
-        for (int64_t r = 0; r < n_reads; ++r) tc[std::min(start[r] / bin_size, NBINS - 1)] += degree[r];
-        for (int j = 0; j < NBINS; ++j) h->true_counts[j] = (int32_t)tc[j];
-    }
-    int rc = upload_plan(h, h->full);
-    if (rc) return rc;
-    CU(cudaStreamSynchronize(h->stream));
-    h->has_reads = true;
+    if (nm < 0 || (nm > 0 && (!rm_pos || !rm_nuc))) return fail(WEPP_E_INVALID, "read mutation arrays are NULL / rm_off is negative");
+    h->has_reads = false;
     h->has_results = false;
+    h->host_reads = false;
+    cudaStream_t st = h->stream;
+    const size_t n = (size_t)n_reads;
+
+    // ---- the reads go to the device once, as they are (caller order) ------------------------------
+    CU(h->d_rstart.ensure(n)); CU(h->d_rend.ensure(n)); CU(h->d_rdegree.ensure(n)); CU(h->d_roff.ensure(n + 1));
+    CU(h->d_rpos.ensure((size_t)nm)); CU(h->d_rnuc.ensure((size_t)nm)); CU(h->d_rcode.ensure((size_t)nm));
+    if (n) {
+        CU(cudaMemcpyAsync(h->d_rstart.p, start, n * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(h->d_rend.p, end, n * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(h->d_rdegree.p, degree, n * 4, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaMemcpyAsync(h->d_roff.p, rm_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nm) {
+        CU(cudaMemcpyAsync(h->d_rpos.p, rm_pos, (size_t)nm * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(h->d_rnuc.p, rm_nuc, (size_t)nm, cudaMemcpyHostToDevice, st));
+    }
+
+    // ---- keying kernel: validation, allele classes, true read counts, reads per (window, bin) cell ----
+    const int32_t q = h->es.stripe_width, n_stripes = h->es.n_stripes;
+    const int32_t bin_size = h->genome / NBINS;
+    const int64_t span_cap = std::min<int64_t>(n_stripes, MAX_WINDOW / q + 2);
+    const int64_t bins_per_stripe = std::min<int64_t>(NBINS, q / std::max(bin_size, 1) + 2);
+    const int64_t n_cells = (int64_t)n_stripes * span_cap * bins_per_stripe;
+    const bool device_keys = n_reads > 0 && n_cells <= (int64_t)(1 << 22);   // else: host keying below
+    const size_t stage_bytes = 16 + NBINS * 8 + (device_keys ? (size_t)n_cells * 4 : 0);
+    if (stage_bytes > h->h_stage_cap) {
+        if (h->h_stage) cudaFreeHost(h->h_stage);
+        h->h_stage = nullptr;
+        h->h_stage_cap = 0;
+        CU(cudaMallocHost(&h->h_stage, stage_bytes));
+        h->h_stage_cap = stage_bytes;
+    }
+    int* st_status = reinterpret_cast<int*>(h->h_stage);
+    unsigned long long* st_true = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(h->h_stage) + 16);
+    int32_t* st_table = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(h->h_stage) + 16 + NBINS * 8);
+    CU(h->d_key_status.ensure(4)); CU(h->d_true_counts.ensure(NBINS)); CU(h->d_cell.ensure(n));
+    CU(h->d_table.ensure((size_t)(device_keys ? n_cells : 1)));
+    CU(cudaMemsetAsync(h->d_key_status.p, 0, 4 * sizeof(int), st));
+    CU(cudaMemsetAsync(h->d_true_counts.p, 0, NBINS * 8, st));
+    if (device_keys) CU(cudaMemsetAsync(h->d_table.p, 0, (size_t)n_cells * 4, st));
+    if (n_reads > 0) {
+        ReadKeyParams kp = {};
+        kp.n_reads = n_reads; kp.n_muts = nm; kp.genome = h->genome; kp.q = q; kp.bin_size = bin_size;
+        kp.span_cap = device_keys ? (int32_t)span_cap : 0;   // 0: every read reports "window exceeds the table"
+        kp.bins_per_stripe = (int32_t)bins_per_stripe;
+        kp.start = h->d_rstart.p; kp.end = h->d_rend.p; kp.degree = h->d_rdegree.p; kp.rm_off = h->d_roff.p;
+        kp.rm_pos = h->d_rpos.p; kp.rm_nuc = h->d_rnuc.p; kp.rm_code = h->d_rcode.p; kp.cell = h->d_cell.p;
+        kp.table = h->d_table.p; kp.true_counts = h->d_true_counts.p; kp.status = h->d_key_status.p;
+        const int blocks = (int)std::min<int64_t>((n_reads + 255) / 256, (int64_t)h->n_sms * 8);
+        read_keys_kernel<<<blocks, 256, 0, st>>>(kp);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(st_status, h->d_key_status.p, 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(st_true, h->d_true_counts.p, NBINS * 8, cudaMemcpyDeviceToHost, st));
+    if (device_keys) CU(cudaMemcpyAsync(st_table, h->d_table.p, (size_t)n_cells * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));   // also: the caller's buffers are consumed from here on
+    if (st_status[0] != RP_OK) return fail(WEPP_E_INVALID, read_plan_error(st_status[0]));
+    h->n_reads = n_reads;
+    h->n_read_muts = nm;
+
+    ReadPlan& pl = h->full.plan;
+    bool host_perm = false;
+    if (device_keys && st_status[1] == 0) {
+        // ---- descriptors from the cell histogram; the reads are scattered into bucket order on the device ----
+        pl = ReadPlan();
+        pl.n_reads = n_reads;
+        pl.n_read_muts = nm;
+        std::vector<int32_t> bucket_of_cell((size_t)n_cells, -1);
+        std::vector<int64_t> bucket_count;
+        for (int32_t qs = 0; qs < n_stripes; ++qs) {
+            const int32_t bin0 = std::min((qs * q) / std::max(bin_size, 1), NBINS - 1);
+            for (int32_t sp = 0; sp < span_cap; ++sp) {
+                int32_t list = -1;
+                for (int32_t bb = 0; bb < bins_per_stripe; ++bb) {
+                    const size_t cell = ((size_t)qs * span_cap + sp) * bins_per_stripe + bb;
+                    const int32_t c = st_table[cell];
+                    if (c == 0) continue;
+                    if (list < 0) {
+                        list = (int32_t)pl.lists.size();
+                        pl.lists.push_back(make_list_desc(h->es, qs, qs + sp));
+                    }
+                    bucket_of_cell[cell] = (int32_t)pl.buckets.size();
+                    pl.buckets.push_back(BucketDesc{0, list, bin0 + bb});
+                    bucket_count.push_back(c);
+                }
+            }
+        }
+        std::vector<int64_t> first;
+        std::string err = finish_read_plan(h->es, h->opt_k, bucket_count, pl, first);
+        if (!err.empty()) return fail(WEPP_E_INVALID, err);
+        std::vector<unsigned long long> cursor(first.begin(), first.end());
+        CU(upload(h->d_bucket_of_cell, bucket_of_cell, st));
+        CU(upload(h->d_cursor, cursor, st));
+        CU(h->full.perm.ensure(n));
+        const int blocks = (int)std::min<int64_t>((n_reads + 255) / 256, (int64_t)h->n_sms * 8);
+        read_scatter_kernel<<<blocks, 256, 0, st>>>(n_reads, h->d_cell.p, h->d_bucket_of_cell.p, h->d_cursor.p, h->full.perm.p);
+        CU(cudaGetLastError());
+    } else {
+        // ---- host keying: stripe geometries whose cell table would be too large, windows wider than the
+        //      table's span, and the empty read set ----
+        std::string err = build_read_plan(h->es, h->genome, n_reads, start, end, degree, rm_off, rm_pos, rm_nuc, h->opt_k,
+                                          nullptr, 0, pl);
+        if (!err.empty()) return fail(WEPP_E_INVALID, err);
+        host_perm = true;
+    }
+    for (int j = 0; j < NBINS; ++j) h->true_counts[j] = (int32_t)st_true[j];
+    int rc = upload_plan(h, h->full, host_perm);
+    if (rc) return rc;
+    h->has_reads = true;
     return WEPP_OK;
 }
 
@@ -511,11 +632,13 @@ int wepp_place_subset(wepp_handle* h, int64_t n_sel, const int64_t* read_idx, in
     if (!h->has_reads) return fail(WEPP_E_STATE, "wepp_set_reads must be called first");
     if (n_sel < 0 || (n_sel > 0 && !read_idx)) return fail(WEPP_E_INVALID, "bad subset");
     CU(cudaSetDevice(h->device));
+    int rc = ensure_host_reads(h);
+    if (rc) return rc;
     std::string err = build_read_plan(h->es, h->genome, h->n_reads, h->r_start.data(), h->r_end.data(), h->r_degree.data(),
                                       h->r_off.data(), h->r_pos.data(), h->r_nuc.data(), h->opt_k, read_idx, n_sel,
                                       h->sub.plan);
     if (!err.empty()) return fail(WEPP_E_INVALID, err);
-    int rc = upload_plan(h, h->sub);
+    rc = upload_plan(h, h->sub, true);
     if (rc) return rc;
     if (!h->has_results) {  // per-read arrays may not exist yet
         CU(h->d_maxpars.ensure((size_t)h->n_reads));
@@ -776,7 +899,9 @@ int wepp_rescore(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, int3
     if (n_cand < 1 || !cand_nodes || !min_dist) return fail(WEPP_E_INVALID, "bad candidate set / min_dist is NULL");
     CU(cudaSetDevice(h->device));
     std::string err;
-    int rc = rescore_run(h->device, h->stream, h->n_nodes, h->genome, h->parent.data(), h->mut_off.data(), h->mut_pos.data(),
+    int rc = ensure_host_reads(h);
+    if (rc) return rc;
+    rc = rescore_run(h->device, h->stream, h->n_nodes, h->genome, h->parent.data(), h->mut_off.data(), h->mut_pos.data(),
                          h->mut_ref.data(), h->mut_nuc.data(), h->n_reads, h->r_start.data(), h->r_end.data(),
                          h->r_off.data(), h->r_pos.data(), h->r_nuc.data(), n_cand, cand_nodes, min_dist, dist, am_off,
                          am_idx, am_capacity, err);
@@ -918,15 +1043,14 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
         CU(cudaGetLastError());
     }
     DevBuf<double> d_cur, d_orig, d_contrib, d_fulls;
-    DevBuf<uint8_t> d_pmapped, d_removed, d_rnuc, d_stnuc;
-    DevBuf<int32_t> d_rstart, d_rend, d_rpos, d_nodes, d_stpos, d_marks;
-    DevBuf<int64_t> d_roff, d_list, d_stoff;
+    DevBuf<uint8_t> d_pmapped, d_removed, d_stnuc;
+    DevBuf<int32_t> d_nodes, d_stpos, d_marks;
+    DevBuf<int64_t> d_list, d_stoff;
     DevBuf<unsigned long long> d_max;
     DevBuf<int> d_count;
     auto release = [&]() {
         d_cur.release(); d_orig.release(); d_contrib.release(); d_fulls.release(); d_pmapped.release();
-        d_removed.release(); d_rnuc.release(); d_stnuc.release(); d_rstart.release(); d_rend.release();
-        d_rpos.release(); d_nodes.release(); d_stpos.release(); d_marks.release(); d_roff.release();
+        d_removed.release(); d_stnuc.release(); d_nodes.release(); d_stpos.release(); d_marks.release();
         d_list.release(); d_stoff.release(); d_max.release(); d_count.release();
     };
 #define FCU(call)                                                                                  \
@@ -946,9 +1070,11 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
     FCU(cudaMemcpyAsync(d_orig.p, h->d_score.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
     FCU(cudaMemsetAsync(d_pmapped.p, 0, (size_t)n, st));
     FCU(cudaMemsetAsync(d_removed.p, 0, (size_t)std::max<int64_t>(R, 1), st));
-    // the reads in caller order for find_correspondents
-    FCU(upload(d_rstart, h->r_start, st)); FCU(upload(d_rend, h->r_end, st)); FCU(upload(d_roff, h->r_off, st));
-    FCU(upload(d_rpos, h->r_pos, st)); FCU(upload(d_rnuc, h->r_nuc, st));
+    // find_correspondents reads the resident reads (caller order); the subset plans below need the host copy
+    if ((rc = ensure_host_reads(h)) != 0) {
+        release();
+        return rc;
+    }
 
     PeakHost ph(h);
     std::vector<uint8_t> mapped((size_t)n, 0);
@@ -1030,8 +1156,8 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
         FCU(upload(d_stoff, so, st)); FCU(upload(d_stpos, sp, st)); FCU(upload(d_stnuc, sn, st));
         FCU(cudaMemsetAsync(d_count.p, 0, sizeof(int), st));
         CorrespondParams cp = {};
-        cp.n_reads = R; cp.start = d_rstart.p; cp.end = d_rend.p; cp.rm_off = d_roff.p; cp.rm_pos = d_rpos.p;
-        cp.rm_nuc = d_rnuc.p; cp.max_pars = h->d_maxpars.p; cp.removed = d_removed.p;
+        cp.n_reads = R; cp.start = h->d_rstart.p; cp.end = h->d_rend.p; cp.rm_off = h->d_roff.p; cp.rm_pos = h->d_rpos.p;
+        cp.rm_nuc = h->d_rnuc.p; cp.max_pars = h->d_maxpars.p; cp.removed = d_removed.p;
         cp.n_cand = (int32_t)consideration.size(); cp.st_off = d_stoff.p; cp.st_pos = d_stpos.p; cp.st_nuc = d_stnuc.p;
         cp.count = d_count.p; cp.list = d_list.p;
         if (R > 0 && !consideration.empty()) correspond_kernel<<<(unsigned)((R + 127) / 128), 128, 0, st>>>(cp);
@@ -1050,7 +1176,7 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
                 release();
                 return fail(WEPP_E_INVALID, err);
             }
-            rc = upload_plan(h, h->sub);
+            rc = upload_plan(h, h->sub, true);
             if (!rc) rc = run_place(h, h->sub, true, 0, 0, /*with_counts*/ false, d_contrib.p);
             if (rc) {
                 release();
