@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-baseline budget per measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-c5", action="store_true", help="skip the candidate re-scoring (C5) measurement")
+    ap.add_argument("--c5-generic", action="store_true", help="also time the generic K4 kernel once (slow)")
     return ap.parse_args()
 
 
@@ -343,6 +345,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "d2h_bytes_per_step": int(r * 8 + n * (8 + 200) + d2h_keys), "ms_per_step": dt * 1e3,
                     "outputs": "as e2e, with mapped_read_counts[N][50] instead of dist_divergence"}
 
+    c5 = None
+    if not args.no_c5:
+        c5 = run_c5(args, p, arena, reads, world, dev, barrier)
+
     if rank != 0:
         return
     peak, peak_src = peaks()
@@ -385,7 +391,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                              "the kernel is co-limited by warp-instruction issue and shared-memory wavefronts "
                              "(see bottleneck and DESIGN.md section 3)",
                      "bottleneck": bottleneck},
-        "clocks": clocks,
+        "clocks": clocks, "c5_rescore": c5,
         "setup_s": {"flatten_tree": t_arena, "pack_reads_and_build_lists": t_reads},
         "stats": {k: st[k] for k in ("n_tiles", "n_lists", "n_buckets", "reads_per_tile", "stripe_width",
                                      "list_entries_total", "scanned_entries", "ms_scan_kernel", "ms_node_kernels")},
@@ -393,6 +399,45 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference(arena, reads, args.cpu_seconds)
     print(json.dumps(out), flush=True)
+
+
+def run_c5(args, p, arena, reads, world, dev, barrier):
+    """BASELINE.json configs[4]: iterative re-scoring of the rank's resident reads against a pool of 5,000
+    candidate haplotypes over 10 iterations with 10 % pool churn (haplotype::mutation_distance + argmin,
+    haplotype.hpp:123-177, arena.cpp:614-625).  One iteration = one wepp_rescore through the C ABI with host
+    buffers: candidate indices in, per-read min distance out (and the argmin counts kept on the device);
+    wall time, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    rng = np.random.default_rng(20260105)
+    n_cand, iters = max(8, int(5000 * min(1.0, args.scale * 4))), 10
+    pool = rng.choice(arena.n_nodes, n_cand, replace=False).astype(np.int32)
+    p.set_reads(reads)
+    p.rescore(pool, want_argmin=False)   # warm-up: buffers, candidate entry lists
+    barrier()
+    times = []
+    for _ in range(iters):
+        churn = rng.choice(n_cand, n_cand // 10, replace=False)
+        pool[churn] = rng.integers(0, arena.n_nodes, churn.size)
+        t0 = time.perf_counter()
+        md, _, _, _ = p.rescore(pool, want_argmin=False)
+        times.append(time.perf_counter() - t0)
+    dt = float(np.sum(times))
+    if world > 1:
+        t = torch.tensor([dt], device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    out = {"workload": f"{reads.n_reads} resident reads per GPU x {n_cand} candidate haplotypes x {iters} iterations, "
+                       f"10% pool churn per iteration", "ms_per_iteration": dt / iters * 1e3,
+           "read_x_candidate_distances_per_s": reads.n_reads * world * n_cand * iters / dt,
+           "checksum_min_dist": int(md.astype(np.int64).sum()),
+           "outputs": "min distance per read to host; argmin counts on the device"}
+    if args.c5_generic:
+        t0 = time.perf_counter()
+        gmd, _, _, _ = p.rescore_reads(reads, pool, want_argmin=False)
+        out["generic_kernel_ms_per_iteration"] = (time.perf_counter() - t0) * 1e3
+        out["generic_agrees"] = bool(np.array_equal(gmd, md))
+    return out
 
 
 def main():

@@ -197,6 +197,60 @@ def test_rescore_matches_oracle():
     p.close()
 
 
+def _rescore_case(name):
+    if name.startswith("tiny"):
+        arena, reads, _ = cases.tiny_case(int(name[4:]))
+    elif name == "star":
+        arena, reads, _ = cases.star_case(1)
+    elif name == "c4":   # ONT shape: 1.1 kb windows, K = 2
+        arena = synth.make_arena(6000, 29903, 5)
+        reads = synth.make_reads(arena, 300, 5, amplicons=synth.amplicon_scheme(29903, 29, 1058, 1201, 5),
+                                 full_amplicon=True, err=0.03, n_rate=0.05, n_templates=40)
+    else:
+        arena, reads = cases.small_case(seed=23)
+    return arena, reads
+
+
+@pytest.mark.parametrize("name,q,k,n_cand", [("tiny0", 8, 8, 5), ("tiny1", 8, 4, 40), ("tiny2", 16, 2, 3), ("tiny3", 4, 0, 1),
+                                             ("tiny4", 32, 8, 64), ("star", 32, 8, 300), ("small", 32, 0, 1000),
+                                             ("small", 16, 4, 9), ("c4", 32, 0, 257)])
+def test_rescore_tile_kernel_matches_oracle(name, q, k, n_cand):
+    """K4 over the resident reads (rescore_tiles.cuh): IUPAC / reversion / N edge cases of the tiny trees,
+    leaves of a polytomy, long reads, candidate sets smaller than the warp count, repeated candidates."""
+    arena, reads = _rescore_case(name)
+    rng = np.random.default_rng(n_cand)
+    cand = rng.integers(0, arena.n_nodes, n_cand).astype(np.int32)   # with repeats
+    p = Placer(0, stripe_width=q, reads_per_lane=k)
+    p.set_arena(arena)
+    p.set_reads(reads)
+    md, dist, off, idx = p.rescore(cand, want_dist=True)
+    omd, odist, ooff, oidx = oracle.rescore(arena, reads, cand)
+    assert np.array_equal(md, omd) and np.array_equal(dist, odist)
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx)
+    md2, _, off2, idx2 = p.rescore(cand[::-1].copy())    # buffers are reused across calls
+    omd2, _, ooff2, oidx2 = oracle.rescore(arena, reads, cand[::-1].copy())
+    assert np.array_equal(md2, omd2) and np.array_equal(off2, ooff2) and np.array_equal(idx2, oidx2)
+    md3, _, _, _ = p.rescore(cand, want_argmin=False)
+    assert np.array_equal(md3, omd)
+    p.close()
+
+
+def test_rescore_tile_and_generic_kernels_agree_at_size():
+    """Beyond what the oracle finishes quickly: 200k nodes, 60k reads, 700 candidates — the tile kernel over the
+    resident reads against the generic one-thread-per-read kernel of wepp_rescore_reads (itself oracle-checked)."""
+    arena, reads, _ = synth.config_shape("C2", scale=0.2)
+    reads = reads.slice(0, 60000)
+    rng = np.random.default_rng(8)
+    cand = rng.choice(arena.n_nodes, 700, replace=False).astype(np.int32)
+    p = Placer(0)
+    p.set_arena(arena)
+    p.set_reads(reads)
+    md, _, off, idx = p.rescore(cand)
+    gmd, _, goff, gidx = p.rescore_reads(reads, cand)
+    assert np.array_equal(md, gmd) and np.array_equal(off, goff) and np.array_equal(idx, gidx)
+    p.close()
+
+
 @pytest.mark.parametrize("seed,n_nodes,n_reads", [(41, 1500, 500), (42, 3000, 900)])
 def test_peak_loop_matches_restated_filter(seed, n_nodes, n_reads):
     """wepp_filter_peaks (GPU-driven peak loop) vs oracle/peaks.py, itself pinned on the reference's object code."""

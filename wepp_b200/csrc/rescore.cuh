@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace wepp {
@@ -68,6 +69,68 @@ __device__ __forceinline__ int mutation_distance_dev(const int32_t* __restrict__
     return muts;
 }
 
+// Candidate stack_muts (arena.cpp:18-46): the last event per position on the root path, kept when
+// mut != ref, sorted by position.  Only candidates need them, not all N nodes as in the reference.
+inline bool build_candidate_stacks(int32_t n_nodes, int32_t genome, const int32_t* parent, const int64_t* mut_off,
+                                   const int32_t* mut_pos, const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t n_cand,
+                                   const int32_t* cand, std::vector<int64_t>& st_off, std::vector<int32_t>& st_pos,
+                                   std::vector<uint8_t>& st_nuc, std::string& err) {
+    st_off.assign((size_t)n_cand + 1, 0);
+    st_pos.clear();
+    st_nuc.clear();
+    for (int32_t c = 0; c < n_cand; ++c)
+        if (cand[c] < 0 || cand[c] >= n_nodes) {
+            err = "candidate node index out of range";
+            return false;
+        }
+    // the root-path walks are latency-bound pointer chasing: spread the candidates over host threads
+    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), 32, n_cand / 64}));
+    std::vector<std::vector<int32_t>> t_pos((size_t)n_thr);
+    std::vector<std::vector<uint8_t>> t_nuc((size_t)n_thr);
+    auto work = [&](int t) {
+        const int32_t c_lo = (int32_t)((int64_t)n_cand * t / n_thr), c_hi = (int32_t)((int64_t)n_cand * (t + 1) / n_thr);
+        std::vector<int32_t> path, touched;
+        std::vector<int64_t> last((size_t)genome + 1, -1);
+        for (int32_t c = c_lo; c < c_hi; ++c) {
+            path.clear();
+            for (int32_t v = cand[c]; v >= 0; v = parent[v]) path.push_back(v);
+            touched.clear();
+            for (auto it = path.rbegin(); it != path.rend(); ++it)
+                for (int64_t k = mut_off[*it]; k < mut_off[*it + 1]; ++k) {
+                    if (last[mut_pos[k]] < 0) touched.push_back(mut_pos[k]);
+                    last[mut_pos[k]] = k;
+                }
+            std::sort(touched.begin(), touched.end());
+            int64_t kept = 0;
+            for (int32_t pos : touched) {
+                const int64_t k = last[pos];
+                if (mut_ref[k] != mut_nuc[k]) {
+                    t_pos[t].push_back(pos);
+                    t_nuc[t].push_back(mut_nuc[k]);
+                    ++kept;
+                }
+                last[pos] = -1;
+            }
+            st_off[(size_t)c + 1] = kept;   // per-candidate count for now
+        }
+    };
+    if (n_thr == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> thr;
+        for (int t = 0; t < n_thr; ++t) thr.emplace_back(work, t);
+        for (auto& th : thr) th.join();
+    }
+    for (int32_t c = 0; c < n_cand; ++c) st_off[(size_t)c + 1] += st_off[(size_t)c];
+    st_pos.reserve((size_t)st_off[(size_t)n_cand]);
+    st_nuc.reserve((size_t)st_off[(size_t)n_cand]);
+    for (int t = 0; t < n_thr; ++t) {
+        st_pos.insert(st_pos.end(), t_pos[t].begin(), t_pos[t].end());
+        st_nuc.insert(st_nuc.end(), t_nuc[t].begin(), t_nuc[t].end());
+    }
+    return true;
+}
+
 template <bool FILL>
 __global__ void rescore_kernel(const RescoreParams p) {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,39 +180,12 @@ inline int rescore_run(int device, cudaStream_t stream, int32_t n_nodes, int32_t
                        int32_t* min_dist, int32_t* dist, int64_t* am_off, int32_t* am_idx, int64_t am_capacity,
                        std::string& err) {
     (void)device;
-    // candidate stack_muts: last event per position on the root path, kept when mut != ref
-    std::vector<int64_t> st_off((size_t)n_cand + 1, 0);
+    std::vector<int64_t> st_off;
     std::vector<int32_t> st_pos;
     std::vector<uint8_t> st_nuc;
-    {
-        std::vector<int32_t> path;
-        std::vector<int64_t> last((size_t)genome + 1, -1);
-        std::vector<int32_t> touched;
-        for (int32_t c = 0; c < n_cand; ++c) {
-            if (cand[c] < 0 || cand[c] >= n_nodes) {
-                err = "candidate node index out of range";
-                return -1;
-            }
-            path.clear();
-            for (int32_t v = cand[c]; v >= 0; v = parent[v]) path.push_back(v);
-            touched.clear();
-            for (auto it = path.rbegin(); it != path.rend(); ++it)
-                for (int64_t k = mut_off[*it]; k < mut_off[*it + 1]; ++k) {
-                    if (last[mut_pos[k]] < 0) touched.push_back(mut_pos[k]);
-                    last[mut_pos[k]] = k;
-                }
-            std::sort(touched.begin(), touched.end());
-            for (int32_t pos : touched) {
-                const int64_t k = last[pos];
-                if (mut_ref[k] != mut_nuc[k]) {
-                    st_pos.push_back(pos);
-                    st_nuc.push_back(mut_nuc[k]);
-                }
-                last[pos] = -1;
-            }
-            st_off[c + 1] = (int64_t)st_pos.size();
-        }
-    }
+    if (!build_candidate_stacks(n_nodes, genome, parent, mut_off, mut_pos, mut_ref, mut_nuc, n_cand, cand, st_off, st_pos,
+                                st_nuc, err))
+        return -1;
     int32_t *d_start = nullptr, *d_end = nullptr, *d_rm_pos = nullptr, *d_st_pos = nullptr, *d_min = nullptr,
             *d_nbest = nullptr, *d_dist = nullptr, *d_am_idx = nullptr;
     int64_t *d_rm_off = nullptr, *d_st_off = nullptr, *d_am_off = nullptr;

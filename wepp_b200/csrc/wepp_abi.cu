@@ -15,6 +15,7 @@
 #include "host_prep.h"
 #include "kernels.cuh"
 #include "rescore.cuh"
+#include "rescore_tiles.cuh"
 #include "peaks.cuh"
 
 using namespace wepp;
@@ -145,6 +146,12 @@ struct wepp_handle {
     bool has_results = false;
     bool has_epp = false;
     int64_t epp_capacity = 0;
+
+    // K4 over the resident reads (rescore_tiles.cuh): candidate stacks, per-window candidate entries, results
+    DevBuf<int64_t> d_st_off, d_ccnt, d_coff, d_am_off;
+    DevBuf<int32_t> d_st_pos, d_rs_min, d_rs_nbest, d_rs_before, d_rs_dist, d_am_idx;
+    DevBuf<uint8_t> d_st_nuc, d_cub_tmp;
+    DevBuf<Entry> d_cent;
 
     wepp_stats stats = {};
 };
@@ -892,6 +899,136 @@ int64_t wepp_host_read_plan(int32_t genome_size, int32_t stripe_width, int32_t r
     return (int64_t)pl.tiles.size();
 }
 
+}  // extern "C"
+
+namespace {
+
+template <int K>
+int launch_rescore_tiles(wepp_handle* h, const RescoreTileParams& p, int n_tiles, int width, int mode) {
+    const size_t smem = (size_t)RtLayout<K>::CODES + (((size_t)width * 32 * K + 15) & ~(size_t)15);
+    if (smem > h->smem_optin || width > MAX_WINDOW)
+        return fail(WEPP_E_INVALID, "read window too wide for shared memory (" + std::to_string(width) + " bases)");
+    if (mode == 0) {
+        CU(cudaFuncSetAttribute(rescore_tile_kernel<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rescore_tile_kernel<K, 0><<<n_tiles, PLACE_WARPS * 32, smem, h->stream>>>(p);
+    } else {
+        CU(cudaFuncSetAttribute(rescore_tile_kernel<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        rescore_tile_kernel<K, 1><<<n_tiles, PLACE_WARPS * 32, smem, h->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return WEPP_OK;
+}
+
+int launch_rescore_tiles_k(wepp_handle* h, const RescoreTileParams& p, int n_tiles, int width, int k, int mode) {
+    if (k == 8) return launch_rescore_tiles<8>(h, p, n_tiles, width, mode);
+    if (k == 4) return launch_rescore_tiles<4>(h, p, n_tiles, width, mode);
+    return launch_rescore_tiles<2>(h, p, n_tiles, width, mode);
+}
+
+// K4 over the resident reads: the candidates' in-window stack mutations become per-list entry runs
+// (count -> scan -> fill), then one tile kernel for min / argmin count and one for the argmin lists.
+int rescore_resident(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, int32_t* min_dist, int32_t* dist,
+                     int64_t* am_off, int32_t* am_idx, int64_t am_capacity) {
+    wepp_handle::DevPlan& dp = h->full;
+    const ReadPlan& pl = dp.plan;
+    const int64_t R = h->n_reads;
+    if (R == 0 || pl.tiles.empty()) {
+        if (am_off) am_off[0] = 0;
+        return WEPP_OK;
+    }
+    std::string err;
+    std::vector<int64_t> st_off;
+    std::vector<int32_t> st_pos;
+    std::vector<uint8_t> st_nuc;
+    if (!build_candidate_stacks(h->n_nodes, h->genome, h->parent.data(), h->mut_off.data(), h->mut_pos.data(),
+                                h->mut_ref.data(), h->mut_nuc.data(), n_cand, cand_nodes, st_off, st_pos, st_nuc, err))
+        return fail(WEPP_E_INVALID, err);
+    const int n_lists = (int)pl.lists.size();
+    const int64_t n_lc = (int64_t)n_lists * n_cand;
+    // capacity of the entry buffer: one entry per (list, candidate) + every stack mutation once per list covering it
+    int64_t cap = n_lc;
+    {
+        std::vector<int32_t> cover((size_t)h->genome + 2, 0);
+        for (const ListDesc& l : pl.lists) {
+            cover[(size_t)std::min(l.b0, h->genome + 1)] += 1;
+            cover[(size_t)std::min(l.b0 + l.width, h->genome + 1)] -= 1;
+        }
+        for (size_t i = 1; i < cover.size(); ++i) cover[i] += cover[i - 1];
+        for (int32_t pos : st_pos) cap += cover[(size_t)pos];
+    }
+    CU(upload(h->d_st_off, st_off, h->stream));
+    CU(upload(h->d_st_pos, st_pos, h->stream));
+    CU(upload(h->d_st_nuc, st_nuc, h->stream));
+    CU(h->d_ccnt.ensure((size_t)n_lc + 1));
+    CU(h->d_coff.ensure((size_t)n_lc + 1));
+    CU(h->d_cent.ensure((size_t)cap));
+    CU(h->d_rs_min.ensure((size_t)R));
+    CU(h->d_rs_nbest.ensure((size_t)R));
+    CU(h->d_rs_before.ensure((size_t)R * PLACE_WARPS));
+    if (dist) CU(h->d_rs_dist.ensure((size_t)R * (size_t)n_cand));
+    const unsigned blocks = (unsigned)((n_lc + 1 + 255) / 256);
+    cand_count_kernel<<<blocks, 256, 0, h->stream>>>(dp.lists.p, n_lists, n_cand, h->d_st_off.p, h->d_st_pos.p, h->d_ccnt.p);
+    CU(cudaGetLastError());
+    size_t tmp_bytes = 0;
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_ccnt.p, h->d_coff.p, (int)(n_lc + 1), h->stream));
+    CU(h->d_cub_tmp.ensure(tmp_bytes));
+    CU(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp_bytes, h->d_ccnt.p, h->d_coff.p, (int)(n_lc + 1), h->stream));
+    cand_fill_kernel<<<blocks, 256, 0, h->stream>>>(dp.lists.p, n_lists, n_cand, h->d_st_off.p, h->d_st_pos.p, h->d_st_nuc.p,
+                                                    h->d_coff.p, h->d_cent.p);
+    CU(cudaGetLastError());
+
+    RescoreTileParams p = {};
+    p.cent = h->d_cent.p;
+    p.coff = h->d_coff.p;
+    p.n_cand = n_cand;
+    p.list_desc = dp.lists.p;
+    p.buckets = dp.buckets.p;
+    p.tiles = dp.tiles.p;
+    p.start = h->d_rstart.p;
+    p.end = h->d_rend.p;
+    p.rm_off = h->d_roff.p;
+    p.rm_pos = h->d_rpos.p;
+    p.rm_code = h->d_rcode.p;
+    p.perm = dp.perm.p;
+    p.min_dist = h->d_rs_min.p;
+    p.n_argmin = h->d_rs_nbest.p;
+    p.before = h->d_rs_before.p;
+    p.dist = dist ? h->d_rs_dist.p : nullptr;
+    const int n_tiles = (int)pl.tiles.size(), k = pl.reads_per_tile / 32;
+    int rc = launch_rescore_tiles_k(h, p, n_tiles, pl.max_width, k, 0);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(min_dist, h->d_rs_min.p, (size_t)R * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (dist) CU(cudaMemcpyAsync(dist, h->d_rs_dist.p, (size_t)R * (size_t)n_cand * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (am_off) {
+        std::vector<int32_t> nbest((size_t)R);
+        CU(cudaMemcpyAsync(nbest.data(), h->d_rs_nbest.p, (size_t)R * 4, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        int64_t tot = 0;
+        for (int64_t r = 0; r < R; ++r) {
+            am_off[r] = tot;
+            tot += nbest[(size_t)r];
+        }
+        am_off[R] = tot;
+        if (am_idx) {
+            if (tot > am_capacity) return fail(WEPP_E_CAPACITY, "am_idx capacity too small");
+            CU(h->d_am_off.ensure((size_t)R + 1));
+            CU(h->d_am_idx.ensure((size_t)std::max<int64_t>(tot, 1)));
+            CU(cudaMemcpyAsync(h->d_am_off.p, am_off, ((size_t)R + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+            p.am_off = h->d_am_off.p;
+            p.am_idx = h->d_am_idx.p;
+            rc = launch_rescore_tiles_k(h, p, n_tiles, pl.max_width, k, 1);
+            if (rc) return rc;
+            CU(cudaMemcpyAsync(am_idx, h->d_am_idx.p, (size_t)tot * 4, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    return WEPP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int wepp_rescore(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, int32_t* min_dist, int32_t* dist,
                  int64_t* am_off, int32_t* am_idx, int64_t am_capacity) {
     if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
@@ -899,6 +1036,10 @@ int wepp_rescore(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, int3
     if (n_cand < 1 || !cand_nodes || !min_dist) return fail(WEPP_E_INVALID, "bad candidate set / min_dist is NULL");
     CU(cudaSetDevice(h->device));
     std::string err;
+    // the tile kernel over the resident reads; WEPP_RESCORE_GENERIC=1 selects the generic one-thread-per-read
+    // kernel of wepp_rescore_reads instead (development: A/B timing)
+    static const bool generic = getenv("WEPP_RESCORE_GENERIC") && atoi(getenv("WEPP_RESCORE_GENERIC")) != 0;
+    if (!generic) return rescore_resident(h, n_cand, cand_nodes, min_dist, dist, am_off, am_idx, am_capacity);
     int rc = ensure_host_reads(h);
     if (rc) return rc;
     rc = rescore_run(h->device, h->stream, h->n_nodes, h->genome, h->parent.data(), h->mut_off.data(), h->mut_pos.data(),

@@ -148,6 +148,23 @@ class Placer:
             idx = idx[: int(off[-1])]
         return md, dist, off, idx
 
+    def rescore_reads(self, reads, cand_nodes, want_dist: bool = False, want_argmin: bool = True):
+        """wepp_rescore_reads: the same over reads handed in directly (generic one-thread-per-read kernel)."""
+        cand = _c(cand_nodes, np.int32)
+        r = (_c(reads.start, np.int32), _c(reads.end, np.int32), _c(reads.rm_off, np.int64), _c(reads.rm_pos, np.int32),
+             _c(reads.rm_nuc, np.uint8))
+        n = r[0].shape[0]
+        md = np.empty(n, np.int32)
+        dist = np.empty((n, cand.shape[0]), np.int32) if want_dist else None
+        off = np.empty(n + 1, np.int64) if want_argmin else None
+        cap = n * cand.shape[0] if want_argmin else 0
+        idx = np.empty(max(cap, 1), np.int32) if want_argmin else None
+        check(self.lib.wepp_rescore_reads(self.h, n, *[ptr(x) for x in r], cand.shape[0], ptr(cand), ptr(md), ptr(dist),
+                                          ptr(off), ptr(idx), cap))
+        if want_argmin:
+            idx = idx[: int(off[-1])]
+        return md, dist, off, idx
+
     def device_buffer(self, which: int):
         p = C.c_void_p()
         n = C.c_int64()
