@@ -224,7 +224,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     dev = local_rank
     arena, reads = workload(args.scale, rank)
     k_env = int(os.environ.get("WEPP_READS_PER_LANE", "0"))   # development knob
-    q_env = int(os.environ.get("WEPP_STRIPE_WIDTH", "32"))
+    q_env = int(os.environ.get("WEPP_STRIPE_WIDTH", "16"))
     p = Placer(dev, stripe_width=q_env, reads_per_lane=k_env)
     stream = torch.cuda.current_stream()
     p.set_stream(stream.cuda_stream)

@@ -67,7 +67,7 @@ int wepp_set_stream(wepp_handle* h, void* cuda_stream);
 int wepp_sync(wepp_handle* h);
 
 /* Tunables (optional, before wepp_set_arena): stripe width in bases used to bucket read
- * windows (default 32) and reads per warp lane K in {2,4,8} (0 = choose per bucket). */
+ * windows (default 16) and reads per warp lane K in {2,4,8} (0 = choose per bucket). */
 int wepp_set_options(wepp_handle* h, int32_t stripe_width, int32_t reads_per_lane);
 
 /* The flattened tree.  Node v is the v-th haplotype in preorder (arena index):

@@ -115,6 +115,26 @@ def test_device_and_host_keying_agree_and_validate_reads():
         p.close()
 
 
+def test_list_build_rank_table_and_binary_search_agree(monkeypatch):
+    """The per-window Euler lists are built from the per-tree rank table when it fits, else by one binary
+    search per stripe: both builds must place identically (and the table must survive a wider second read set)."""
+    arena, reads = cases.small_case(seed=29)
+    _check(arena, reads, None, 8, 0)
+    monkeypatch.setenv("WEPP_NO_RANK_TABLE", "1")
+    _check(arena, reads, None, 8, 0)
+    monkeypatch.delenv("WEPP_NO_RANK_TABLE")
+    p = Placer(0, stripe_width=8)
+    p.set_arena(arena)
+    short = reads.take(np.flatnonzero(reads.end - reads.start < np.median(reads.end - reads.start)))
+    for r in (short, reads, short):      # the table is rebuilt when a read set spans more stripes
+        p.set_reads(r)
+        p.place(0, 0)
+        mp, mu = p.read_results()
+        o = oracle.cartesian_map(arena, r, None, n_threads=4)
+        assert np.array_equal(mp, o["max_parsimony"]) and np.array_equal(mu, o["multiplicity"])
+    p.close()
+
+
 def test_everything_mapped_gives_zero_multiplicity():
     arena, reads = cases.small_case(seed=5, n_reads=100)
     mapped = np.ones(arena.n_nodes, np.uint8)

@@ -209,6 +209,74 @@ __global__ void build_lists_kernel(const Entry* __restrict__ stripes, const int6
     }
 }
 
+// Stripe-neighbourhood rank table (built once per tree, on the first wepp_set_reads that can use it):
+// for every stripe entry e of stripe s and d = 1..D,
+//   tab[(d - 1) * E + e]       = entries of stripes s-d .. s-1 with key <= key(e)
+//   tab[(D + d - 1) * E + e]   = entries of stripes s+1 .. s+d with key <  key(e)
+// so that an entry's rank in ANY list [qs, qe] with qe - qs <= D is its rank in its own stripe plus two
+// table look-ups (build_lists_ranked_kernel) instead of one binary search per other stripe.
+__global__ void rank_table_kernel(const Entry* __restrict__ stripes, const int64_t* __restrict__ stripe_off,
+                                  int n_stripes, int q, int D, int64_t E, int32_t* __restrict__ tab) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < E; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint4 e = ld_entry(stripes + i);
+        const int s = (int)(e.y / (uint32_t)q);
+        int32_t acc = 0;
+        for (int d = 1; d <= D; ++d) {
+            const int t = s - d;
+            if (t >= 0) {
+                int64_t lo = stripe_off[t], hi = stripe_off[t + 1];
+                const int64_t base = lo;
+                const uint32_t key = e.x + 1u;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (__ldg(&stripes[mid].x) < key) lo = mid + 1; else hi = mid;
+                }
+                acc += (int32_t)(lo - base);
+            }
+            tab[(int64_t)(d - 1) * E + i] = acc;
+        }
+        acc = 0;
+        for (int d = 1; d <= D; ++d) {
+            const int t = s + d;
+            if (t < n_stripes) {
+                int64_t lo = stripe_off[t], hi = stripe_off[t + 1];
+                const int64_t base = lo;
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (__ldg(&stripes[mid].x) < e.x) lo = mid + 1; else hi = mid;
+                }
+                acc += (int32_t)(lo - base);
+            }
+            tab[(int64_t)(D + d - 1) * E + i] = acc;
+        }
+    }
+}
+
+// build_lists_kernel with the ranks read from the table (same output, bit for bit).
+__global__ void build_lists_ranked_kernel(const Entry* __restrict__ stripes, const int64_t* __restrict__ stripe_off,
+                                          const ListDesc* __restrict__ list_desc, Entry* __restrict__ out, int q,
+                                          const int32_t* __restrict__ tab, int D, int64_t E) {
+    const ListDesc ld = list_desc[blockIdx.y];
+    const int64_t src0 = stripe_off[ld.qs];
+    const int n_src = ld.n - 1;
+    Entry* dst = out + ld.off;
+    if (blockIdx.x == 0 && threadIdx.x == 0) dst[0] = Entry{0u, 0u, 0u, 0u};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_src; i += gridDim.x * blockDim.x) {
+        const int64_t gi = src0 + i;
+        const uint4 e = ld_entry(stripes + gi);
+        const int s = (int)(e.y / (uint32_t)q);
+        int64_t rank = 1 + (gi - stripe_off[s]);
+        if (s > ld.qs) rank += __ldg(&tab[(int64_t)(s - ld.qs - 1) * E + gi]);
+        if (ld.qe > s) rank += __ldg(&tab[(int64_t)(D + ld.qe - s - 1) * E + gi]);
+        Entry o;
+        o.x = (e.x >> 1) | ((e.x & 1u) ? ENT_POINT : 0u);
+        o.y = 0;
+        o.z = e.z;
+        o.w = (e.w & 0xFFu) | ((e.y - (uint32_t)ld.b0) << 16);
+        dst[rank] = o;
+    }
+}
+
 // Entry kinds, countable-node counts, enclosing boundary entries and scan chunks.
 // grid = (chunks, n_lists).  Threads only ever change the ENT_EVAL / ENT_SKIP bits of x, and
 // neighbours read x through KEY_MASK, so the kernel can be re-run in place when `mapped` changes.

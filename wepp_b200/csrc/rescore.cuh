@@ -83,35 +83,65 @@ inline bool build_candidate_stacks(int32_t n_nodes, int32_t genome, const int32_
             err = "candidate node index out of range";
             return false;
         }
-    // the root-path walks are latency-bound pointer chasing: spread the candidates over host threads
-    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), 32, n_cand / 64}));
+    // The root-path walks are latency-bound pointer chasing (every step misses the cache on an 8M-node tree):
+    // spread the candidates over host threads, and inside a thread walk LANES paths in lockstep so that
+    // their independent misses overlap; the event arrays of the nodes ahead are prefetched.
+    const int n_thr = (int)std::max<int64_t>(1, std::min<int64_t>({(int64_t)std::thread::hardware_concurrency(), 32, n_cand / 16}));
     std::vector<std::vector<int32_t>> t_pos((size_t)n_thr);
     std::vector<std::vector<uint8_t>> t_nuc((size_t)n_thr);
     auto work = [&](int t) {
+        constexpr int LANES = 16, AHEAD = 6;
         const int32_t c_lo = (int32_t)((int64_t)n_cand * t / n_thr), c_hi = (int32_t)((int64_t)n_cand * (t + 1) / n_thr);
-        std::vector<int32_t> path, touched;
+        std::vector<int32_t> path[LANES], touched;
         std::vector<int64_t> last((size_t)genome + 1, -1);
-        for (int32_t c = c_lo; c < c_hi; ++c) {
-            path.clear();
-            for (int32_t v = cand[c]; v >= 0; v = parent[v]) path.push_back(v);
-            touched.clear();
-            for (auto it = path.rbegin(); it != path.rend(); ++it)
-                for (int64_t k = mut_off[*it]; k < mut_off[*it + 1]; ++k) {
-                    if (last[mut_pos[k]] < 0) touched.push_back(mut_pos[k]);
-                    last[mut_pos[k]] = k;
-                }
-            std::sort(touched.begin(), touched.end());
-            int64_t kept = 0;
-            for (int32_t pos : touched) {
-                const int64_t k = last[pos];
-                if (mut_ref[k] != mut_nuc[k]) {
-                    t_pos[t].push_back(pos);
-                    t_nuc[t].push_back(mut_nuc[k]);
-                    ++kept;
-                }
-                last[pos] = -1;
+        for (int32_t cb = c_lo; cb < c_hi; cb += LANES) {
+            const int nb = std::min<int32_t>(LANES, c_hi - cb);
+            int32_t cur[LANES];
+            for (int b = 0; b < nb; ++b) {
+                path[b].clear();
+                cur[b] = cand[cb + b];
             }
-            st_off[(size_t)c + 1] = kept;   // per-candidate count for now
+            for (bool any = true; any;) {
+                any = false;
+                for (int b = 0; b < nb; ++b) {
+                    const int32_t v = cur[b];
+                    if (v < 0) continue;
+                    __builtin_prefetch(&mut_off[v]);
+                    path[b].push_back(v);
+                    cur[b] = parent[v];
+                    any = true;
+                }
+            }
+            for (int b = 0; b < nb; ++b) {
+                const std::vector<int32_t>& pth = path[b];
+                const int np = (int)pth.size();
+                touched.clear();
+                for (int i = np - 1; i >= 0; --i) {   // root first: the deepest event at a position wins
+                    if (i - AHEAD >= 0) {
+                        const int64_t ka = mut_off[pth[(size_t)(i - AHEAD)]];
+                        __builtin_prefetch(&mut_pos[ka]);
+                        __builtin_prefetch(&mut_ref[ka]);
+                        __builtin_prefetch(&mut_nuc[ka]);
+                    }
+                    const int32_t v = pth[(size_t)i];
+                    for (int64_t k = mut_off[v]; k < mut_off[v + 1]; ++k) {
+                        if (last[mut_pos[k]] < 0) touched.push_back(mut_pos[k]);
+                        last[mut_pos[k]] = k;
+                    }
+                }
+                std::sort(touched.begin(), touched.end());
+                int64_t kept = 0;
+                for (int32_t pos : touched) {
+                    const int64_t k = last[pos];
+                    if (mut_ref[k] != mut_nuc[k]) {
+                        t_pos[t].push_back(pos);
+                        t_nuc[t].push_back(mut_nuc[k]);
+                        ++kept;
+                    }
+                    last[pos] = -1;
+                }
+                st_off[(size_t)(cb + b) + 1] = kept;   // per-candidate count for now
+            }
         }
     };
     if (n_thr == 1) {

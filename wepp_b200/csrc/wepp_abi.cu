@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cmath>
 #include <cstring>
@@ -74,7 +75,7 @@ struct wepp_handle {
     bool own_stream = true;
     bool stats_pending = false;
     cudaEvent_t ev[6] = {};
-    int32_t opt_q = 32, opt_k = 0;
+    int32_t opt_q = 16, opt_k = 0;
 
     // arena
     bool has_arena = false;
@@ -86,6 +87,8 @@ struct wepp_handle {
     EulerStripes es;
     DevBuf<Entry> d_stripes;
     DevBuf<int64_t> d_stripe_off;
+    DevBuf<int32_t> d_rank_tab;   // stripe-neighbourhood rank table (rank_table_kernel), built on first use
+    int32_t rank_tab_d = 0;       // neighbour stripes per side it covers (0 = not built)
 
     // mask
     bool has_mask = false;
@@ -152,6 +155,10 @@ struct wepp_handle {
     DevBuf<int32_t> d_st_pos, d_rs_min, d_rs_nbest, d_rs_before, d_rs_dist, d_am_idx;
     DevBuf<uint8_t> d_st_nuc, d_cub_tmp;
     DevBuf<Entry> d_cent;
+    // candidate stack_muts by node, kept across calls (the iterative loops re-score mostly the same candidates)
+    std::unordered_map<int32_t, std::pair<int64_t, int32_t>> st_cache;
+    std::vector<int32_t> st_cache_pos;
+    std::vector<uint8_t> st_cache_nuc;
 
     wepp_stats stats = {};
 };
@@ -181,8 +188,27 @@ int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp, bool host_perm) {
         int max_n = 0;
         for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
         dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.lists.size());
-        build_lists_kernel<<<grid, 256, 0, h->stream>>>(h->d_stripes.p, h->d_stripe_off.p, dp.lists.p, dp.entries.p,
-                                                        h->es.stripe_width);
+        // Entry ranks from the per-tree rank table when it fits (<= 16 GiB), else one binary search per stripe.
+        int span = 0;
+        for (const ListDesc& l : pl.lists) span = std::max(span, l.qe - l.qs);
+        const int64_t E = (int64_t)h->es.entries.size();
+        const char* no_tab = getenv("WEPP_NO_RANK_TABLE");
+        const bool use_tab = span >= 1 && E > 0 && !(no_tab && atoi(no_tab) != 0) &&
+                             (double)E * 2.0 * span * sizeof(int32_t) <= 16.0 * 1024 * 1024 * 1024;
+        if (use_tab && h->rank_tab_d < span) {
+            h->rank_tab_d = 0;
+            CU(h->d_rank_tab.ensure((size_t)E * 2 * (size_t)span));
+            rank_table_kernel<<<(unsigned)std::min<int64_t>((E + 255) / 256, 1 << 20), 256, 0, h->stream>>>(
+                h->d_stripes.p, h->d_stripe_off.p, h->es.n_stripes, h->es.stripe_width, span, E, h->d_rank_tab.p);
+            CU(cudaGetLastError());
+            h->rank_tab_d = span;
+        }
+        if (use_tab)
+            build_lists_ranked_kernel<<<grid, 256, 0, h->stream>>>(h->d_stripes.p, h->d_stripe_off.p, dp.lists.p, dp.entries.p,
+                                                                   h->es.stripe_width, h->d_rank_tab.p, h->rank_tab_d, E);
+        else
+            build_lists_kernel<<<grid, 256, 0, h->stream>>>(h->d_stripes.p, h->d_stripe_off.p, dp.lists.p, dp.entries.p,
+                                                            h->es.stripe_width);
         CU(cudaGetLastError());
     }
     dp.final_for_mask = false;
@@ -476,6 +502,10 @@ int wepp_set_arena(wepp_handle* h, int32_t n_nodes, const int32_t* parent, const
     h->has_reads = false;
     h->has_mask = false;
     h->has_results = false;
+    h->rank_tab_d = 0;
+    h->st_cache.clear();
+    h->st_cache_pos.clear();
+    h->st_cache_nuc.clear();
     return WEPP_OK;
 }
 
@@ -937,12 +967,57 @@ int rescore_resident(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, 
         return WEPP_OK;
     }
     std::string err;
-    std::vector<int64_t> st_off;
+    static const bool timing = getenv("WEPP_RESCORE_TIMING") && atoi(getenv("WEPP_RESCORE_TIMING")) != 0;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {   // development aid: phase times on stderr (serialises the stream)
+        if (!timing) return;
+        cudaStreamSynchronize(h->stream);
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[wepp_rescore] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
+    std::vector<int64_t> st_off((size_t)n_cand + 1, 0);
     std::vector<int32_t> st_pos;
     std::vector<uint8_t> st_nuc;
-    if (!build_candidate_stacks(h->n_nodes, h->genome, h->parent.data(), h->mut_off.data(), h->mut_pos.data(),
-                                h->mut_ref.data(), h->mut_nuc.data(), n_cand, cand_nodes, st_off, st_pos, st_nuc, err))
-        return fail(WEPP_E_INVALID, err);
+    {
+        if (h->st_cache_pos.size() > ((size_t)64 << 20)) {   // bound the cache
+            h->st_cache.clear();
+            h->st_cache_pos.clear();
+            h->st_cache_nuc.clear();
+        }
+        std::vector<int32_t> missing;
+        for (int32_t c = 0; c < n_cand; ++c) {
+            if (cand_nodes[c] < 0 || cand_nodes[c] >= h->n_nodes) return fail(WEPP_E_INVALID, "candidate node index out of range");
+            if (h->st_cache.emplace(cand_nodes[c], std::make_pair((int64_t)-1, 0)).second) missing.push_back(cand_nodes[c]);
+        }
+        if (!missing.empty()) {
+            std::vector<int64_t> m_off;
+            std::vector<int32_t> m_pos;
+            std::vector<uint8_t> m_nuc;
+            if (!build_candidate_stacks(h->n_nodes, h->genome, h->parent.data(), h->mut_off.data(), h->mut_pos.data(),
+                                        h->mut_ref.data(), h->mut_nuc.data(), (int32_t)missing.size(), missing.data(), m_off,
+                                        m_pos, m_nuc, err))
+                return fail(WEPP_E_INVALID, err);
+            const int64_t base = (int64_t)h->st_cache_pos.size();
+            h->st_cache_pos.insert(h->st_cache_pos.end(), m_pos.begin(), m_pos.end());
+            h->st_cache_nuc.insert(h->st_cache_nuc.end(), m_nuc.begin(), m_nuc.end());
+            for (size_t i = 0; i < missing.size(); ++i)
+                h->st_cache[missing[i]] = std::make_pair(base + m_off[i], (int32_t)(m_off[i + 1] - m_off[i]));
+        }
+        std::vector<std::pair<int64_t, int32_t>> where((size_t)n_cand);
+        for (int32_t c = 0; c < n_cand; ++c) {
+            where[(size_t)c] = h->st_cache[cand_nodes[c]];
+            st_off[(size_t)c + 1] = st_off[(size_t)c] + where[(size_t)c].second;
+        }
+        st_pos.resize((size_t)st_off[(size_t)n_cand]);
+        st_nuc.resize((size_t)st_off[(size_t)n_cand]);
+        for (int32_t c = 0; c < n_cand; ++c) {
+            const auto& w = where[(size_t)c];
+            std::copy_n(h->st_cache_pos.begin() + w.first, w.second, st_pos.begin() + st_off[(size_t)c]);
+            std::copy_n(h->st_cache_nuc.begin() + w.first, w.second, st_nuc.begin() + st_off[(size_t)c]);
+        }
+    }
+    lap("candidate stacks (host)");
     const int n_lists = (int)pl.lists.size();
     const int64_t n_lc = (int64_t)n_lists * n_cand;
     // capacity of the entry buffer: one entry per (list, candidate) + every stack mutation once per list covering it
@@ -976,6 +1051,7 @@ int rescore_resident(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, 
     cand_fill_kernel<<<blocks, 256, 0, h->stream>>>(dp.lists.p, n_lists, n_cand, h->d_st_off.p, h->d_st_pos.p, h->d_st_nuc.p,
                                                     h->d_coff.p, h->d_cent.p);
     CU(cudaGetLastError());
+    lap("upload + entry lists");
 
     RescoreTileParams p = {};
     p.cent = h->d_cent.p;
@@ -997,6 +1073,7 @@ int rescore_resident(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, 
     const int n_tiles = (int)pl.tiles.size(), k = pl.reads_per_tile / 32;
     int rc = launch_rescore_tiles_k(h, p, n_tiles, pl.max_width, k, 0);
     if (rc) return rc;
+    lap("tile kernel (min / count)");
     CU(cudaMemcpyAsync(min_dist, h->d_rs_min.p, (size_t)R * 4, cudaMemcpyDeviceToHost, h->stream));
     if (dist) CU(cudaMemcpyAsync(dist, h->d_rs_dist.p, (size_t)R * (size_t)n_cand * 4, cudaMemcpyDeviceToHost, h->stream));
     if (am_off) {
@@ -1022,6 +1099,7 @@ int rescore_resident(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, 
         }
     }
     CU(cudaStreamSynchronize(h->stream));
+    lap("results out (+ argmin lists)");
     return WEPP_OK;
 }
 

@@ -35,7 +35,7 @@ class Placer:
         self.n_nodes = 0
         self.n_reads = 0
         if stripe_width is not None or reads_per_lane is not None:
-            check(self.lib.wepp_set_options(self.h, int(stripe_width or 32), int(reads_per_lane or 0)))
+            check(self.lib.wepp_set_options(self.h, int(stripe_width or 16), int(reads_per_lane or 0)))
 
     def close(self):
         if getattr(self, "h", None):
