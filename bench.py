@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="CPU-baseline budget per measurement")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: per-node exchange step — fused peer-memory merge kernel (default) or NCCL all-reduce")
     ap.add_argument("--no-c5", action="store_true", help="skip the candidate re-scoring (C5) measurement")
     ap.add_argument("--c5-generic", action="store_true", help="also time the generic K4 kernel once (slow)")
     return ap.parse_args()
@@ -242,9 +244,23 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         cp, cb = p.device_buffer(2)
         multigpu.allreduce_node_arrays(cuda_view(sp, sb // 8, "<f8", dev), cuda_view(cp, cb // 4, "<i4", dev))
 
+    # N>1 exchange step: the peer-memory merge kernel (sums the ranks' per-node arrays over NVLink and evaluates
+    # dist_divergence in the same pass) or, with --exchange nccl, the all-reduce of score[N] and counts[N][50]
+    peer = None
+    if world > 1 and args.exchange == "peer":
+        peer = multigpu.PeerMerge(p, rank, world, dev)
+
+    def exchange(full_counts: bool = False):
+        if world == 1:
+            return
+        if peer is not None and not full_counts:
+            peer.merge()
+        else:
+            allreduce_nodes()
+
     def step():
         p.place(0, 0, sync=False)
-        allreduce_nodes()
+        exchange()
 
     def barrier():
         if world > 1:
@@ -272,6 +288,22 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         p.place(0, 0, sync=True)
         scan_ms.append(p.stats()["ms_scan_kernel"])
     st = p.stats()
+    # the exchange step alone: ranks aligned by a barrier first, CUDA events around it on the launching stream
+    exch_ms = None
+    if world > 1:
+        xs = []
+        for _ in range(3):
+            p.place(0, 0, sync=False)
+            barrier()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record()
+            exchange()
+            x1.record()
+            torch.cuda.synchronize()
+            xs.append(x0.elapsed_time(x1))
+        t = torch.tensor([float(np.median(xs))], device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exch_ms = float(t.item())
     if world > 1:
         t = torch.tensor([ms], device=f"cuda:{dev}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -307,7 +339,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             p.set_reads(reads_h)        # H2D of the raw reads, device keying/bucketing, per-window Euler list build
             p.set_mapped(None)
             p.place(0, 0, sync=False)
-            allreduce_nodes()
+            exchange(full_counts=full)
             check(p.lib.wepp_get_read_results(p.h, ptr(mp), ptr(mu)))
             if rank == 0 or world == 1:
                 if full:
@@ -392,6 +424,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                              "(see bottleneck and DESIGN.md section 3)",
                      "bottleneck": bottleneck},
         "clocks": clocks, "c5_rescore": c5,
+        "exchange": None if world == 1 else ("peer-memory merge kernel (wepp_peer_merge)" if peer is not None
+                                             else "NCCL all-reduce of score[N] + counts[N][50]"),
+        "exchange_ms": exch_ms,
         "setup_s": {"flatten_tree": t_arena, "pack_reads_and_build_lists": t_reads},
         "stats": {k: st[k] for k in ("n_tiles", "n_lists", "n_buckets", "reads_per_tile", "stripe_width",
                                      "list_entries_total", "scanned_entries", "ms_scan_kernel", "ms_node_kernels")},
@@ -451,6 +486,8 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":   # keeps NCCL's banner off stdout: one JSON line only
+            del os.environ["NCCL_DEBUG"]
         dist.init_process_group("nccl", device_id=None)
     try:
         run_ours(args, rank, world, local_rank)

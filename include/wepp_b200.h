@@ -135,6 +135,26 @@ int wepp_rescore_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, co
                        const int32_t* rm_pos, const uint8_t* rm_nuc, int32_t n_cand, const int32_t* cand_nodes,
                        int32_t* min_dist, int32_t* dist, int64_t* am_off, int32_t* am_idx, int64_t am_capacity);
 
+/* Multi-GPU exchange step (one process per GPU, reads sharded, tree replicated): the GPU form of the
+ * reference's chunk merge of the per-thread node arrays (src/WEPP/initial_filter.cpp:199-211) fused with the
+ * dist_divergence evaluation that follows it (:214-231), over NVLink peer memory instead of a collective.
+ *   wepp_peer_export  after wepp_set_reads: this rank's blob (CUDA IPC handles of its per-node arrays + its
+ *                     degree-weighted reads per count bin, arena::read_counts, src/WEPP/arena.cpp:138-151)
+ *   wepp_peer_open    all ranks' blobs, in rank order (the caller moves them: torch.distributed / MPI / files)
+ *   wepp_peer_merge   enqueued after wepp_place on the handle's stream.  Each rank sums, for its slice of the
+ *                     nodes, the counts and scores of all ranks straight from their HBM, evaluates
+ *                     dist_divergence and stores the merged score / dist_divergence of the slice into every
+ *                     rank; wepp_get_node_summary then returns the merged arrays.  The caller brackets it with
+ *                     stream-ordered barriers across the ranks (all placements done before; all merges done
+ *                     before the next wepp_place).  The merged mapped_read_counts stay distributed (each rank
+ *                     holds its slice); use an all-reduce of WEPP_BUF_COUNTS if every rank needs all of them.
+ * At most 8 ranks (one NVSwitch domain).  Re-export after wepp_set_arena or when the read set changes. */
+#define WEPP_PEER_BLOB_BYTES 664
+int wepp_peer_export(wepp_handle* h, void* blob);
+int wepp_peer_open(wepp_handle* h, int32_t rank, int32_t world, const void* blobs);
+int wepp_peer_merge(wepp_handle* h);
+int wepp_peer_close(wepp_handle* h);
+
 /* The whole initial filter: wepp_filter::filter (src/WEPP/initial_filter.cpp:455-506) — cartesian_map over
  * the current reads with nothing mapped, then the greedy peak loop (step / clear_neighbors / singular_step /
  * find_correspondents / remove_read, :241-453: pick the top full_score = score * sqrt(dist_divergence) nodes

@@ -52,6 +52,10 @@ SIGNATURES = {
     "wepp_filter_peaks": (C.c_int, [VP, VP, VP, VP, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "wepp_rescore": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, C.c_int64]),
     "wepp_rescore_reads": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, C.c_int32, VP, VP, VP, VP, VP, C.c_int64]),
+    "wepp_peer_export": (C.c_int, [VP, VP]),
+    "wepp_peer_open": (C.c_int, [VP, C.c_int32, C.c_int32, VP]),
+    "wepp_peer_merge": (C.c_int, [VP]),
+    "wepp_peer_close": (C.c_int, [VP]),
     "wepp_cli_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "wepp_device_buffer": (C.c_int, [VP, C.c_int32, C.POINTER(VP), C.POINTER(C.c_int64)]),
     "wepp_get_stats": (C.c_int, [VP, C.POINTER(WeppStats)]),

@@ -1231,4 +1231,103 @@ __global__ void divergence_kernel(const int32_t* __restrict__ counts, int n, Bin
     out[v] = (double)divergence / (double)bins_active;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Multi-GPU exchange step fused with the dist_divergence evaluation, over NVLink peer memory
+// (the GPU form of the reference's chunk merge, initial_filter.cpp:199-211, followed by :214-231).
+// Every rank owns a slice of the nodes.  For its slice it loads the per-node read counts and
+// scores of ALL ranks straight from their HBM (peer pointers opened with CUDA IPC), sums them,
+// keeps the merged counts in its own counts slice, evaluates dist_divergence from the merged rows
+// while they are in shared memory, and stores the merged score and dist_divergence of the slice
+// into every rank's output arrays.  Per rank: (W-1)/W x N x 208 B in over NVLink, N/W x 16 B x W out
+// — against 2 x (W-1)/W x N x 208 B each way for a ring all-reduce of the same arrays — and the
+// counts matrix never makes the second (all-gather) trip, because nothing reads it after the
+// divergence is known.  Ranks synchronise around the kernel with a stream-ordered barrier
+// (the caller's tiny NCCL all-reduce): peers' scans done before, peers' loads done after.
+constexpr int MAX_PEERS = 8;
+constexpr int PM_NODES = 64;      // nodes per block iteration (slice starts are multiples of it: 16-byte aligned rows)
+constexpr int PM_THREADS = 256;
+
+struct PeerMergeParams {
+    int32_t world, lo, hi;                   // this rank's node slice [lo, hi)
+    const int32_t* counts_in[MAX_PEERS];     // every rank's scanned counts[N][50]
+    const double* score_in[MAX_PEERS];       // every rank's score[N]
+    double* score_out[MAX_PEERS];            // every rank's merged score[N]
+    double* div_out[MAX_PEERS];              // every rank's dist_divergence[N]
+    int32_t* counts_own;                     // this rank's counts: the slice is overwritten with the merged rows
+    BinCounts true_counts;                   // degree-weighted reads per bin over ALL ranks (arena.cpp:138-151)
+    int32_t bins_active;
+    double threshold;
+};
+
+__global__ void __launch_bounds__(PM_THREADS) peer_merge_kernel(const PeerMergeParams p) {
+    __shared__ __align__(16) int32_t rows[PM_NODES * NBINS];
+    for (int64_t v0 = (int64_t)p.lo + (int64_t)blockIdx.x * PM_NODES; v0 < p.hi; v0 += (int64_t)gridDim.x * PM_NODES) {
+        const int nv = (int)min((int64_t)PM_NODES, (int64_t)p.hi - v0);
+        const int64_t base = v0 * NBINS;
+        if (nv == PM_NODES) {   // 128-bit loads over NVLink, all ranks' loads of one chunk in flight together
+            constexpr int N4 = PM_NODES * NBINS / 4;                 // 800 16-byte words per rank
+            constexpr int U = (N4 + PM_THREADS - 1) / PM_THREADS;    // 4 per thread: all issued before the first use
+            int4 s[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) s[u] = make_int4(0, 0, 0, 0);
+#pragma unroll
+            for (int g = 0; g < MAX_PEERS; ++g) {
+                if (g < p.world) {
+                    const int4* src = reinterpret_cast<const int4*>(p.counts_in[g] + base);
+                    int4 v[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int i = threadIdx.x + u * PM_THREADS;
+                        v[u] = i < N4 ? src[i] : make_int4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        s[u].x += v[u].x; s[u].y += v[u].y; s[u].z += v[u].z; s[u].w += v[u].w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = threadIdx.x + u * PM_THREADS;
+                if (i < N4) {
+                    reinterpret_cast<int4*>(rows)[i] = s[u];
+                    reinterpret_cast<int4*>(p.counts_own + base)[i] = s[u];
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < nv * NBINS; i += PM_THREADS) {
+                int32_t s = 0;
+#pragma unroll
+                for (int g = 0; g < MAX_PEERS; ++g)
+                    if (g < p.world) s += p.counts_in[g][base + i];
+                rows[i] = s;
+                p.counts_own[base + i] = s;
+            }
+        }
+        __syncthreads();
+        if ((int)threadIdx.x < nv) {
+            const int64_t v = v0 + threadIdx.x;
+            const int32_t* row = rows + threadIdx.x * NBINS;
+            int divergence = 0;
+#pragma unroll 10
+            for (int j = 0; j < NBINS; ++j) {
+                const double proportion = (double)row[j] / (double)p.true_counts.v[j];   // as divergence_kernel
+                divergence += proportion > p.threshold;
+            }
+            const double dv = (double)divergence / (double)p.bins_active;
+            double sc = 0.0;   // fixed rank order: every rank receives the same bits
+#pragma unroll
+            for (int g = 0; g < MAX_PEERS; ++g)
+                if (g < p.world) sc += p.score_in[g][v];
+#pragma unroll
+            for (int g = 0; g < MAX_PEERS; ++g)
+                if (g < p.world) {
+                    p.score_out[g][v] = sc;
+                    p.div_out[g][v] = dv;
+                }
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace wepp

@@ -150,6 +150,13 @@ struct wepp_handle {
     bool has_epp = false;
     int64_t epp_capacity = 0;
 
+    // multi-GPU exchange over peer memory (peer_merge_kernel): 0 score, 1 counts, 2 merged score, 3 dist_divergence
+    DevBuf<double> d_score_merged;
+    void* peer_ptr[MAX_PEERS][4] = {};
+    int32_t peer_rank = -1, peer_world = 0;
+    int64_t peer_true_counts[NBINS] = {};
+    bool peer_merged = false;   // d_score_merged / d_divergence hold the merged results of the last place
+
     // K4 over the resident reads (rescore_tiles.cuh): candidate stacks, per-window candidate entries, results
     DevBuf<int64_t> d_st_off, d_ccnt, d_coff, d_am_off;
     DevBuf<int32_t> d_st_pos, d_rs_min, d_rs_nbest, d_rs_before, d_rs_dist, d_am_idx;
@@ -280,6 +287,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     if (rc) return rc;
     const int n = h->n_nodes;
     int64_t launches = 0;
+    h->peer_merged = false;
 
     CU(h->d_maxpars.ensure((size_t)h->n_reads));
     CU(h->d_mult.ensure((size_t)h->n_reads));
@@ -452,6 +460,9 @@ void wepp_destroy(wepp_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
+    for (int g = 0; g < MAX_PEERS; ++g)
+        for (int b = 0; b < 4; ++b)
+            if (h->peer_ptr[g][b] && g != h->peer_rank) cudaIpcCloseMemHandle(h->peer_ptr[g][b]);
     h->d_stripes.release(); h->d_stripe_off.release(); h->d_mapped.release(); h->d_mapped_prefix.release();
     h->full.release(); h->sub.release();
     h->d_rstart.release(); h->d_rend.release(); h->d_rdegree.release(); h->d_rpos.release(); h->d_roff.release();
@@ -709,6 +720,12 @@ int wepp_get_node_summary(wepp_handle* h, double* score, double* dist_divergence
     if (!h->has_results || !h->d_score.p) return fail(WEPP_E_STATE, "no per-node results yet (call wepp_place)");
     CU(cudaSetDevice(h->device));
     const int n = h->n_nodes;
+    if (h->peer_merged) {   // wepp_peer_merge already evaluated both over all ranks
+        if (dist_divergence) CU(cudaMemcpyAsync(dist_divergence, h->d_divergence.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (score) CU(cudaMemcpyAsync(score, h->d_score_merged.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return WEPP_OK;
+    }
     if (dist_divergence) {
         CU(h->d_divergence.ensure((size_t)n));
         BinCounts tc;
@@ -791,6 +808,126 @@ int wepp_device_buffer(wepp_handle* h, int32_t which, void** dev_ptr, int64_t* n
     if (!p) return fail(WEPP_E_STATE, "buffer not allocated");
     *dev_ptr = p;
     if (n_bytes) *n_bytes = b;
+    return WEPP_OK;
+}
+
+// ---- multi-GPU exchange step over NVLink peer memory ---------------------------------------------
+namespace {
+struct PeerBlob {   // what one rank publishes (WEPP_PEER_BLOB_BYTES)
+    cudaIpcMemHandle_t mem[4];
+    int64_t true_counts[NBINS];
+    int64_t n_nodes;
+};
+static_assert(sizeof(PeerBlob) == WEPP_PEER_BLOB_BYTES, "WEPP_PEER_BLOB_BYTES out of date");
+
+void peer_release(wepp_handle* h) {
+    for (int g = 0; g < MAX_PEERS; ++g)
+        for (int b = 0; b < 4; ++b) {
+            if (h->peer_ptr[g][b] && g != h->peer_rank) cudaIpcCloseMemHandle(h->peer_ptr[g][b]);
+            h->peer_ptr[g][b] = nullptr;
+        }
+    h->peer_rank = -1;
+    h->peer_world = 0;
+}
+}  // namespace
+
+int wepp_peer_export(wepp_handle* h, void* blob) {
+    if (!h || !blob) return fail(WEPP_E_INVALID, "NULL argument");
+    if (!h->has_arena || !h->has_reads) return fail(WEPP_E_STATE, "wepp_set_arena and wepp_set_reads must be called first");
+    CU(cudaSetDevice(h->device));
+    const size_t n = (size_t)h->n_nodes;
+    CU(h->d_score.ensure(n));
+    CU(h->d_counts.ensure((n + 1) * NBINS));
+    CU(h->d_score_merged.ensure(n));
+    CU(h->d_divergence.ensure(n));
+    PeerBlob pb = {};
+    CU(cudaIpcGetMemHandle(&pb.mem[0], h->d_score.p));
+    CU(cudaIpcGetMemHandle(&pb.mem[1], h->d_counts.p));
+    CU(cudaIpcGetMemHandle(&pb.mem[2], h->d_score_merged.p));
+    CU(cudaIpcGetMemHandle(&pb.mem[3], h->d_divergence.p));
+    for (int j = 0; j < NBINS; ++j) pb.true_counts[j] = h->true_counts[j];
+    pb.n_nodes = h->n_nodes;
+    std::memcpy(blob, &pb, sizeof(pb));
+    return WEPP_OK;
+}
+
+int wepp_peer_open(wepp_handle* h, int32_t rank, int32_t world, const void* blobs) {
+    if (!h || !blobs) return fail(WEPP_E_INVALID, "NULL argument");
+    if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) return fail(WEPP_E_INVALID, "bad rank / world (at most 8 ranks)");
+    if (!h->d_score.p || !h->d_counts.p || !h->d_score_merged.p || !h->d_divergence.p)
+        return fail(WEPP_E_STATE, "wepp_peer_export must be called first");
+    CU(cudaSetDevice(h->device));
+    peer_release(h);
+    const PeerBlob* pb = static_cast<const PeerBlob*>(blobs);
+    for (int j = 0; j < NBINS; ++j) h->peer_true_counts[j] = 0;
+    h->peer_rank = rank;
+    h->peer_world = world;
+    for (int g = 0; g < world; ++g) {
+        if (pb[g].n_nodes != h->n_nodes) {
+            peer_release(h);
+            return fail(WEPP_E_INVALID, "ranks hold different trees");
+        }
+        for (int j = 0; j < NBINS; ++j) h->peer_true_counts[j] += pb[g].true_counts[j];
+        if (g == rank) {
+            h->peer_ptr[g][0] = h->d_score.p;
+            h->peer_ptr[g][1] = h->d_counts.p;
+            h->peer_ptr[g][2] = h->d_score_merged.p;
+            h->peer_ptr[g][3] = h->d_divergence.p;
+            continue;
+        }
+        for (int b = 0; b < 4; ++b) {
+            cudaError_t e = cudaIpcOpenMemHandle(&h->peer_ptr[g][b], pb[g].mem[b], cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                h->peer_ptr[g][b] = nullptr;
+                peer_release(h);
+                return fail(WEPP_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+            }
+        }
+    }
+    return WEPP_OK;
+}
+
+int wepp_peer_merge(wepp_handle* h) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    if (h->peer_world < 1) return fail(WEPP_E_STATE, "wepp_peer_open must be called first");
+    if (!h->has_results) return fail(WEPP_E_STATE, "no per-node results yet (call wepp_place)");
+    CU(cudaSetDevice(h->device));
+    PeerMergeParams p = {};
+    const int64_t n = h->n_nodes;
+    const int w = h->peer_world, r = h->peer_rank;
+    auto cut = [&](int g) { return g >= w ? n : (n * g / w) / PM_NODES * PM_NODES; };
+    p.world = w;
+    p.lo = (int32_t)cut(r);
+    p.hi = (int32_t)cut(r + 1);
+    for (int g = 0; g < w; ++g) {
+        p.score_in[g] = static_cast<const double*>(h->peer_ptr[g][0]);
+        p.counts_in[g] = static_cast<const int32_t*>(h->peer_ptr[g][1]);
+        p.score_out[g] = static_cast<double*>(h->peer_ptr[g][2]);
+        p.div_out[g] = static_cast<double*>(h->peer_ptr[g][3]);
+    }
+    p.counts_own = h->d_counts.p;
+    p.bins_active = 0;
+    for (int j = 0; j < NBINS; ++j) {
+        if (h->peer_true_counts[j] > 0x7FFFFFFFll) return fail(WEPP_E_INVALID, "degree-weighted read count of a bin exceeds int32");
+        p.true_counts.v[j] = (int32_t)h->peer_true_counts[j];
+        p.bins_active += p.true_counts.v[j] != 0;
+    }
+    p.threshold = 0.5 / 100;
+    if (p.hi > p.lo) {
+        const int blocks = (int)std::min<int64_t>(((int64_t)p.hi - p.lo + PM_NODES - 1) / PM_NODES, (int64_t)h->n_sms * 8);
+        peer_merge_kernel<<<blocks, PM_THREADS, 0, h->stream>>>(p);
+        CU(cudaGetLastError());
+    }
+    h->peer_merged = true;
+    return WEPP_OK;
+}
+
+int wepp_peer_close(wepp_handle* h) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    peer_release(h);
+    h->peer_merged = false;
     return WEPP_OK;
 }
 

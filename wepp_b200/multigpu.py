@@ -22,6 +22,32 @@ def allreduce_node_arrays(score, counts, group=None) -> None:
     dist.all_reduce(score, op=dist.ReduceOp.SUM, group=group)
 
 
+class PeerMerge:
+    """The exchange step over NVLink peer memory (wepp_peer_*, include/wepp_b200.h): every rank sums its slice of
+    the nodes straight out of the other ranks' HBM, evaluates dist_divergence on the merged rows and stores the
+    merged score / dist_divergence into every rank.  torch.distributed only moves the 664-byte IPC blobs once
+    and provides the two stream-ordered barriers around the kernel (a 4-byte all-reduce on the placement stream)."""
+
+    def __init__(self, placer, rank: int, world: int, device: int, group=None):
+        import torch
+        import torch.distributed as dist
+        self.placer, self.group = placer, group
+        blobs = [None] * world
+        dist.all_gather_object(blobs, placer.peer_export(), group=group)
+        placer.peer_open(rank, world, b"".join(blobs))
+        self.token = torch.zeros(1, dtype=torch.int32, device=f"cuda:{device}")
+
+    def merge(self) -> None:
+        """Enqueue: barrier, merge kernel, barrier — all on the current (= the placer's) stream."""
+        import torch.distributed as dist
+        dist.all_reduce(self.token, group=self.group)   # every rank's placement + scans are done
+        self.placer.peer_merge()
+        dist.all_reduce(self.token, group=self.group)   # every rank is done reading: the next place may overwrite
+
+    def close(self) -> None:
+        self.placer.peer_close()
+
+
 def gather_read_results(local, n_reads: int, rank: int, world: int, group=None):
     """Concatenate per-read int32 results of all ranks in read order (rank slices are contiguous)."""
     import torch

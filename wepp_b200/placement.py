@@ -165,6 +165,24 @@ class Placer:
             idx = idx[: int(off[-1])]
         return md, dist, off, idx
 
+    PEER_BLOB_BYTES = 664
+
+    def peer_export(self) -> bytes:
+        """wepp_peer_export: this rank's CUDA IPC handles + per-bin read counts, to be exchanged between ranks."""
+        buf = C.create_string_buffer(self.PEER_BLOB_BYTES)
+        check(self.lib.wepp_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_open(self, rank: int, world: int, blobs: bytes) -> None:
+        assert len(blobs) == world * self.PEER_BLOB_BYTES
+        check(self.lib.wepp_peer_open(self.h, rank, world, C.c_char_p(blobs)))
+
+    def peer_merge(self) -> None:
+        check(self.lib.wepp_peer_merge(self.h))
+
+    def peer_close(self) -> None:
+        check(self.lib.wepp_peer_close(self.h))
+
     def device_buffer(self, which: int):
         p = C.c_void_p()
         n = C.c_int64()
