@@ -50,7 +50,7 @@ def build_cuda(force: bool = False) -> str:
     objs = []
     cu, cu_o = os.path.join(CSRC, "wepp_abi.cu"), os.path.join(OBJ_DIR, "wepp_abi.o")
     if force or not _newer(cu_o, [cu] + headers):
-        _run([nvcc, *NVCC_OBJ_FLAGS, "-c", cu, "-o", cu_o])
+        _run([nvcc, *NVCC_OBJ_FLAGS, *os.environ.get("WEPP_NVCC_EXTRA", "").split(), "-c", cu, "-o", cu_o])
     objs.append(cu_o)
     for f in HOST_SRCS:
         src, obj = os.path.join(CSRC, f), os.path.join(OBJ_DIR, f[:-4] + ".o")

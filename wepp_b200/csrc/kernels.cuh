@@ -1248,7 +1248,7 @@ constexpr int PM_NODES = 64;      // nodes per block iteration (slice starts are
 constexpr int PM_THREADS = 256;
 
 struct PeerMergeParams {
-    int32_t world, lo, hi;                   // this rank's node slice [lo, hi)
+    int32_t world, rank, lo, hi;             // this rank's node slice [lo, hi)
     const int32_t* counts_in[MAX_PEERS];     // every rank's scanned counts[N][50]
     const double* score_in[MAX_PEERS];       // every rank's score[N]
     double* score_out[MAX_PEERS];            // every rank's merged score[N]
@@ -1270,20 +1270,26 @@ __global__ void __launch_bounds__(PM_THREADS) peer_merge_kernel(const PeerMergeP
             int4 s[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) s[u] = make_int4(0, 0, 0, 0);
+            // two ranks' loads in flight at a time, starting from the next rank up so that the ranks do not all
+            // pull from the same GPU at once (integer sums: the order does not matter)
+            for (int k = 0; k < p.world; k += 2) {
+                int g0 = p.rank + 1 + k, g1 = g0 + 1;
+                g0 -= g0 >= p.world ? p.world : 0;
+                g1 -= g1 >= p.world ? p.world : 0;
+                const bool two = k + 1 < p.world;
+                const int4* src0 = reinterpret_cast<const int4*>(p.counts_in[g0] + base);
+                const int4* src1 = reinterpret_cast<const int4*>(p.counts_in[g1] + base);
+                int4 v[U], w[U];
 #pragma unroll
-            for (int g = 0; g < MAX_PEERS; ++g) {
-                if (g < p.world) {
-                    const int4* src = reinterpret_cast<const int4*>(p.counts_in[g] + base);
-                    int4 v[U];
+                for (int u = 0; u < U; ++u) {
+                    const int i = threadIdx.x + u * PM_THREADS;
+                    v[u] = i < N4 ? src0[i] : make_int4(0, 0, 0, 0);
+                    w[u] = (two && i < N4) ? src1[i] : make_int4(0, 0, 0, 0);
+                }
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int i = threadIdx.x + u * PM_THREADS;
-                        v[u] = i < N4 ? src[i] : make_int4(0, 0, 0, 0);
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        s[u].x += v[u].x; s[u].y += v[u].y; s[u].z += v[u].z; s[u].w += v[u].w;
-                    }
+                for (int u = 0; u < U; ++u) {
+                    s[u].x += v[u].x + w[u].x; s[u].y += v[u].y + w[u].y;
+                    s[u].z += v[u].z + w[u].z; s[u].w += v[u].w + w[u].w;
                 }
             }
 #pragma unroll

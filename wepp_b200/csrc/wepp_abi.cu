@@ -897,6 +897,7 @@ int wepp_peer_merge(wepp_handle* h) {
     const int w = h->peer_world, r = h->peer_rank;
     auto cut = [&](int g) { return g >= w ? n : (n * g / w) / PM_NODES * PM_NODES; };
     p.world = w;
+    p.rank = r;
     p.lo = (int32_t)cut(r);
     p.hi = (int32_t)cut(r + 1);
     for (int g = 0; g < w; ++g) {
