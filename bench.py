@@ -368,6 +368,29 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 dt = float(t.item())
             return dt
 
+        def e2e_phases():
+            """One more e2e step with a synchronisation after each phase (not part of the e2e figure)."""
+            ph = {}
+            barrier()
+            t0 = time.perf_counter()
+            p.set_reads(reads_h)
+            p.set_mapped(None)
+            torch.cuda.synchronize()
+            ph["reads_in_keying_lists_ms"] = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            p.place(0, 0, sync=False)
+            exchange()
+            torch.cuda.synchronize()
+            ph["place_and_exchange_ms"] = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            check(p.lib.wepp_get_read_results(p.h, ptr(mp), ptr(mu)))
+            ph["read_results_out_ms"] = (time.perf_counter() - t0) * 1e3
+            t0 = time.perf_counter()
+            check(p.lib.wepp_get_node_summary(p.h, ptr(sc), ptr(dv)))
+            ph["node_summary_out_ms"] = (time.perf_counter() - t0) * 1e3
+            barrier()
+            return ph
+
         q = st["stripe_width"]
         n_stripes = GENOME // q + 1
         n_cells = n_stripes * min(n_stripes, 4000 // q + 2) * min(50, q // (GENOME // 50) + 2)   # keying histogram
@@ -377,7 +400,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dt = time_e2e(False)
         e2e = {"value": reads_total / dt, "unit": "reads/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(r * 8 + n * 16 + d2h_keys), "ms_per_step": dt * 1e3,
-               "outputs": "max_parsimony, multiplicity per read; score, dist_divergence per node"}
+               "outputs": "max_parsimony, multiplicity per read; score, dist_divergence per node",
+               "phases": e2e_phases()}
         dt = time_e2e(True)
         e2e_full = {"value": reads_total / dt, "unit": "reads/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(r * 8 + n * (8 + 200) + d2h_keys), "ms_per_step": dt * 1e3,

@@ -51,11 +51,20 @@ struct DevBuf {
     size_t cap = 0;
     cudaError_t ensure(size_t n) {
         if (n <= cap) return cudaSuccess;
+        // a buffer that has to grow again gets 25 % headroom: sizes that creep up call after call (candidate
+        // sets, subsets) must not pay a cudaFree + cudaMalloc (a device synchronisation) every time
+        const size_t want = p ? n + n / 4 : n;
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        cudaError_t e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
-        if (e == cudaSuccess) cap = n;
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(want, 1) * sizeof(T));
+        if (e != cudaSuccess && want > n) {
+            (void)cudaGetLastError();
+            e = cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T));
+            if (e == cudaSuccess) cap = n;
+            return e;
+        }
+        if (e == cudaSuccess) cap = want;
         return e;
     }
     void release() {
