@@ -423,12 +423,22 @@ std::vector<Abundance> freyja_filter(Pipeline& p, const std::vector<int32_t>& in
 std::string pipeline_post_filter(Pipeline& p, std::vector<int32_t> input, std::vector<Abundance>& out) {
     const int num_filter_rounds = MAX_NEIGHBOR_ITERATIONS, freeze_round = 1;
     std::set<int32_t> frozen, last_round;
+    // WEPP_TIMING=1: stage times on stderr (development aid)
+    const bool timing = std::getenv("WEPP_TIMING") && std::atoi(std::getenv("WEPP_TIMING")) != 0;
+    auto t_last = std::chrono::steady_clock::now();
+    auto stage = [&](const char* what) {
+        const auto now = std::chrono::steady_clock::now();
+        if (timing && what) std::fprintf(stderr, "[wepp timing] %-28s %9.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     out.clear();
     for (int i = 0; i < num_filter_rounds; ++i) {
         std::vector<int32_t> full_input = input;
         for (int32_t hap : frozen)
             if (std::find(full_input.begin(), full_input.end(), hap) == full_input.end()) full_input.push_back(hap);
+        stage(nullptr);
         std::vector<Abundance> filtered = freyja_filter(p, full_input);
+        stage("barcodes + freyja demix");
         std::vector<int32_t> this_round;
         for (const Abundance& a : filtered) this_round.push_back(a.hap);
         std::sort(this_round.begin(), this_round.end());
@@ -439,23 +449,25 @@ std::string pipeline_post_filter(Pipeline& p, std::vector<int32_t> input, std::v
         if (i >= freeze_round)
             std::set_intersection(this_round.begin(), this_round.end(), last_round.begin(), last_round.end(), std::inserter(frozen, frozen.end()));
         last_round = std::set<int32_t>(this_round.begin(), this_round.end());
-        // add neighbours: the stacks of the BFS frontiers are warmed in parallel, the sets are built in the
-        // reference's order
+        // add neighbours: every haplotype's neighbourhood is searched in parallel (closest_neighbors is a pure
+        // function of the tree and the scores); the union is built serially, in the reference's order
+        std::vector<std::vector<int32_t>> nbrs(this_round.size());
         {
             std::vector<std::thread> pool;
             std::atomic<size_t> next{0};
             for (int t = 0; t < p.n_threads; ++t)
                 pool.emplace_back([&]() {
-                    for (size_t k; (k = next.fetch_add(1)) < this_round.size();) closest_neighbors(p, this_round[k], MAX_NEIGHBOR_MUTATION, MAX_NEIGHBORS_FREYJA);
+                    for (size_t k; (k = next.fetch_add(1)) < this_round.size();) {
+                        const ScoreSet s = closest_neighbors(p, this_round[k], MAX_NEIGHBOR_MUTATION, MAX_NEIGHBORS_FREYJA);
+                        nbrs[k].assign(s.begin(), s.end());
+                    }
                 });
             for (auto& th : pool) th.join();
         }
         ScoreSet build(ScoreCmp{&p});
-        for (int32_t hap : this_round) {
-            ScoreSet nbrs = closest_neighbors(p, hap, MAX_NEIGHBOR_MUTATION, MAX_NEIGHBORS_FREYJA);
-            build.insert(nbrs.begin(), nbrs.end());
-        }
+        for (const std::vector<int32_t>& nb : nbrs) build.insert(nb.begin(), nb.end());
         input.assign(build.begin(), build.end());
+        stage("neighbour expansion");
     }
     return "";
 }
@@ -499,11 +511,16 @@ int detect_peaks(const Dataset& ds) {
         std::fprintf(stderr, "%s\n", err.c_str());
         return 1;
     }
+    const bool timing = std::getenv("WEPP_TIMING") && std::atoi(std::getenv("WEPP_TIMING")) != 0;
+    const auto t_w = std::chrono::steady_clock::now();
     err = pipeline_write_results(p, full);
     if (!err.empty()) {
         std::fprintf(stderr, "%s\n", err.c_str());
         return 1;
     }
+    if (timing)
+        std::fprintf(stderr, "[wepp timing] %-28s %9.1f ms\n", "result files",
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_w).count());
     std::cout << "--- post filter + result files took " << t.seconds() << " seconds " << std::endl;
     std::cout << "--- RUN COMPLETED" << std::endl;
     return 0;
