@@ -189,9 +189,11 @@ std::string finish_read_plan(const EulerStripes& es, int32_t reads_per_lane, con
     // reads per tile
     int32_t k = reads_per_lane;
     if (k != 2 && k != 4 && k != 8) {
-        // selector table = width * 32 lanes * K bytes next to ~48 KB of staging: two CTAs per SM
-        // up to 256 (K=8) / 512 (K=4) bases
-        k = out.max_width <= 256 ? 8 : (out.max_width <= 640 ? 4 : 2);
+        // selector table = width * 32 lanes * K bytes next to ~49 KB of staging and pattern tables.  The largest K
+        // whose table fits the 227 KB of a B200 CTA wins even when only one CTA is then resident per SM: measured
+        // on 8M nodes, K=8 at one CTA/SM beats K=4 at two by 1.6x on 490-base windows, K=4 at one beats K=2 at
+        // two by 1.8x on 1.1 kb (ONT) windows (profiles/other_configs.py) — the per-entry work is shared by 2x the reads.
+        k = out.max_width <= PLACE_TABLE_BYTES / (32 * 8) ? 8 : (out.max_width <= PLACE_TABLE_BYTES / (32 * 4) ? 4 : 2);
         auto tiles_for = [&](int kk) {
             int64_t t = 0;
             for (int64_t c : bucket_count) t += (c + 32 * kk - 1) / (32 * kk);

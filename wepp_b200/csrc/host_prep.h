@@ -81,6 +81,10 @@ struct ReadPlan {
     int64_t scanned_read_entries = 0;  // sum over reads of list length
 };
 
+// Shared memory left for place_kernel's selector table on a B200 CTA (232,448 B opt-in maximum minus the kernel's
+// fixed areas; kept in step with kernels.cuh by a static_assert in wepp_abi.cu).
+constexpr int32_t PLACE_TABLE_BYTES = 232448 - 50192;
+
 // Read validation errors (shared by the host keying and the device keying kernel).
 enum { RP_OK = 0, RP_ERR_WINDOW = 1, RP_ERR_DEGREE = 2, RP_ERR_OFFSETS = 3, RP_ERR_MUT_ORDER = 4, RP_ERR_MUT_CODE = 5 };
 const char* read_plan_error(int code);

@@ -266,6 +266,8 @@ int finalize_plan(wepp_handle* h, wepp_handle::DevPlan& dp) {
     return WEPP_OK;
 }
 
+static_assert(PLACE_TABLE_BYTES == 232448 - SMEM_CODES, "host_prep.h: PLACE_TABLE_BYTES out of step with the kernel's layout");
+
 template <int K, bool ACC, bool EPP>
 int launch_place(wepp_handle* h, const PlaceParams& pp, int width) {
     PlaceParams p = pp;
