@@ -407,6 +407,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "d2h_bytes_per_step": int(r * 8 + n * (8 + 200) + d2h_keys), "ms_per_step": dt * 1e3,
                     "outputs": "as e2e, with mapped_read_counts[N][50] instead of dist_divergence"}
 
+    if peer is not None:
+        p.place(0, 0, sync=False)
+        peer.merge()
+        peer.close()
     c5 = None
     if not args.no_c5:
         c5 = run_c5(args, p, arena, reads, world, dev, barrier)

@@ -927,8 +927,10 @@ int wepp_peer_merge(wepp_handle* h) {
     p.threshold = 0.5 / 100;
     if (p.hi > p.lo) {
         const int blocks = (int)std::min<int64_t>(((int64_t)p.hi - p.lo + PM_NODES - 1) / PM_NODES, (int64_t)h->n_sms * 8);
+        CU(cudaEventRecord(h->ev[4], h->stream));
         peer_merge_kernel<<<blocks, PM_THREADS, 0, h->stream>>>(p);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(h->ev[5], h->stream));
     }
     h->peer_merged = true;
     return WEPP_OK;
@@ -938,6 +940,11 @@ int wepp_peer_close(wepp_handle* h) {
     if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
     CU(cudaSetDevice(h->device));
     CU(cudaStreamSynchronize(h->stream));
+    if (getenv("WEPP_TIMING") && atoi(getenv("WEPP_TIMING")) != 0 && h->peer_merged) {   // development aid
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]) == cudaSuccess)
+            fprintf(stderr, "[wepp timing] rank %d: last peer_merge_kernel %.3f ms\n", h->peer_rank, ms);
+    }
     peer_release(h);
     h->peer_merged = false;
     return WEPP_OK;
