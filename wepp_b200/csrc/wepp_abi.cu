@@ -1463,7 +1463,22 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
     std::vector<int32_t> cand_nodes, consideration, nb, marks;
     std::vector<double> cand_full;
     std::vector<int64_t> removed_now;
+    // WEPP_TIMING=1: accumulated phase times of the loop on stderr (development aid; adds synchronisations)
+    const bool timing = getenv("WEPP_TIMING") && atoi(getenv("WEPP_TIMING")) != 0;
+    double t_phase[6] = {};
+    int n_steps = 0;
+    int64_t n_removed_total = 0;
+    auto t_mark = std::chrono::steady_clock::now();
+    auto lap = [&](int k) {
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        const auto t = std::chrono::steady_clock::now();
+        t_phase[k] += std::chrono::duration<double, std::milli>(t - t_mark).count();
+        t_mark = t;
+    };
     while (remaining > 0 && (int)peaks.size() < MAX_PEAKS) {
+        ++n_steps;
+        lap(5);
         // ---- the head of the sorted `current` list (initial_filter.cpp:396-417) -------------------
         FCU(cudaMemsetAsync(d_max.p, 0, 8, st));
         peak_max_kernel<<<1184, 256, 0, st>>>(d_cur.p, h->d_divergence.p, d_pmapped.p, n, d_max.p);
@@ -1506,6 +1521,7 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
                 marks.push_back(v);
             }
         }
+        lap(0);
         // ---- clear_neighbors (:368-385) ------------------------------------------------------------
         for (int32_t pivot : consideration) {
             peaks.insert(pivot);
@@ -1515,6 +1531,7 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
                 marks.push_back(v);
             }
         }
+        lap(1);
         FCU(upload(d_marks, marks, st));
         if (!marks.empty()) mark_kernel<<<((int)marks.size() + 255) / 256, 256, 0, st>>>(d_pmapped.p, d_marks.p, (int)marks.size());
         // ---- singular_step for every chosen peak (:344-366): correspondents, then their removal -----
@@ -1539,6 +1556,8 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
         int n_rem = 0;
         FCU(cudaMemcpyAsync(&n_rem, d_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         FCU(cudaStreamSynchronize(st));
+        lap(2);
+        n_removed_total += n_rem;
         if (n_rem > 0) {
             removed_now.resize((size_t)n_rem);
             FCU(cudaMemcpyAsync(removed_now.data(), d_list.p, (size_t)n_rem * 8, cudaMemcpyDeviceToHost, st));
@@ -1551,6 +1570,7 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
                 release();
                 return fail(WEPP_E_INVALID, err);
             }
+            lap(3);
             rc = upload_plan(h, h->sub, true);
             if (!rc) rc = run_place(h, h->sub, true, 0, 0, /*with_counts*/ false, d_contrib.p);
             if (rc) {
@@ -1559,11 +1579,17 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
             }
             subtract_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_cur.p, d_contrib.p, n);
             remaining -= n_rem;
+            lap(4);
         }
         if (consideration.empty()) break;   // nothing selectable: the reference would spin on the same head
     }
 
+    if (timing)
+        fprintf(stderr, "[wepp timing] peak loop: %d steps, %lld reads removed | top score + ties %.1f ms | neighbourhoods (host) %.1f ms | "
+                        "correspondents %.1f ms | subset plan (host) %.1f ms | subset lists + place + subtract %.1f ms | other %.1f ms\n",
+                n_steps, (long long)n_removed_total, t_phase[0], t_phase[1], t_phase[2], t_phase[3], t_phase[4], t_phase[5]);
     // ---- neighbours of the peaks (:476-503) ---------------------------------------------------------
+    const auto t_nb = std::chrono::steady_clock::now();
     std::vector<double> full((size_t)n), dv((size_t)n);
     FCU(cudaMemcpyAsync(full.data(), d_orig.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
     FCU(cudaMemcpyAsync(dv.data(), h->d_divergence.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
@@ -1594,6 +1620,9 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
             std::abs(FREYJA_PEAKS_LIMIT - ((int)nbrs.size() + (int)peaks.size())))
             nbrs = curr;
     }
+    if (timing)
+        fprintf(stderr, "[wepp timing] neighbour expansion (host) %.1f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_nb).count());
     release();
 #undef FCU
     const int total = (int)peaks.size() + (int)nbrs.size();
