@@ -135,6 +135,30 @@ def test_list_build_rank_table_and_binary_search_agree(monkeypatch):
     p.close()
 
 
+def test_scattered_windows_bucket_coarsening(monkeypatch):
+    """Trimmed short reads (starts anywhere, lengths 30-150): merged buckets (reads served by a wider list of the
+    same first stripe) and plain buckets must both give the oracle's placement, on the device- and host-keyed paths."""
+    arena, base = cases.small_case(seed=17)
+    rng = np.random.default_rng(6)
+    idx = rng.integers(0, base.n_reads, 900)
+    reads = base.take(idx)
+    # shrink every window to a random sub-interval that still holds the read's mutations
+    lo = reads.start.copy(); hi = reads.end.copy()
+    for i in range(reads.n_reads):
+        a, b = int(reads.rm_off[i]), int(reads.rm_off[i + 1])
+        first = int(reads.rm_pos[a]) if b > a else int(hi[i])
+        last = int(reads.rm_pos[b - 1]) if b > a else int(lo[i])
+        lo[i] = rng.integers(lo[i], min(first, hi[i]) + 1)
+        hi[i] = rng.integers(max(last, lo[i]), hi[i] + 1)
+    reads = synth.Reads(lo.astype(np.int32), hi.astype(np.int32), reads.degree, reads.rm_off, reads.rm_pos, reads.rm_nuc)
+    for q in (8, 1):      # 8: device keying, 1: host keying (cell table too large)
+        st_m = _check(arena, reads, None, q, 0)
+        monkeypatch.setenv("WEPP_NO_BUCKET_MERGE", "1")
+        st_p = _check(arena, reads, None, q, 0)
+        monkeypatch.delenv("WEPP_NO_BUCKET_MERGE")
+        assert st_m["n_buckets"] < st_p["n_buckets"]
+
+
 def test_everything_mapped_gives_zero_multiplicity():
     arena, reads = cases.small_case(seed=5, n_reads=100)
     mapped = np.ones(arena.n_nodes, np.uint8)

@@ -9,6 +9,7 @@ import pytest
 
 import oracle
 from tests import cases, emulate
+from wepp_b200 import synth
 from wepp_b200 import _lib
 from wepp_b200._lib import ptr
 
@@ -88,6 +89,47 @@ def test_read_plan_is_a_permutation_and_buckets_cover_windows():
     s, e = reads.start[perm], reads.end[perm]
     assert np.all(qs * 32 <= s) and np.all(e <= qe * 32 + 31)
     assert np.array_equal(bn, np.minimum(s // (arena.genome_size // 50), 49))
+
+
+def _host_plan(arena, reads, q):
+    lib = _lib.load()
+    r = reads.n_reads
+    perm = np.full(r, -1, np.int64)
+    qs = np.zeros(r, np.int32); qe = np.zeros(r, np.int32); bn = np.zeros(r, np.int32)
+    rpt = C.c_int32(0)
+    nt = _lib.check(lib.wepp_host_read_plan(arena.genome_size, q, 0, r, ptr(reads.start), ptr(reads.end),
+                                            ptr(reads.degree), ptr(reads.rm_off), ptr(reads.rm_pos), ptr(reads.rm_nuc),
+                                            ptr(perm), ptr(qs), ptr(qe), ptr(bn), C.byref(rpt)))
+    return nt, rpt.value, perm, qs, qe, bn
+
+
+def test_bucket_coarsening_keeps_windows_covered_and_saves_tile_entries(monkeypatch):
+    """Reads with scattered starts and lengths (trimmed short reads): sparse (stripe range, bin) buckets are merged
+    into wider ones of the same first stripe.  Every window must stay inside its list's range, the count bin must be
+    the read's own, and the tile-entries (tiles x list width) must not grow."""
+    arena, _ = cases.small_case(seed=13, n_reads=10)
+    rng = np.random.default_rng(4)
+    r = 4000
+    start = rng.integers(1, arena.genome_size - 160, r).astype(np.int32)
+    end = (start + rng.integers(30, 150, r)).astype(np.int32)
+    reads = synth.Reads(start, end, np.ones(r, np.int32), np.zeros(r + 1, np.int64), np.zeros(0, np.int32), np.zeros(0, np.uint8))
+    q = 8
+
+    def cost(plan):
+        nt, rpt, perm, qs, qe, bn = plan
+        s, e = reads.start[perm], reads.end[perm]
+        assert np.array_equal(np.sort(perm), np.arange(r))
+        assert np.all(qs * q <= s) and np.all(e <= qe * q + q - 1)
+        assert np.array_equal(bn, np.minimum(s // (arena.genome_size // 50), 49))
+        key = np.stack([qs, qe, bn], axis=1)
+        uniq, counts = np.unique(key, axis=0, return_counts=True)
+        tiles = -(-counts // rpt)
+        return int((tiles * (uniq[:, 1] - uniq[:, 0] + 1)).sum()), len(uniq)
+
+    merged = cost(_host_plan(arena, reads, q))
+    monkeypatch.setenv("WEPP_NO_BUCKET_MERGE", "1")
+    plain = cost(_host_plan(arena, reads, q))
+    assert merged[1] < plain[1] and merged[0] <= plain[0]
 
 
 @pytest.mark.parametrize("bad", ["parent", "dup_pos", "pos_range", "read_nuc", "read_order", "read_window"])

@@ -1,6 +1,7 @@
 // host_prep.cpp — see host_prep.h.
 #include "host_prep.h"
 
+#include <cstdlib>
 #include <algorithm>
 #include <cstring>
 #include <numeric>
@@ -193,7 +194,7 @@ std::string finish_read_plan(const EulerStripes& es, int32_t reads_per_lane, con
         // whose table fits the 227 KB of a B200 CTA wins even when only one CTA is then resident per SM: measured
         // on 8M nodes, K=8 at one CTA/SM beats K=4 at two by 1.6x on 490-base windows, K=4 at one beats K=2 at
         // two by 1.8x on 1.1 kb (ONT) windows (profiles/other_configs.py) — the per-entry work is shared by 2x the reads.
-        k = out.max_width <= PLACE_TABLE_BYTES / (32 * 8) ? 8 : (out.max_width <= PLACE_TABLE_BYTES / (32 * 4) ? 4 : 2);
+        k = reads_per_lane_for_width(out.max_width);
         auto tiles_for = [&](int kk) {
             int64_t t = 0;
             for (int64_t c : bucket_count) t += (c + 32 * kk - 1) / (32 * kk);
@@ -223,6 +224,33 @@ std::string finish_read_plan(const EulerStripes& es, int32_t reads_per_lane, con
         return out.lists[out.buckets[a.bucket].list].n > out.lists[out.buckets[b.bucket].list].n;
     });
     return "";
+}
+
+int32_t reads_per_lane_for_width(int32_t width) {
+    return width <= PLACE_TABLE_BYTES / (32 * 8) ? 8 : (width <= PLACE_TABLE_BYTES / (32 * 4) ? 4 : 2);
+}
+
+void merge_span_chain(const std::vector<std::pair<int32_t, int64_t>>& spans, int64_t reads_per_tile, std::vector<int32_t>& target) {
+    const size_t m = spans.size();
+    target.assign(m, 0);
+    auto tiles = [&](int64_t c) { return (c + reads_per_tile - 1) / reads_per_tile; };
+    size_t group = 0;      // first span of the group being carried upwards
+    int64_t carry = 0;
+    for (size_t i = 0; i < m; ++i) {
+        const int64_t total = carry + spans[i].second;
+        bool move = false;
+        if (i + 1 < m) {
+            const int64_t w = spans[i].first + 1, w2 = spans[i + 1].first + 1, c2 = spans[i + 1].second;
+            move = tiles(total + c2) * w2 <= tiles(total) * w + tiles(c2) * w2;
+        }
+        if (move) {
+            carry = total;
+        } else {
+            for (size_t j = group; j <= i; ++j) target[j] = (int32_t)i;
+            group = i + 1;
+            carry = 0;
+        }
+    }
 }
 
 ListDesc make_list_desc(const EulerStripes& es, int32_t qs, int32_t qe) {
@@ -287,6 +315,44 @@ std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t
     for (const char* e : errs)
         if (e) return e;
     for (int64_t m : n_mut) out.n_read_muts += m;
+
+    // bucket coarsening (merge_span_chain): per (first stripe, count bin) the spans that occur, then every
+    // read's qe becomes its group's
+    if (n_sel > 0 && !(std::getenv("WEPP_NO_BUCKET_MERGE") && std::atoi(std::getenv("WEPP_NO_BUCKET_MERGE")) != 0)) {
+        int32_t max_span = 0;
+        for (int64_t i = 0; i < n_sel; ++i) max_span = std::max(max_span, key_qe[i] - key_qs[i]);
+        const int64_t tile = 32 * (int64_t)((reads_per_lane == 2 || reads_per_lane == 4 || reads_per_lane == 8)
+                                                ? reads_per_lane : reads_per_lane_for_width((max_span + 1) * q));
+        const uint64_t S = (uint64_t)max_span + 1;
+        std::vector<uint64_t> keys((size_t)n_sel);
+        for (int64_t i = 0; i < n_sel; ++i)
+            keys[(size_t)i] = (((uint64_t)key_qs[i] * NUM_RANGE_BINS + key_bin[i]) * S) + (uint64_t)(key_qe[i] - key_qs[i]);
+        std::vector<uint64_t> sorted(keys);
+        std::sort(sorted.begin(), sorted.end());
+        std::vector<uint64_t> uniq;          // distinct keys, ascending
+        std::vector<int32_t> uniq_target;    // the span each one is served by
+        std::vector<std::pair<int32_t, int64_t>> chain;
+        std::vector<int32_t> tgt;
+        for (size_t a = 0; a < sorted.size();) {
+            const uint64_t head = sorted[a] / S;
+            chain.clear();
+            size_t b = a;
+            while (b < sorted.size() && sorted[b] / S == head) {
+                size_t c = b;
+                while (c < sorted.size() && sorted[c] == sorted[b]) ++c;
+                chain.emplace_back((int32_t)(sorted[b] % S), (int64_t)(c - b));
+                uniq.push_back(sorted[b]);
+                b = c;
+            }
+            merge_span_chain(chain, tile, tgt);
+            for (size_t j = 0; j < chain.size(); ++j) uniq_target.push_back(chain[(size_t)tgt[j]].first);
+            a = b;
+        }
+        for (int64_t i = 0; i < n_sel; ++i) {
+            const size_t u = (size_t)(std::lower_bound(uniq.begin(), uniq.end(), keys[(size_t)i]) - uniq.begin());
+            key_qe[i] = key_qs[i] + uniq_target[u];
+        }
+    }
 
     // list and bucket ids in first-appearance order (flat tables: one short vector of (qe, list) per qs)
     std::vector<std::vector<std::pair<int32_t, int32_t>>> lists_of_qs((size_t)es.n_stripes + 1);

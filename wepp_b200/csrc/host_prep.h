@@ -97,6 +97,14 @@ std::string build_read_plan(const EulerStripes& es, int32_t genome_size, int64_t
                             const uint8_t* rm_nuc, int32_t reads_per_lane, const int64_t* subset, int64_t n_subset,
                             ReadPlan& out);
 
+// Bucket coarsening.  A read may use ANY list whose stripe range contains its window (positions outside the
+// window select class "outside" and change nothing), at the price of a longer list.  For one (first stripe,
+// count bin), `spans` holds the (qe - qs, reads) pairs in ascending span order; target[i] is the index of the
+// span whose list the reads of span i use.  Greedy, smallest span first: a group moves up to the next span when
+// that does not cost more tile-entries (tiles x list width) — sparse buckets stop paying for nearly empty tiles.
+void merge_span_chain(const std::vector<std::pair<int32_t, int64_t>>& spans, int64_t reads_per_tile, std::vector<int32_t>& target);
+int32_t reads_per_lane_for_width(int32_t width);
+
 // Descriptor half of the plan, from per-bucket read counts (out.lists / out.buckets already filled).
 ListDesc make_list_desc(const EulerStripes& es, int32_t qs, int32_t qe);
 std::string finish_read_plan(const EulerStripes& es, int32_t reads_per_lane, const std::vector<int64_t>& bucket_count,

@@ -614,21 +614,47 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
         pl.n_read_muts = nm;
         std::vector<int32_t> bucket_of_cell((size_t)n_cells, -1);
         std::vector<int64_t> bucket_count;
+        // bucket coarsening (merge_span_chain, host_prep.h): per (first stripe, count bin) the occupied spans are
+        // grouped; a group's reads share the list of its widest span
+        const char* no_merge = getenv("WEPP_NO_BUCKET_MERGE");
+        const bool merge = !(no_merge && atoi(no_merge) != 0);
+        int32_t max_sp = 0;
+        for (int64_t c = 0; c < n_cells; ++c)
+            if (st_table[c]) max_sp = std::max(max_sp, (int32_t)((c / bins_per_stripe) % span_cap));
+        const int64_t tile = 32 * (int64_t)((h->opt_k == 2 || h->opt_k == 4 || h->opt_k == 8) ? h->opt_k
+                                                                                              : reads_per_lane_for_width((max_sp + 1) * q));
+        std::vector<std::pair<int32_t, int64_t>> chain;
+        std::vector<int32_t> tgt, list_of_sp((size_t)span_cap);
         for (int32_t qs = 0; qs < n_stripes; ++qs) {
             const int32_t bin0 = std::min((qs * q) / std::max(bin_size, 1), NBINS - 1);
-            for (int32_t sp = 0; sp < span_cap; ++sp) {
-                int32_t list = -1;
-                for (int32_t bb = 0; bb < bins_per_stripe; ++bb) {
-                    const size_t cell = ((size_t)qs * span_cap + sp) * bins_per_stripe + bb;
-                    const int32_t c = st_table[cell];
-                    if (c == 0) continue;
-                    if (list < 0) {
-                        list = (int32_t)pl.lists.size();
-                        pl.lists.push_back(make_list_desc(h->es, qs, qs + sp));
+            std::fill(list_of_sp.begin(), list_of_sp.begin() + std::min<int64_t>(span_cap, max_sp + 1), -1);
+            for (int32_t bb = 0; bb < bins_per_stripe; ++bb) {
+                chain.clear();
+                for (int32_t sp = 0; sp <= max_sp && sp < span_cap; ++sp) {
+                    const int32_t c = st_table[((size_t)qs * span_cap + sp) * bins_per_stripe + bb];
+                    if (c) chain.emplace_back(sp, c);
+                }
+                if (chain.empty()) continue;
+                if (merge) merge_span_chain(chain, tile, tgt);
+                else {
+                    tgt.resize(chain.size());
+                    for (size_t j = 0; j < chain.size(); ++j) tgt[j] = (int32_t)j;
+                }
+                int32_t cur_bucket = -1, cur_target = -1;
+                for (size_t j = 0; j < chain.size(); ++j) {
+                    if (tgt[j] != cur_target) {   // a new group: its bucket uses the list of the group's widest span
+                        cur_target = tgt[j];
+                        const int32_t sp_t = chain[(size_t)cur_target].first;
+                        if (list_of_sp[(size_t)sp_t] < 0) {
+                            list_of_sp[(size_t)sp_t] = (int32_t)pl.lists.size();
+                            pl.lists.push_back(make_list_desc(h->es, qs, qs + sp_t));
+                        }
+                        cur_bucket = (int32_t)pl.buckets.size();
+                        pl.buckets.push_back(BucketDesc{0, list_of_sp[(size_t)sp_t], bin0 + bb});
+                        bucket_count.push_back(0);
                     }
-                    bucket_of_cell[cell] = (int32_t)pl.buckets.size();
-                    pl.buckets.push_back(BucketDesc{0, list, bin0 + bb});
-                    bucket_count.push_back(c);
+                    bucket_of_cell[((size_t)qs * span_cap + chain[j].first) * bins_per_stripe + bb] = cur_bucket;
+                    bucket_count[(size_t)cur_bucket] += chain[j].second;
                 }
             }
         }
