@@ -409,6 +409,25 @@ __global__ void read_keys_kernel(const ReadKeyParams p) {
         if (tc[j]) atomicAdd(&p.true_counts[j], tc[j]);
 }
 
+// The occupied cells of the histogram as (cell << 32 | reads) pairs, so that the host never walks the table
+// (a few hundred of its ~10^6 cells are occupied).  counter = status[2]; pairs beyond `cap` are only counted.
+__global__ void cells_compact_kernel(const int32_t* __restrict__ table, int64_t n_cells, unsigned long long* __restrict__ pairs,
+                                     int cap, int* __restrict__ status) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n_cells; c += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t v = table[c];
+        if (v != 0) {
+            const int i = atomicAdd(&status[2], 1);
+            if (i < cap) pairs[i] = ((unsigned long long)c << 32) | (unsigned long long)(uint32_t)v;
+        }
+    }
+}
+
+// bucket_of_cell[cell] = bucket for the occupied cells ((cell << 32 | bucket) pairs from the host)
+__global__ void cells_assign_kernel(const unsigned long long* __restrict__ pairs, int n, int32_t* __restrict__ bucket_of_cell) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) bucket_of_cell[pairs[i] >> 32] = (int32_t)(uint32_t)pairs[i];
+}
+
 // cursor[b] starts at the bucket's first sorted position.  The order inside a bucket is the order
 // the atomics land in: it only decides which reads share a tile, never a result.
 __global__ void read_scatter_kernel(int64_t n_reads, const int32_t* __restrict__ cell,
@@ -1217,6 +1236,22 @@ __global__ void __launch_bounds__(64) counts_apply_kernel(int32_t* __restrict__ 
 struct BinCounts {
     int32_t v[NBINS];
 };
+// The same as a count of bins (0..50) in one byte per node: what wepp_get_node_summary moves over PCIe
+// (the host divides by bins_active: the same IEEE division, bit-identical).
+__global__ void divergence_count_kernel(const int32_t* __restrict__ counts, int n, BinCounts true_counts, double threshold,
+                                        uint8_t* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    const int32_t* row = counts + (size_t)v * NBINS;
+    int divergence = 0;
+#pragma unroll 10
+    for (int j = 0; j < NBINS; ++j) {
+        const double proportion = (double)row[j] / (double)true_counts.v[j];
+        divergence += proportion > threshold;
+    }
+    out[v] = (uint8_t)divergence;
+}
+
 __global__ void divergence_kernel(const int32_t* __restrict__ counts, int n, BinCounts true_counts, int bins_active,
                                   double threshold, double* __restrict__ out) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;

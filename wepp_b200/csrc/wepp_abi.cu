@@ -9,6 +9,7 @@
 #include <set>
 #include <unordered_map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/wepp_b200.h"
@@ -119,10 +120,13 @@ struct wepp_handle {
     DevBuf<uint8_t> d_rnuc, d_rcode;
     // device keying scratch (wepp_set_reads)
     DevBuf<int32_t> d_cell, d_table, d_bucket_of_cell;
-    DevBuf<unsigned long long> d_cursor, d_true_counts;
+    DevBuf<unsigned long long> d_cursor, d_true_counts, d_cell_pairs, d_cell_assign;
     DevBuf<int> d_key_status;
     void* h_stage = nullptr;   // pinned: key status + true counts + cell table
     size_t h_stage_cap = 0;
+    uint8_t* h_div_stage = nullptr;   // pinned: per-node divergence bin counts (wepp_get_node_summary)
+    size_t h_div_cap = 0;
+    DevBuf<uint8_t> d_div_count;
 
     struct DevPlan {
         ReadPlan plan;
@@ -474,11 +478,13 @@ void wepp_destroy(wepp_handle* h) {
     for (int g = 0; g < MAX_PEERS; ++g)
         for (int b = 0; b < 4; ++b)
             if (h->peer_ptr[g][b] && g != h->peer_rank) cudaIpcCloseMemHandle(h->peer_ptr[g][b]);
+    if (h->h_div_stage) cudaFreeHost(h->h_div_stage);
+    h->d_div_count.release();
     h->d_stripes.release(); h->d_stripe_off.release(); h->d_mapped.release(); h->d_mapped_prefix.release();
     h->full.release(); h->sub.release();
     h->d_rstart.release(); h->d_rend.release(); h->d_rdegree.release(); h->d_rpos.release(); h->d_roff.release();
     h->d_rnuc.release(); h->d_rcode.release(); h->d_cell.release(); h->d_table.release(); h->d_bucket_of_cell.release();
-    h->d_cursor.release(); h->d_true_counts.release(); h->d_key_status.release();
+    h->d_cursor.release(); h->d_true_counts.release(); h->d_key_status.release(); h->d_cell_pairs.release(); h->d_cell_assign.release();
     if (h->h_stage) cudaFreeHost(h->h_stage);
     h->d_accS.release(); h->d_accC.release(); h->d_maxpars.release(); h->d_mult.release(); h->d_score.release();
     h->d_counts.release(); h->d_divergence.release(); h->d_diff_lo.release(); h->d_diff_hi.release(); h->d_chunk128.release();
@@ -547,6 +553,16 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
     h->host_reads = false;
     cudaStream_t st = h->stream;
     const size_t n = (size_t)n_reads;
+    // WEPP_TIMING=2: phase times on stderr (development aid; adds synchronisations)
+    const bool timing = getenv("WEPP_TIMING") && atoi(getenv("WEPP_TIMING")) == 2;
+    auto t_mark = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        cudaStreamSynchronize(st);
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "[wepp_set_reads] %-34s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_mark).count());
+        t_mark = t;
+    };
 
     // ---- the reads go to the device once, as they are (caller order) ------------------------------
     CU(h->d_rstart.ensure(n)); CU(h->d_rend.ensure(n)); CU(h->d_rdegree.ensure(n)); CU(h->d_roff.ensure(n + 1));
@@ -562,6 +578,7 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
         CU(cudaMemcpyAsync(h->d_rnuc.p, rm_nuc, (size_t)nm, cudaMemcpyHostToDevice, st));
     }
 
+    lap("reads to the device");
     // ---- keying kernel: validation, allele classes, true read counts, reads per (window, bin) cell ----
     const int32_t q = h->es.stripe_width, n_stripes = h->es.n_stripes;
     const int32_t bin_size = h->genome / NBINS;
@@ -569,7 +586,8 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
     const int64_t bins_per_stripe = std::min<int64_t>(NBINS, q / std::max(bin_size, 1) + 2);
     const int64_t n_cells = (int64_t)n_stripes * span_cap * bins_per_stripe;
     const bool device_keys = n_reads > 0 && n_cells <= (int64_t)(1 << 22);   // else: host keying below
-    const size_t stage_bytes = 16 + NBINS * 8 + (device_keys ? (size_t)n_cells * 4 : 0);
+    constexpr int CELL_PAIR_CAP = 1 << 16;   // occupied histogram cells handed back as pairs (else the whole table)
+    const size_t stage_bytes = 16 + NBINS * 8 + (device_keys ? std::max((size_t)n_cells * 4, (size_t)CELL_PAIR_CAP * 8) : 0);
     if (stage_bytes > h->h_stage_cap) {
         if (h->h_stage) cudaFreeHost(h->h_stage);
         h->h_stage = nullptr;
@@ -580,6 +598,7 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
     int* st_status = reinterpret_cast<int*>(h->h_stage);
     unsigned long long* st_true = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(h->h_stage) + 16);
     int32_t* st_table = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(h->h_stage) + 16 + NBINS * 8);
+    unsigned long long* st_pairs = reinterpret_cast<unsigned long long*>(st_table);   // same area: pairs, or the table on overflow
     CU(h->d_key_status.ensure(4)); CU(h->d_true_counts.ensure(NBINS)); CU(h->d_cell.ensure(n));
     CU(h->d_table.ensure((size_t)(device_keys ? n_cells : 1)));
     CU(cudaMemsetAsync(h->d_key_status.p, 0, 4 * sizeof(int), st));
@@ -596,11 +615,18 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
         const int blocks = (int)std::min<int64_t>((n_reads + 255) / 256, (int64_t)h->n_sms * 8);
         read_keys_kernel<<<blocks, 256, 0, st>>>(kp);
         CU(cudaGetLastError());
+        if (device_keys) {
+            CU(h->d_cell_pairs.ensure(CELL_PAIR_CAP));
+            cells_compact_kernel<<<(unsigned)std::min<int64_t>((n_cells + 255) / 256, (int64_t)h->n_sms * 8), 256, 0, st>>>(
+                h->d_table.p, n_cells, h->d_cell_pairs.p, CELL_PAIR_CAP, h->d_key_status.p);
+            CU(cudaGetLastError());
+        }
     }
     CU(cudaMemcpyAsync(st_status, h->d_key_status.p, 16, cudaMemcpyDeviceToHost, st));
     CU(cudaMemcpyAsync(st_true, h->d_true_counts.p, NBINS * 8, cudaMemcpyDeviceToHost, st));
-    if (device_keys) CU(cudaMemcpyAsync(st_table, h->d_table.p, (size_t)n_cells * 4, cudaMemcpyDeviceToHost, st));
+    if (device_keys) CU(cudaMemcpyAsync(st_pairs, h->d_cell_pairs.p, (size_t)CELL_PAIR_CAP * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));   // also: the caller's buffers are consumed from here on
+    lap("keying kernel + histogram out");
     if (st_status[0] != RP_OK) return fail(WEPP_E_INVALID, read_plan_error(st_status[0]));
     h->n_reads = n_reads;
     h->n_read_muts = nm;
@@ -612,28 +638,44 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
         pl = ReadPlan();
         pl.n_reads = n_reads;
         pl.n_read_muts = nm;
-        std::vector<int32_t> bucket_of_cell((size_t)n_cells, -1);
+        // the occupied cells, ascending (= by first stripe, then span, then bin)
+        std::vector<unsigned long long> occ;
+        if (st_status[2] <= CELL_PAIR_CAP) {
+            occ.assign(st_pairs, st_pairs + st_status[2]);
+        } else {   // more occupied cells than pairs fit: fetch the table itself
+            CU(cudaMemcpyAsync(st_table, h->d_table.p, (size_t)n_cells * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (int64_t c = 0; c < n_cells; ++c)
+                if (st_table[c]) occ.push_back(((unsigned long long)c << 32) | (unsigned long long)(uint32_t)st_table[c]);
+        }
+        std::sort(occ.begin(), occ.end());
+        std::vector<unsigned long long> assign;   // (cell << 32 | bucket)
+        assign.reserve(occ.size());
         std::vector<int64_t> bucket_count;
         // bucket coarsening (merge_span_chain, host_prep.h): per (first stripe, count bin) the occupied spans are
         // grouped; a group's reads share the list of its widest span
         const char* no_merge = getenv("WEPP_NO_BUCKET_MERGE");
         const bool merge = !(no_merge && atoi(no_merge) != 0);
+        const int64_t cells_per_qs = span_cap * bins_per_stripe;
         int32_t max_sp = 0;
-        for (int64_t c = 0; c < n_cells; ++c)
-            if (st_table[c]) max_sp = std::max(max_sp, (int32_t)((c / bins_per_stripe) % span_cap));
+        for (unsigned long long pr : occ) max_sp = std::max(max_sp, (int32_t)(((int64_t)(pr >> 32) % cells_per_qs) / bins_per_stripe));
         const int64_t tile = 32 * (int64_t)((h->opt_k == 2 || h->opt_k == 4 || h->opt_k == 8) ? h->opt_k
                                                                                               : reads_per_lane_for_width((max_sp + 1) * q));
-        std::vector<std::pair<int32_t, int64_t>> chain;
-        std::vector<int32_t> tgt, list_of_sp((size_t)span_cap);
-        for (int32_t qs = 0; qs < n_stripes; ++qs) {
+        std::vector<std::vector<std::pair<int32_t, int64_t>>> chains((size_t)bins_per_stripe);
+        std::vector<int32_t> tgt;
+        std::vector<std::pair<int32_t, int32_t>> lists_here;   // (span, list) of the current first stripe
+        for (size_t a0 = 0; a0 < occ.size();) {
+            const int32_t qs = (int32_t)((int64_t)(occ[a0] >> 32) / cells_per_qs);
             const int32_t bin0 = std::min((qs * q) / std::max(bin_size, 1), NBINS - 1);
-            std::fill(list_of_sp.begin(), list_of_sp.begin() + std::min<int64_t>(span_cap, max_sp + 1), -1);
+            for (auto& ch : chains) ch.clear();
+            size_t a1 = a0;
+            for (; a1 < occ.size() && (int32_t)((int64_t)(occ[a1] >> 32) / cells_per_qs) == qs; ++a1) {
+                const int64_t in_qs = (int64_t)(occ[a1] >> 32) % cells_per_qs;
+                chains[(size_t)(in_qs % bins_per_stripe)].emplace_back((int32_t)(in_qs / bins_per_stripe), (int64_t)(uint32_t)occ[a1]);
+            }
+            lists_here.clear();
             for (int32_t bb = 0; bb < bins_per_stripe; ++bb) {
-                chain.clear();
-                for (int32_t sp = 0; sp <= max_sp && sp < span_cap; ++sp) {
-                    const int32_t c = st_table[((size_t)qs * span_cap + sp) * bins_per_stripe + bb];
-                    if (c) chain.emplace_back(sp, c);
-                }
+                const auto& chain = chains[(size_t)bb];
                 if (chain.empty()) continue;
                 if (merge) merge_span_chain(chain, tile, tgt);
                 else {
@@ -645,24 +687,37 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
                     if (tgt[j] != cur_target) {   // a new group: its bucket uses the list of the group's widest span
                         cur_target = tgt[j];
                         const int32_t sp_t = chain[(size_t)cur_target].first;
-                        if (list_of_sp[(size_t)sp_t] < 0) {
-                            list_of_sp[(size_t)sp_t] = (int32_t)pl.lists.size();
+                        int32_t list = -1;
+                        for (const auto& lh : lists_here)
+                            if (lh.first == sp_t) list = lh.second;
+                        if (list < 0) {
+                            list = (int32_t)pl.lists.size();
+                            lists_here.emplace_back(sp_t, list);
                             pl.lists.push_back(make_list_desc(h->es, qs, qs + sp_t));
                         }
                         cur_bucket = (int32_t)pl.buckets.size();
-                        pl.buckets.push_back(BucketDesc{0, list_of_sp[(size_t)sp_t], bin0 + bb});
+                        pl.buckets.push_back(BucketDesc{0, list, bin0 + bb});
                         bucket_count.push_back(0);
                     }
-                    bucket_of_cell[((size_t)qs * span_cap + chain[j].first) * bins_per_stripe + bb] = cur_bucket;
+                    const int64_t cell = ((int64_t)qs * span_cap + chain[j].first) * bins_per_stripe + bb;
+                    assign.push_back(((unsigned long long)cell << 32) | (unsigned long long)(uint32_t)cur_bucket);
                     bucket_count[(size_t)cur_bucket] += chain[j].second;
                 }
             }
+            a0 = a1;
         }
         std::vector<int64_t> first;
         std::string err = finish_read_plan(h->es, h->opt_k, bucket_count, pl, first);
         if (!err.empty()) return fail(WEPP_E_INVALID, err);
+        lap("descriptors (host)");
         std::vector<unsigned long long> cursor(first.begin(), first.end());
-        CU(upload(h->d_bucket_of_cell, bucket_of_cell, st));
+        CU(h->d_bucket_of_cell.ensure((size_t)n_cells));   // only the occupied cells are ever read
+        CU(upload(h->d_cell_assign, assign, st));
+        if (!assign.empty()) {
+            cells_assign_kernel<<<(unsigned)((assign.size() + 255) / 256), 256, 0, st>>>(h->d_cell_assign.p, (int)assign.size(),
+                                                                                        h->d_bucket_of_cell.p);
+            CU(cudaGetLastError());
+        }
         CU(upload(h->d_cursor, cursor, st));
         CU(h->full.perm.ensure(n));
         const int blocks = (int)std::min<int64_t>((n_reads + 255) / 256, (int64_t)h->n_sms * 8);
@@ -677,8 +732,10 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
         host_perm = true;
     }
     for (int j = 0; j < NBINS; ++j) h->true_counts[j] = (int32_t)st_true[j];
+    lap("scatter into bucket order");
     int rc = upload_plan(h, h->full, host_perm);
     if (rc) return rc;
+    lap("descriptors up + Euler lists");
     h->has_reads = true;
     return WEPP_OK;
 }
@@ -763,18 +820,47 @@ int wepp_get_node_summary(wepp_handle* h, double* score, double* dist_divergence
         CU(cudaStreamSynchronize(h->stream));
         return WEPP_OK;
     }
-    if (dist_divergence) {
-        CU(h->d_divergence.ensure((size_t)n));
+    if (dist_divergence && n > 0) {
+        // dist_divergence = (bins over the threshold) / (bins with reads): the device counts the bins into one byte
+        // per node, only those bytes cross PCIe (1 instead of 8 per node), and host threads do the division while
+        // the score array is still in flight — the same IEEE division as on the device, bit for bit.
+        CU(h->d_div_count.ensure((size_t)n));
+        if ((size_t)n > h->h_div_cap) {
+            if (h->h_div_stage) cudaFreeHost(h->h_div_stage);
+            h->h_div_stage = nullptr;
+            h->h_div_cap = 0;
+            CU(cudaMallocHost(&h->h_div_stage, (size_t)n));
+            h->h_div_cap = (size_t)n;
+        }
         BinCounts tc;
         int active = 0;
         for (int j = 0; j < NBINS; ++j) {
             tc.v[j] = h->true_counts[j];
             active += tc.v[j] != 0;
         }
-        divergence_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_counts.p, n, tc, active, 0.5 / 100,
-                                                                  h->d_divergence.p);
+        divergence_count_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_counts.p, n, tc, 0.5 / 100, h->d_div_count.p);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(dist_divergence, h->d_divergence.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(h->h_div_stage, h->d_div_count.p, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventRecord(h->ev[3], h->stream));
+        if (score) CU(cudaMemcpyAsync(score, h->d_score.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaEventSynchronize(h->ev[3]));
+        double table[NBINS + 1];
+        for (int k = 0; k <= NBINS; ++k) table[k] = (double)k / (double)active;
+        const uint8_t* src = h->h_div_stage;
+        const int n_thr = (int)std::max(1u, std::min(16u, std::min(std::thread::hardware_concurrency(), (unsigned)(n / 65536 + 1))));
+        auto expand = [&](int t) {
+            const int64_t a = (int64_t)n * t / n_thr, b = (int64_t)n * (t + 1) / n_thr;
+            for (int64_t v = a; v < b; ++v) dist_divergence[v] = table[src[v]];
+        };
+        if (n_thr == 1) {
+            expand(0);
+        } else {
+            std::vector<std::thread> pool;
+            for (int t = 0; t < n_thr; ++t) pool.emplace_back(expand, t);
+            for (auto& th : pool) th.join();
+        }
+        CU(cudaStreamSynchronize(h->stream));
+        return WEPP_OK;
     }
     if (score) CU(cudaMemcpyAsync(score, h->d_score.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
