@@ -1288,6 +1288,7 @@ int rescore_resident(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, 
     lap("candidate stacks (host)");
     const int n_lists = (int)pl.lists.size();
     const int64_t n_lc = (int64_t)n_lists * n_cand;
+    if (n_lc + 1 > 0x7FFFFFFFll) return fail(WEPP_E_INVALID, "too many (window list, candidate) pairs: split the candidate set");
     // capacity of the entry buffer: one entry per (list, candidate) + every stack mutation once per list covering it
     int64_t cap = n_lc;
     {
