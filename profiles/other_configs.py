@@ -20,8 +20,8 @@ def main():
     name = sys.argv[1] if len(sys.argv) > 1 else "C4"
     rscale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
     g = 29903
-    n = {"C2": 1_000_000, "C4": 8_000_000, "MID": 8_000_000, "FRAG": 8_000_000}[name]
-    r = int({"C2": 1_000_000, "C4": 1_000_000, "MID": 1_000_000, "FRAG": 1_000_000}[name] * rscale)
+    n = {"C2": 1_000_000, "C3": 8_000_000, "C4": 8_000_000, "MID": 8_000_000, "FRAG": 8_000_000}[name]
+    r = int({"C2": 1_000_000, "C3": 10_000_000, "C4": 1_000_000, "MID": 1_000_000, "FRAG": 1_000_000}[name] * rscale)
     arena = synth.make_arena(n, g, synth.SEED)
     if name == "C4":
         reads = synth.make_reads(arena, r, synth.SEED, amplicons=synth.amplicon_scheme(g, 29, 1058, 1201, synth.SEED),

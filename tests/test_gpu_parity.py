@@ -276,6 +276,8 @@ def test_rescore_tile_kernel_matches_oracle(name, q, k, n_cand):
     assert np.array_equal(md2, omd2) and np.array_equal(off2, ooff2) and np.array_equal(idx2, oidx2)
     md3, _, _, _ = p.rescore(cand, want_argmin=False)
     assert np.array_equal(md3, omd)
+    md4, _, off4, _ = p.rescore(cand, want_argmin="count")   # compact entry lists: empty candidates evaluated in bulk
+    assert np.array_equal(md4, omd) and np.array_equal(off4, ooff)
     p.close()
 
 
@@ -292,6 +294,8 @@ def test_rescore_tile_and_generic_kernels_agree_at_size():
     md, _, off, idx = p.rescore(cand)
     gmd, _, goff, gidx = p.rescore_reads(reads, cand)
     assert np.array_equal(md, gmd) and np.array_equal(off, goff) and np.array_equal(idx, gidx)
+    md2, _, off2, _ = p.rescore(cand, want_argmin="count")
+    assert np.array_equal(md2, gmd) and np.array_equal(off2, goff)
     p.close()
 
 

@@ -58,7 +58,7 @@ struct RescoreTileParams {
 // entries of (list, candidate): its stack mutations inside the list's window, at least one
 __global__ void cand_count_kernel(const ListDesc* __restrict__ ld, int n_lists, int n_cand,
                                   const int64_t* __restrict__ st_off, const int32_t* __restrict__ st_pos,
-                                  int64_t* __restrict__ cnt) {
+                                  int64_t* __restrict__ cnt, int min_one) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t n = (int64_t)n_lists * n_cand;
     if (i > n) return;
@@ -80,7 +80,7 @@ __global__ void cand_count_kernel(const ListDesc* __restrict__ ld, int n_lists, 
         const int64_t mid = (lo + hi) >> 1;
         if (st_pos[mid] < b1) lo = mid + 1; else hi = mid;
     }
-    cnt[i] = max(lo - first, (int64_t)1);
+    cnt[i] = max(lo - first, (int64_t)min_one);   // min_one = 0: candidates with nothing in the window get no entry
 }
 
 __global__ void cand_fill_kernel(const ListDesc* __restrict__ ld, int n_lists, int n_cand,
@@ -98,6 +98,7 @@ __global__ void cand_fill_kernel(const ListDesc* __restrict__ ld, int n_lists, i
         if (st_pos[mid] < b0) lo = mid + 1; else hi = mid;
     }
     const int64_t o = coff[i], n = coff[i + 1] - o;
+    if (n == 0) return;   // compact lists (min / count only): the kernel evaluates such candidates in bulk
     if (lo == b || st_pos[lo] >= b0 + ld[l].width) {   // nothing in the window: one zero entry
         out[o] = Entry{(uint32_t)c | RT_END, 0u, 0u, 0u};
         return;
@@ -113,6 +114,108 @@ __global__ void cand_fill_kernel(const ListDesc* __restrict__ ld, int n_lists, i
         e.w = (nuc == 8u ? 0xFFu : 0u) | ((uint32_t)(st_pos[lo + k] - b0) << 16);
         out[o + k] = e;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Candidate stack_muts on the device (haplotype::stack_muts, arena.cpp:18-46: the last event per position on the
+// root path, kept when it differs from the reference allele, sorted by position).  One warp per candidate walks
+// from the node up to the root; a per-warp bitmap over the genome in shared memory records the positions already
+// decided by a deeper event, kept (position, allele) pairs are collected in shared memory and bitonic-sorted.
+// The root-path walk is a chain of dependent loads — ~0.1 ms for hundreds of candidates at once here, against
+// ~1 ms of cache misses on the host.  Candidates with more than SB_CAP kept mutations report -1 (host builds those).
+constexpr int SB_CAP = 1024;
+constexpr int SB_WARPS = 4;
+constexpr int SB_MAX_GENOME = 65536 * 2;   // bitmap words are sized by the launch; this bounds the shared memory
+
+struct StackBuildParams {
+    const int32_t* parent;
+    const int64_t* mut_off;
+    const int32_t* mut_pos;
+    const uint8_t* mut_ref;
+    const uint8_t* mut_nuc;
+    const int32_t* nodes;
+    int32_t n, bitmap_words;
+    uint32_t* out;      // [n][SB_CAP]: position << 4 | allele, ascending
+    int32_t* count;     // [n]
+};
+
+__global__ void __launch_bounds__(SB_WARPS * 32) cand_stack_kernel(const StackBuildParams p) {
+    extern __shared__ __align__(16) uint32_t sb_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * SB_WARPS + warp;
+    if (c >= p.n) return;   // whole warps only: no block-wide barrier below
+    uint32_t* bitmap = sb_smem + (size_t)warp * (p.bitmap_words + SB_CAP);
+    uint32_t* buf = bitmap + p.bitmap_words;
+    const unsigned FULL = 0xFFFFFFFFu;
+    for (int i = lane; i < p.bitmap_words; i += 32) bitmap[i] = 0u;
+    __syncwarp();
+    int cnt = 0;
+    for (int32_t v = p.nodes[c]; v >= 0; v = p.parent[v]) {
+        const int64_t a = p.mut_off[v], b = p.mut_off[v + 1];
+        for (int64_t k0 = a; k0 < b; k0 += 32) {
+            const int64_t k = k0 + lane;
+            bool keep = false;
+            uint32_t packed = 0;
+            if (k < b) {
+                const uint32_t pos = (uint32_t)p.mut_pos[k];
+                const uint32_t bit = 1u << (pos & 31u);
+                const uint32_t old = atomicOr(&bitmap[pos >> 5], bit);   // a node has at most one event per position
+                const uint32_t nuc = p.mut_nuc[k];
+                keep = !(old & bit) && p.mut_ref[k] != nuc;
+                packed = (pos << 4) | nuc;
+            }
+            const uint32_t m = __ballot_sync(FULL, keep);
+            const int idx = cnt + __popc(m & ((1u << lane) - 1u));
+            if (keep && idx < SB_CAP) buf[idx] = packed;
+            cnt += __popc(m);
+        }
+        __syncwarp();
+    }
+    if (cnt > SB_CAP) {
+        if (lane == 0) p.count[c] = -1;
+        return;
+    }
+    int size = 32;
+    while (size < cnt) size <<= 1;
+    for (int i = cnt + lane; i < size; i += 32) buf[i] = 0xFFFFFFFFu;
+    __syncwarp();
+    for (int k = 2; k <= size; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = lane; i < size; i += 32) {
+                const int partner = i ^ j;
+                if (partner > i) {
+                    const uint32_t x = buf[i], y = buf[partner];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) {
+                        buf[i] = y;
+                        buf[partner] = x;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    uint32_t* dst = p.out + (size_t)c * SB_CAP;
+    for (int i = lane; i < cnt; i += 32) dst[i] = buf[i];
+    if (lane == 0) p.count[c] = cnt;
+}
+
+// scratch rows -> CSR arrays (offsets from an exclusive scan of the counts, overflowed candidates count 0)
+__global__ void cand_stack_compact_kernel(const uint32_t* __restrict__ rows, const int32_t* __restrict__ count,
+                                          const int64_t* __restrict__ off, int n, int32_t* __restrict__ pos,
+                                          uint8_t* __restrict__ nuc) {
+    const int c = blockIdx.x;
+    if (c >= n) return;
+    const int m = max(count[c], 0);
+    const uint32_t* src = rows + (size_t)c * SB_CAP;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        pos[off[c] + i] = (int32_t)(src[i] >> 4);
+        nuc[off[c] + i] = (uint8_t)(src[i] & 15u);
+    }
+}
+
+__global__ void clamp_counts_kernel(const int32_t* __restrict__ count, int n, int64_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) out[i] = i < n ? (int64_t)max(count[i], 0) : 0;
 }
 
 template <int K, int MODE>
@@ -215,11 +318,13 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) rescore_tile_kernel(const
         }
     }
 
+    int n_end = 0;   // candidates with an entry run in this warp's range (mode 0)
     uint4 nxt = make_uint4(0, 0, 0, 0);
     if (c0 + lane < c1) nxt = ld_entry(ent + c0 + lane);
     for (int64_t base = c0; base < c1; base += 32) {
         sts128(ebuf_s + lane * 16, nxt);
         const uint32_t em = __ballot_sync(FULL, (nxt.x & RT_END) != 0u);
+        n_end += __popc(em);
         __syncwarp();
         nxt = make_uint4(0, 0, 0, 0);   // zero entries pad the tail: no delta, no RT_END
         if (base + 32 + lane < c1) nxt = ld_entry(ent + base + 32 + lane);
@@ -263,6 +368,9 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) rescore_tile_kernel(const
         __syncwarp();
     }
     if constexpr (MODE == 0) {
+    // compact lists: the candidates of this warp's range without an entry have no stack mutation in the window,
+    // so their distance is the read's own k: one evaluation for all of them
+    if (cw1 - cw0 - n_end > 0) st.eval(S0, cw1 - cw0 - n_end);
 
     // ---- fold the warps' (min, count) ------------------------------------------------------------------
 #pragma unroll

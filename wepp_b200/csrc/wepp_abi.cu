@@ -50,6 +50,10 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }   // wepp_destroy selects the device before the handle goes
     cudaError_t ensure(size_t n) {
         if (n <= cap) return cudaSuccess;
         // a buffer that has to grow again gets 25 % headroom: sizes that creep up call after call (candidate
@@ -175,6 +179,12 @@ struct wepp_handle {
     DevBuf<int32_t> d_st_pos, d_rs_min, d_rs_nbest, d_rs_before, d_rs_dist, d_am_idx;
     DevBuf<uint8_t> d_st_nuc, d_cub_tmp;
     DevBuf<Entry> d_cent;
+    // the tree on the device for the candidates' root-path walks (cand_stack_kernel); uploaded on first use
+    bool tree_on_device = false;
+    DevBuf<int32_t> d_parent, d_mut_pos, d_sb_nodes, d_sb_count, d_sb_pos;
+    DevBuf<int64_t> d_mut_off, d_sb_cnt64, d_sb_off;
+    DevBuf<uint8_t> d_mut_ref, d_mut_nuc, d_sb_nuc;
+    DevBuf<uint32_t> d_sb_rows;
     // candidate stack_muts by node, kept across calls (the iterative loops re-score mostly the same candidates)
     std::unordered_map<int32_t, std::pair<int64_t, int32_t>> st_cache;
     std::vector<int32_t> st_cache_pos;
@@ -531,6 +541,7 @@ int wepp_set_arena(wepp_handle* h, int32_t n_nodes, const int32_t* parent, const
     h->has_mask = false;
     h->has_results = false;
     h->rank_tab_d = 0;
+    h->tree_on_device = false;
     h->st_cache.clear();
     h->st_cache_pos.clear();
     h->st_cache_nuc.clear();
@@ -1262,7 +1273,62 @@ int rescore_resident(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, 
             std::vector<int64_t> m_off;
             std::vector<int32_t> m_pos;
             std::vector<uint8_t> m_nuc;
-            if (!build_candidate_stacks(h->n_nodes, h->genome, h->parent.data(), h->mut_off.data(), h->mut_pos.data(),
+            bool on_device = false;
+            const int bitmap_words = (h->genome + 1 + 31) / 32;
+            const size_t sb_smem = (size_t)SB_WARPS * ((size_t)bitmap_words + SB_CAP) * 4;
+            static const bool host_stacks = getenv("WEPP_HOST_STACKS") && atoi(getenv("WEPP_HOST_STACKS")) != 0;
+            if (!host_stacks && missing.size() >= 16 && sb_smem <= 48 * 1024) {
+                // root-path walks on the device (cand_stack_kernel); the tree arrays go up on first use
+                const int nmiss = (int)missing.size();
+                if (!h->tree_on_device) {
+                    CU(upload(h->d_parent, h->parent, h->stream));
+                    CU(upload(h->d_mut_off, h->mut_off, h->stream));
+                    CU(upload(h->d_mut_pos, h->mut_pos, h->stream));
+                    CU(upload(h->d_mut_ref, h->mut_ref, h->stream));
+                    CU(upload(h->d_mut_nuc, h->mut_nuc, h->stream));
+                    h->tree_on_device = true;
+                }
+                CU(upload(h->d_sb_nodes, missing, h->stream));
+                CU(h->d_sb_rows.ensure((size_t)nmiss * SB_CAP));
+                CU(h->d_sb_count.ensure((size_t)nmiss));
+                CU(h->d_sb_cnt64.ensure((size_t)nmiss + 1));
+                CU(h->d_sb_off.ensure((size_t)nmiss + 1));
+                StackBuildParams sp = {};
+                sp.parent = h->d_parent.p; sp.mut_off = h->d_mut_off.p; sp.mut_pos = h->d_mut_pos.p;
+                sp.mut_ref = h->d_mut_ref.p; sp.mut_nuc = h->d_mut_nuc.p; sp.nodes = h->d_sb_nodes.p;
+                sp.n = nmiss; sp.bitmap_words = bitmap_words; sp.out = h->d_sb_rows.p; sp.count = h->d_sb_count.p;
+                cand_stack_kernel<<<(nmiss + SB_WARPS - 1) / SB_WARPS, SB_WARPS * 32, sb_smem, h->stream>>>(sp);
+                CU(cudaGetLastError());
+                clamp_counts_kernel<<<(nmiss + 1 + 255) / 256, 256, 0, h->stream>>>(h->d_sb_count.p, nmiss, h->d_sb_cnt64.p);
+                CU(cudaGetLastError());
+                size_t tmp_bytes = 0;
+                CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_sb_cnt64.p, h->d_sb_off.p, nmiss + 1, h->stream));
+                CU(h->d_cub_tmp.ensure(tmp_bytes));
+                CU(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp_bytes, h->d_sb_cnt64.p, h->d_sb_off.p, nmiss + 1, h->stream));
+                std::vector<int32_t> cnt((size_t)nmiss);
+                m_off.resize((size_t)nmiss + 1);
+                CU(cudaMemcpyAsync(cnt.data(), h->d_sb_count.p, (size_t)nmiss * 4, cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaMemcpyAsync(m_off.data(), h->d_sb_off.p, ((size_t)nmiss + 1) * 8, cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+                on_device = std::find(cnt.begin(), cnt.end(), -1) == cnt.end();   // a stack over SB_CAP: the host builds them all
+                if (on_device) {
+                    const size_t total = (size_t)m_off[(size_t)nmiss];
+                    m_pos.resize(total);
+                    m_nuc.resize(total);
+                    if (total) {
+                        CU(h->d_sb_pos.ensure(total));
+                        CU(h->d_sb_nuc.ensure(total));
+                        cand_stack_compact_kernel<<<nmiss, 64, 0, h->stream>>>(h->d_sb_rows.p, h->d_sb_count.p, h->d_sb_off.p, nmiss,
+                                                                              h->d_sb_pos.p, h->d_sb_nuc.p);
+                        CU(cudaGetLastError());
+                        CU(cudaMemcpyAsync(m_pos.data(), h->d_sb_pos.p, total * 4, cudaMemcpyDeviceToHost, h->stream));
+                        CU(cudaMemcpyAsync(m_nuc.data(), h->d_sb_nuc.p, total, cudaMemcpyDeviceToHost, h->stream));
+                        CU(cudaStreamSynchronize(h->stream));
+                    }
+                }
+            }
+            if (!on_device &&
+                !build_candidate_stacks(h->n_nodes, h->genome, h->parent.data(), h->mut_off.data(), h->mut_pos.data(),
                                         h->mut_ref.data(), h->mut_nuc.data(), (int32_t)missing.size(), missing.data(), m_off,
                                         m_pos, m_nuc, err))
                 return fail(WEPP_E_INVALID, err);
@@ -1311,7 +1377,10 @@ int rescore_resident(wepp_handle* h, int32_t n_cand, const int32_t* cand_nodes, 
     CU(h->d_rs_before.ensure((size_t)R * PLACE_WARPS));
     if (dist) CU(h->d_rs_dist.ensure((size_t)R * (size_t)n_cand));
     const unsigned blocks = (unsigned)((n_lc + 1 + 255) / 256);
-    cand_count_kernel<<<blocks, 256, 0, h->stream>>>(dp.lists.p, n_lists, n_cand, h->d_st_off.p, h->d_st_pos.p, h->d_ccnt.p);
+    // min / count only: candidates with nothing in a window are evaluated in bulk and get no entry there; the dense
+    // matrix and the argmin lists need every candidate's own evaluation
+    const int min_one = (dist || (am_off && am_idx)) ? 1 : 0;
+    cand_count_kernel<<<blocks, 256, 0, h->stream>>>(dp.lists.p, n_lists, n_cand, h->d_st_off.p, h->d_st_pos.p, h->d_ccnt.p, min_one);
     CU(cudaGetLastError());
     size_t tmp_bytes = 0;
     CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, h->d_ccnt.p, h->d_coff.p, (int)(n_lc + 1), h->stream));

@@ -136,15 +136,18 @@ class Placer:
         self.n_reads = int(n)
         return mp, mu, sc, ct
 
-    def rescore(self, cand_nodes, want_dist: bool = False, want_argmin: bool = True):
+    def rescore(self, cand_nodes, want_dist: bool = False, want_argmin=True):
+        """wepp_rescore over the resident reads.  want_argmin: True = CSR argmin lists, "count" = only their
+        offsets (am_off; the number of argmins per read), False = min distance only."""
         cand = _c(cand_nodes, np.int32)
         md = np.empty(self.n_reads, np.int32)
         dist = np.empty((self.n_reads, cand.shape[0]), np.int32) if want_dist else None
         off = np.empty(self.n_reads + 1, np.int64) if want_argmin else None
-        cap = self.n_reads * cand.shape[0] if want_argmin else 0
-        idx = np.empty(max(cap, 1), np.int32) if want_argmin else None
+        lists = want_argmin is True
+        cap = self.n_reads * cand.shape[0] if lists else 0
+        idx = np.empty(max(cap, 1), np.int32) if lists else None
         check(self.lib.wepp_rescore(self.h, cand.shape[0], ptr(cand), ptr(md), ptr(dist), ptr(off), ptr(idx), cap))
-        if want_argmin:
+        if lists:
             idx = idx[: int(off[-1])]
         return md, dist, off, idx
 
