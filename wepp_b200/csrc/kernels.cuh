@@ -1272,8 +1272,8 @@ __global__ void divergence_kernel(const int32_t* __restrict__ counts, int n, Bin
 // Every rank owns a slice of the nodes.  For its slice it loads the per-node read counts and
 // scores of ALL ranks straight from their HBM (peer pointers opened with CUDA IPC), sums them,
 // keeps the merged counts in its own counts slice, evaluates dist_divergence from the merged rows
-// while they are in shared memory, and stores the merged score and dist_divergence of the slice
-// into every rank's output arrays.  Per rank: (W-1)/W x N x 208 B in over NVLink, N/W x 16 B x W out
+// while they are in shared memory, and stores the merged score and dist_divergence (as its bin count, one
+// byte) of the slice into every rank's output arrays.  Per rank: (W-1)/W x N x 208 B in over NVLink, N/W x 9 B x W out
 // — against 2 x (W-1)/W x N x 208 B each way for a ring all-reduce of the same arrays — and the
 // counts matrix never makes the second (all-gather) trip, because nothing reads it after the
 // divergence is known.  Ranks synchronise around the kernel with a stream-ordered barrier
@@ -1287,7 +1287,7 @@ struct PeerMergeParams {
     const int32_t* counts_in[MAX_PEERS];     // every rank's scanned counts[N][50]
     const double* score_in[MAX_PEERS];       // every rank's score[N]
     double* score_out[MAX_PEERS];            // every rank's merged score[N]
-    double* div_out[MAX_PEERS];              // every rank's dist_divergence[N]
+    uint8_t* div_out[MAX_PEERS];             // every rank's dist_divergence[N] as the count of bins over the threshold
     int32_t* counts_own;                     // this rank's counts: the slice is overwritten with the merged rows
     BinCounts true_counts;                   // degree-weighted reads per bin over ALL ranks (arena.cpp:138-151)
     int32_t bins_active;
@@ -1355,7 +1355,6 @@ __global__ void __launch_bounds__(PM_THREADS) peer_merge_kernel(const PeerMergeP
                 const double proportion = (double)row[j] / (double)p.true_counts.v[j];   // as divergence_kernel
                 divergence += proportion > p.threshold;
             }
-            const double dv = (double)divergence / (double)p.bins_active;
             double sc = 0.0;   // fixed rank order: every rank receives the same bits
 #pragma unroll
             for (int g = 0; g < MAX_PEERS; ++g)
@@ -1364,7 +1363,7 @@ __global__ void __launch_bounds__(PM_THREADS) peer_merge_kernel(const PeerMergeP
             for (int g = 0; g < MAX_PEERS; ++g)
                 if (g < p.world) {
                     p.score_out[g][v] = sc;
-                    p.div_out[g][v] = dv;
+                    p.div_out[g][v] = (uint8_t)divergence;   // wepp_get_node_summary divides by the bins with reads
                 }
         }
         __syncthreads();

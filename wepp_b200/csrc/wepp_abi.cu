@@ -172,7 +172,7 @@ struct wepp_handle {
     void* peer_ptr[MAX_PEERS][4] = {};
     int32_t peer_rank = -1, peer_world = 0;
     int64_t peer_true_counts[NBINS] = {};
-    bool peer_merged = false;   // d_score_merged / d_divergence hold the merged results of the last place
+    bool peer_merged = false;   // d_score_merged / d_div_count hold the merged results of the last place
 
     // K4 over the resident reads (rescore_tiles.cuh): candidate stacks, per-window candidate entries, results
     DevBuf<int64_t> d_st_off, d_ccnt, d_coff, d_am_off;
@@ -825,12 +825,8 @@ int wepp_get_node_summary(wepp_handle* h, double* score, double* dist_divergence
     if (!h->has_results || !h->d_score.p) return fail(WEPP_E_STATE, "no per-node results yet (call wepp_place)");
     CU(cudaSetDevice(h->device));
     const int n = h->n_nodes;
-    if (h->peer_merged) {   // wepp_peer_merge already evaluated both over all ranks
-        if (dist_divergence) CU(cudaMemcpyAsync(dist_divergence, h->d_divergence.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        if (score) CU(cudaMemcpyAsync(score, h->d_score_merged.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        return WEPP_OK;
-    }
+    const bool merged = h->peer_merged;   // wepp_peer_merge already evaluated both over all ranks
+    const double* d_score_src = merged ? h->d_score_merged.p : h->d_score.p;
     if (dist_divergence && n > 0) {
         // dist_divergence = (bins over the threshold) / (bins with reads): the device counts the bins into one byte
         // per node, only those bytes cross PCIe (1 instead of 8 per node), and host threads do the division while
@@ -846,14 +842,16 @@ int wepp_get_node_summary(wepp_handle* h, double* score, double* dist_divergence
         BinCounts tc;
         int active = 0;
         for (int j = 0; j < NBINS; ++j) {
-            tc.v[j] = h->true_counts[j];
+            tc.v[j] = merged ? (int32_t)h->peer_true_counts[j] : h->true_counts[j];
             active += tc.v[j] != 0;
         }
-        divergence_count_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_counts.p, n, tc, 0.5 / 100, h->d_div_count.p);
-        CU(cudaGetLastError());
+        if (!merged) {
+            divergence_count_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_counts.p, n, tc, 0.5 / 100, h->d_div_count.p);
+            CU(cudaGetLastError());
+        }
         CU(cudaMemcpyAsync(h->h_div_stage, h->d_div_count.p, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
         CU(cudaEventRecord(h->ev[3], h->stream));
-        if (score) CU(cudaMemcpyAsync(score, h->d_score.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        if (score) CU(cudaMemcpyAsync(score, d_score_src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaEventSynchronize(h->ev[3]));
         double table[NBINS + 1];
         for (int k = 0; k <= NBINS; ++k) table[k] = (double)k / (double)active;
@@ -873,7 +871,7 @@ int wepp_get_node_summary(wepp_handle* h, double* score, double* dist_divergence
         CU(cudaStreamSynchronize(h->stream));
         return WEPP_OK;
     }
-    if (score) CU(cudaMemcpyAsync(score, h->d_score.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (score) CU(cudaMemcpyAsync(score, d_score_src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     return WEPP_OK;
 }
@@ -973,12 +971,12 @@ int wepp_peer_export(wepp_handle* h, void* blob) {
     CU(h->d_score.ensure(n));
     CU(h->d_counts.ensure((n + 1) * NBINS));
     CU(h->d_score_merged.ensure(n));
-    CU(h->d_divergence.ensure(n));
+    CU(h->d_div_count.ensure(n));
     PeerBlob pb = {};
     CU(cudaIpcGetMemHandle(&pb.mem[0], h->d_score.p));
     CU(cudaIpcGetMemHandle(&pb.mem[1], h->d_counts.p));
     CU(cudaIpcGetMemHandle(&pb.mem[2], h->d_score_merged.p));
-    CU(cudaIpcGetMemHandle(&pb.mem[3], h->d_divergence.p));
+    CU(cudaIpcGetMemHandle(&pb.mem[3], h->d_div_count.p));
     for (int j = 0; j < NBINS; ++j) pb.true_counts[j] = h->true_counts[j];
     pb.n_nodes = h->n_nodes;
     std::memcpy(blob, &pb, sizeof(pb));
@@ -988,7 +986,7 @@ int wepp_peer_export(wepp_handle* h, void* blob) {
 int wepp_peer_open(wepp_handle* h, int32_t rank, int32_t world, const void* blobs) {
     if (!h || !blobs) return fail(WEPP_E_INVALID, "NULL argument");
     if (world < 1 || world > MAX_PEERS || rank < 0 || rank >= world) return fail(WEPP_E_INVALID, "bad rank / world (at most 8 ranks)");
-    if (!h->d_score.p || !h->d_counts.p || !h->d_score_merged.p || !h->d_divergence.p)
+    if (!h->d_score.p || !h->d_counts.p || !h->d_score_merged.p || !h->d_div_count.p)
         return fail(WEPP_E_STATE, "wepp_peer_export must be called first");
     CU(cudaSetDevice(h->device));
     peer_release(h);
@@ -1006,7 +1004,7 @@ int wepp_peer_open(wepp_handle* h, int32_t rank, int32_t world, const void* blob
             h->peer_ptr[g][0] = h->d_score.p;
             h->peer_ptr[g][1] = h->d_counts.p;
             h->peer_ptr[g][2] = h->d_score_merged.p;
-            h->peer_ptr[g][3] = h->d_divergence.p;
+            h->peer_ptr[g][3] = h->d_div_count.p;
             continue;
         }
         for (int b = 0; b < 4; ++b) {
@@ -1038,7 +1036,7 @@ int wepp_peer_merge(wepp_handle* h) {
         p.score_in[g] = static_cast<const double*>(h->peer_ptr[g][0]);
         p.counts_in[g] = static_cast<const int32_t*>(h->peer_ptr[g][1]);
         p.score_out[g] = static_cast<double*>(h->peer_ptr[g][2]);
-        p.div_out[g] = static_cast<double*>(h->peer_ptr[g][3]);
+        p.div_out[g] = static_cast<uint8_t*>(h->peer_ptr[g][3]);
     }
     p.counts_own = h->d_counts.p;
     p.bins_active = 0;
