@@ -457,6 +457,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                              "the kernel is co-limited by warp-instruction issue and shared-memory wavefronts "
                              "(see bottleneck and DESIGN.md section 3)",
                      "bottleneck": bottleneck},
+        "roofline_node_kernels": node_roofline(st, arena, peak),
         "clocks": clocks, "c5_rescore": c5,
         "exchange": None if world == 1 else ("peer-memory merge kernel (wepp_peer_merge)" if peer is not None
                                              else "NCCL all-reduce of score[N] + counts[N][50]"),
@@ -468,6 +469,19 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference(arena, reads, args.cpu_seconds)
     print(json.dumps(out), flush=True)
+
+
+def node_roofline(st, arena, peak):
+    """The node-side kernels of a step (expand_kernel + the score / count scans, 6-7 % of it) are plain HBM
+    streaming.  Algorithmic bytes: the per-node accumulators written once (N x (8 + 200) B), the per-bucket entry
+    accumulators (12 B), list entries (16 B) and enclosing-boundary indices (4 B) read once."""
+    acc_total = st["list_entries_total"] * st["n_buckets"] / max(st["n_lists"], 1)
+    alg = arena.n_nodes * 208 + acc_total * 12 + st["list_entries_total"] * 20
+    ms = st["ms_node_kernels"]
+    ach = alg / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+    return {"bound": "hbm", "kernels": "expand_kernel + score/count difference-array scans", "ms": ms,
+            "algorithmic_bytes": int(alg), "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "note": "the difference-array formulation moves ~4x the algorithmic bytes (zero, scatter, sum pass, apply pass)"}
 
 
 def run_c5(args, p, arena, reads, world, dev, barrier):
