@@ -448,6 +448,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config_dict(arena, reads, args),
         "read_x_node_scores_per_s": value * arena.n_nodes,
+        # degree-weighted: the raw (uncollapsed) reads the placed collapsed reads stand for (rank 0's shard x N)
+        "raw_reads_per_s": float(reads.degree.sum(dtype=np.int64)) * world / (ms_per_step / 1e3),
         "touched_read_entries_per_s": st["scanned_read_entries"] * 2 * world / (ms_per_step / 1e3),
         "e2e": e2e, "e2e_full_counts": e2e_full, "gpu_launches": int(st["kernel_launches"] * args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
