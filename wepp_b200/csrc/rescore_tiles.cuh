@@ -368,41 +368,41 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) rescore_tile_kernel(const
         __syncwarp();
     }
     if constexpr (MODE == 0) {
-    // compact lists: the candidates of this warp's range without an entry have no stack mutation in the window,
-    // so their distance is the read's own k: one evaluation for all of them
-    if (cw1 - cw0 - n_end > 0) st.eval(S0, cw1 - cw0 - n_end);
+        // compact lists: the candidates of this warp's range without an entry have no stack mutation in the window,
+        // so their distance is the read's own k: one evaluation for all of them
+        if (cw1 - cw0 - n_end > 0) st.eval(S0, cw1 - cw0 - n_end);
 
-    // ---- fold the warps' (min, count) ------------------------------------------------------------------
+        // ---- fold the warps' (min, count) ------------------------------------------------------------------
 #pragma unroll
-    for (int q = 0; q < P; ++q) {
-        const uint32_t bl = st.B[q] & 0xFFFFu, bh = st.B[q] >> 16;
-        xch[(warp * 2 + 0) * T + (2 * q) * 32 + lane] = bl == BEST_NONE ? 0x3FFFFFFF : (int)bl - (int)S_BIAS;
-        xch[(warp * 2 + 0) * T + (2 * q + 1) * 32 + lane] = bh == BEST_NONE ? 0x3FFFFFFF : (int)bh - (int)S_BIAS;
-    }
+        for (int q = 0; q < P; ++q) {
+            const uint32_t bl = st.B[q] & 0xFFFFu, bh = st.B[q] >> 16;
+            xch[(warp * 2 + 0) * T + (2 * q) * 32 + lane] = bl == BEST_NONE ? 0x3FFFFFFF : (int)bl - (int)S_BIAS;
+            xch[(warp * 2 + 0) * T + (2 * q + 1) * 32 + lane] = bh == BEST_NONE ? 0x3FFFFFFF : (int)bh - (int)S_BIAS;
+        }
 #pragma unroll
-    for (int j = 0; j < K; ++j) xch[(warp * 2 + 1) * T + j * 32 + lane] = st.cnt[j];
-    __syncthreads();
+        for (int j = 0; j < K; ++j) xch[(warp * 2 + 1) * T + j * 32 + lane] = st.cnt[j];
+        __syncthreads();
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        if (rid[j] < 0) continue;
-        int gb = 0x3FFFFFFF;
+        for (int j = 0; j < K; ++j) {
+            if (rid[j] < 0) continue;
+            int gb = 0x3FFFFFFF;
 #pragma unroll
-        for (int w = 0; w < PLACE_WARPS; ++w) gb = min(gb, xch[(w * 2 + 0) * T + j * 32 + lane]);
-        int gc = 0, before = 0;
+            for (int w = 0; w < PLACE_WARPS; ++w) gb = min(gb, xch[(w * 2 + 0) * T + j * 32 + lane]);
+            int gc = 0, before = 0;
 #pragma unroll
-        for (int w = 0; w < PLACE_WARPS; ++w) {
-            if (xch[(w * 2 + 0) * T + j * 32 + lane] == gb) {
-                const int c = xch[(w * 2 + 1) * T + j * 32 + lane];
-                gc += c;
-                if (w < warp) before += c;
+            for (int w = 0; w < PLACE_WARPS; ++w) {
+                if (xch[(w * 2 + 0) * T + j * 32 + lane] == gb) {
+                    const int c = xch[(w * 2 + 1) * T + j * 32 + lane];
+                    gc += c;
+                    if (w < warp) before += c;
+                }
+            }
+            p.before[rid[j] * PLACE_WARPS + warp] = before;
+            if (warp == 0) {
+                p.min_dist[rid[j]] = gb;
+                p.n_argmin[rid[j]] = gc;
             }
         }
-        p.before[rid[j] * PLACE_WARPS + warp] = before;
-        if (warp == 0) {
-            p.min_dist[rid[j]] = gb;
-            p.n_argmin[rid[j]] = gc;
-        }
-    }
     }
 }
 
