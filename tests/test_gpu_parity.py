@@ -281,6 +281,39 @@ def test_rescore_tile_kernel_matches_oracle(name, q, k, n_cand):
     p.close()
 
 
+def _check_state_path(arena, reads, q=None, k=None):
+    """place(0, 0) — no mask, no explicit EPP lists — with WEPP_STATE_PLACE=1 against the oracle."""
+    o = oracle.cartesian_map(arena, reads, None, n_threads=4, want_node=True)
+    p = Placer(0, stripe_width=q, reads_per_lane=k)
+    p.set_arena(arena)
+    p.set_reads(reads)
+    for _ in range(2):          # twice: the states are built once per read set and reused
+        p.place(0, 0)
+        mp, mu = p.read_results()
+        sc, ct = p.node_results()
+        assert np.array_equal(mp, o["max_parsimony"])
+        assert np.array_equal(mu, o["multiplicity"])
+        assert np.array_equal(ct, o["counts"])
+        np.testing.assert_allclose(sc, o["score"], rtol=SCORE_RTOL, atol=1e-15)
+    p.close()
+
+
+@pytest.mark.parametrize("name,q,k", [("tiny0", 8, 8), ("tiny1", 8, 4), ("tiny2", 16, 2), ("tiny3", 4, 0), ("tiny4", 32, 8),
+                                      ("tiny5", 1, 2), ("star", 32, 8), ("star", 16, 0), ("small", 32, 0), ("small", 16, 4),
+                                      ("c4", 16, 0)])
+def test_state_place_matches_oracle(name, q, k, monkeypatch):
+    """Experimental path (state_place.cuh): scoring the distinct window-restricted haplotypes of every window list."""
+    monkeypatch.setenv("WEPP_STATE_PLACE", "1")
+    arena, reads = _rescore_case(name)
+    _check_state_path(arena, reads, q, k)
+
+
+def test_state_place_medium_c2_shape(monkeypatch):
+    monkeypatch.setenv("WEPP_STATE_PLACE", "1")
+    arena, reads, _ = synth.config_shape("C2", scale=0.02)
+    _check_state_path(arena, reads)
+
+
 def test_rescore_tile_and_generic_kernels_agree_at_size():
     """Beyond what the oracle finishes quickly: 200k nodes, 60k reads, 700 candidates — the tile kernel over the
     resident reads against the generic one-thread-per-read kernel of wepp_rescore_reads (itself oracle-checked)."""

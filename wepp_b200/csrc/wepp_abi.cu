@@ -18,6 +18,7 @@
 #include "kernels.cuh"
 #include "rescore.cuh"
 #include "rescore_tiles.cuh"
+#include "state_place.cuh"
 #include "peaks.cuh"
 
 using namespace wepp;
@@ -142,16 +143,24 @@ struct wepp_handle {
         DevBuf<int32_t> prev_boundary;   // per list entry: enclosing / previous boundary entry
         DevBuf<int32_t> chunk_start;     // [n_lists][PLACE_WARPS + 1]
         bool final_for_mask = false;
+        // distinct window-restricted haplotypes of the lists (state_place.cuh; built on demand, no mask)
+        bool states_ready = false, states_usable = false;
+        int32_t n_states = 0;
+        int64_t sacc_total = 0;
+        DevBuf<int32_t> sid, state_first;
+        DevBuf<int64_t> state_eoff, sacc_off;
+        DevBuf<Entry> state_ent;
         void release() {
             perm.release(); lists.release(); buckets.release(); tiles.release(); entries.release();
             prev_boundary.release(); chunk_start.release();
+            sid.release(); state_first.release(); state_eoff.release(); sacc_off.release(); state_ent.release();
         }
     };
     DevPlan full, sub;
 
     // accumulators and outputs
-    DevBuf<double> d_accS;
-    DevBuf<int32_t> d_accC;
+    DevBuf<double> d_accS, d_saccS;
+    DevBuf<int32_t> d_accC, d_saccC;
     DevBuf<int32_t> d_maxpars, d_mult;
     DevBuf<double> d_score, d_divergence;
     DevBuf<int32_t> d_counts;
@@ -242,6 +251,7 @@ int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp, bool host_perm) {
         CU(cudaGetLastError());
     }
     dp.final_for_mask = false;
+    dp.states_ready = false;
     return WEPP_OK;
 }
 
@@ -303,6 +313,105 @@ template <int K>
 int launch_place_k(wepp_handle* h, const PlaceParams& pp, int width) {
     if (pp.accumulate) return pp.epp_off ? launch_place<K, true, true>(h, pp, width) : launch_place<K, true, false>(h, pp, width);
     return launch_place<K, false, true>(h, pp, width);
+}
+
+// The distinct restricted haplotypes ("states") of every list of the plan: state_place.cuh.
+int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
+    if (dp.states_ready) return WEPP_OK;
+    dp.states_ready = true;
+    dp.states_usable = false;
+    const ReadPlan& pl = dp.plan;
+    const int n_lists = (int)pl.lists.size();
+    const int64_t E = pl.list_entries_total;
+    if (n_lists == 0 || n_lists > SW_MAX_LISTS || E <= 0 || E > 0x7FFFFFFFll) return WEPP_OK;
+    cudaStream_t st = h->stream;
+    DevBuf<uint64_t> key, key2, h2;
+    DevBuf<uint32_t> val, val2;
+    DevBuf<int32_t> overflow, flag, incl, rep_state, state_ucnt, state_rep, state_list;
+    DevBuf<int64_t> state_len;
+    CU(key.ensure((size_t)E)); CU(key2.ensure((size_t)E)); CU(h2.ensure((size_t)E));
+    CU(val.ensure((size_t)E)); CU(val2.ensure((size_t)E));
+    CU(overflow.ensure((size_t)n_lists)); CU(flag.ensure((size_t)E)); CU(incl.ensure((size_t)E));
+    CU(dp.sid.ensure((size_t)E));
+    StateWalkParams wp = {};
+    wp.lists = dp.entries.p; wp.list_desc = dp.lists.p; wp.n_lists = n_lists; wp.pass = 0;
+    wp.key = key.p; wp.h2 = h2.p; wp.overflow = overflow.p;
+    state_walk_kernel<<<n_lists, 32, 0, st>>>(wp);
+    CU(cudaGetLastError());
+    std::vector<int32_t> ov((size_t)n_lists);
+    CU(cudaMemcpyAsync(ov.data(), overflow.p, (size_t)n_lists * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int32_t o : ov)
+        if (o) return WEPP_OK;   // a list with too many active positions: place_kernel serves this plan
+    iota_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(val.p, E);
+    CU(cudaGetLastError());
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, key.p, key2.p, val.p, val2.p, (int)E, 0, 64, st));
+    CU(h->d_cub_tmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp.p, tmp, key.p, key2.p, val.p, val2.p, (int)E, 0, 64, st));
+    state_flag_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(key2.p, val2.p, h2.p, E, flag.p);
+    CU(cudaGetLastError());
+    CU(cub::DeviceScan::InclusiveSum(nullptr, tmp, flag.p, incl.p, (int)E, st));
+    CU(h->d_cub_tmp.ensure(tmp));
+    CU(cub::DeviceScan::InclusiveSum(h->d_cub_tmp.p, tmp, flag.p, incl.p, (int)E, st));
+    int32_t n_states = 0;
+    CU(cudaMemcpyAsync(&n_states, incl.p + (E - 1), 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (n_states <= 0) return WEPP_OK;
+    const size_t S = (size_t)n_states;
+    CU(state_ucnt.ensure(S)); CU(state_rep.ensure(S)); CU(state_list.ensure(S)); CU(state_len.ensure(S + 1));
+    CU(dp.state_eoff.ensure(S + 1)); CU(dp.state_first.ensure((size_t)n_lists + 1)); CU(rep_state.ensure((size_t)E));
+    CU(cudaMemsetAsync(state_ucnt.p, 0, S * 4, st));
+    CU(cudaMemsetAsync(state_rep.p, 0x7F, S * 4, st));
+    CU(cudaMemsetAsync(state_len.p, 0, (S + 1) * 8, st));
+    CU(cudaMemsetAsync(rep_state.p, 0xFF, (size_t)E * 4, st));
+    state_assign_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(key2.p, val2.p, incl.p, dp.entries.p, h2.p, E, dp.sid.p,
+                                                                     state_ucnt.p, state_rep.p, state_len.p, state_list.p);
+    CU(cudaGetLastError());
+    CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, state_len.p, dp.state_eoff.p, (int)(S + 1), st));
+    CU(h->d_cub_tmp.ensure(tmp));
+    CU(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, state_len.p, dp.state_eoff.p, (int)(S + 1), st));
+    state_first_kernel<<<(unsigned)((S + 1 + 255) / 256), 256, 0, st>>>(state_list.p, n_states, n_lists, dp.state_first.p);
+    CU(cudaGetLastError());
+    state_rep_mark_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(state_rep.p, n_states, rep_state.p);
+    CU(cudaGetLastError());
+    int64_t total_ent = 0;
+    std::vector<int32_t> first((size_t)n_lists + 1);
+    CU(cudaMemcpyAsync(&total_ent, dp.state_eoff.p + S, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(first.data(), dp.state_first.p, ((size_t)n_lists + 1) * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    CU(dp.state_ent.ensure((size_t)std::max<int64_t>(total_ent, 1)));
+    wp.pass = 1;
+    wp.rep_state = rep_state.p; wp.state_eoff = dp.state_eoff.p; wp.state_ucnt = state_ucnt.p;
+    wp.state_first = dp.state_first.p; wp.state_ent = dp.state_ent.p;
+    state_walk_kernel<<<n_lists, 32, 0, st>>>(wp);
+    CU(cudaGetLastError());
+    std::vector<int64_t> sacc((size_t)pl.buckets.size());
+    int64_t acc = 0;
+    for (size_t b = 0; b < pl.buckets.size(); ++b) {
+        sacc[b] = acc;
+        acc += first[(size_t)pl.buckets[b].list + 1] - first[(size_t)pl.buckets[b].list];
+    }
+    CU(upload(dp.sacc_off, sacc, st));
+    CU(cudaStreamSynchronize(st));   // the temporaries above go out of scope
+    dp.sacc_total = acc;
+    dp.n_states = n_states;
+    dp.states_usable = true;
+    if (getenv("WEPP_TIMING") && atoi(getenv("WEPP_TIMING")) != 0)
+        fprintf(stderr, "[wepp timing] states: %d lists, %lld list entries -> %d distinct restricted haplotypes, %lld state entries\n",
+                n_lists, (long long)E, n_states, (long long)total_ent);
+    return WEPP_OK;
+}
+
+template <int K>
+int launch_state_place(wepp_handle* h, const StatePlaceParams& p, int n_tiles, int width) {
+    const size_t smem = (size_t)RtLayout<K>::CODES + (((size_t)width * 32 * K + 15) & ~(size_t)15);
+    if (smem > h->smem_optin || width > MAX_WINDOW)
+        return fail(WEPP_E_INVALID, "read window too wide for shared memory (" + std::to_string(width) + " bases)");
+    CU(cudaFuncSetAttribute(state_place_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    state_place_kernel<K><<<n_tiles, PLACE_WARPS * 32, smem, h->stream>>>(p);
+    CU(cudaGetLastError());
+    return WEPP_OK;
 }
 
 int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t epp_cap, int64_t epp_capacity,
@@ -368,8 +477,40 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     pp.epp_off = want_epp ? h->d_epp_off.p : nullptr;
     pp.epp_nodes = want_epp ? h->d_epp_nodes.p : nullptr;
 
+    // experimental: score the distinct window-restricted haplotypes instead of scanning the Euler lists
+    // (state_place.cuh; the whole read set, nothing mapped, no explicit EPP lists)
+    const bool state_env = getenv("WEPP_STATE_PLACE") && atoi(getenv("WEPP_STATE_PLACE")) != 0;
+    bool by_states = false;
+    if (state_env && accumulate && !want_epp && !h->has_mask && &dp == &h->full && pp.n_tiles > 0) {
+        rc = build_states(h, dp);
+        if (rc) return rc;
+        by_states = dp.states_usable;
+    }
     CU(cudaEventRecord(h->ev[0], h->stream));
-    if (pp.n_tiles > 0) {
+    if (by_states) {
+        CU(h->d_saccS.ensure((size_t)std::max<int64_t>(dp.sacc_total, 1)));
+        CU(h->d_saccC.ensure((size_t)std::max<int64_t>(dp.sacc_total, 1)));
+        CU(cudaMemsetAsync(h->d_saccS.p, 0, (size_t)dp.sacc_total * sizeof(double), h->stream));
+        CU(cudaMemsetAsync(h->d_saccC.p, 0, (size_t)dp.sacc_total * sizeof(int32_t), h->stream));
+        StatePlaceParams sp = {};
+        sp.state_ent = dp.state_ent.p; sp.state_eoff = dp.state_eoff.p; sp.state_first = dp.state_first.p;
+        sp.sacc_off = dp.sacc_off.p; sp.list_desc = dp.lists.p; sp.buckets = dp.buckets.p; sp.tiles = dp.tiles.p;
+        sp.start = h->d_rstart.p; sp.end = h->d_rend.p; sp.degree = h->d_rdegree.p; sp.rm_off = h->d_roff.p;
+        sp.rm_pos = h->d_rpos.p; sp.rm_code = h->d_rcode.p; sp.perm = dp.perm.p;
+        sp.max_pars = h->d_maxpars.p; sp.mult = h->d_mult.p; sp.saccS = h->d_saccS.p; sp.saccC = h->d_saccC.p;
+        const int k = pl.reads_per_tile / 32;
+        if (k == 8) rc = launch_state_place<8>(h, sp, pp.n_tiles, pl.max_width);
+        else if (k == 4) rc = launch_state_place<4>(h, sp, pp.n_tiles, pl.max_width);
+        else rc = launch_state_place<2>(h, sp, pp.n_tiles, pl.max_width);
+        if (rc) return rc;
+        int max_n = 0;
+        for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
+        dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
+        state_scatter_kernel<<<grid, 256, 0, h->stream>>>(dp.lists.p, dp.buckets.p, dp.sid.p, dp.state_first.p, dp.sacc_off.p,
+                                                          h->d_saccS.p, h->d_saccC.p, h->d_accS.p, h->d_accC.p);
+        CU(cudaGetLastError());
+        launches += 2;
+    } else if (pp.n_tiles > 0) {
         const int k = pl.reads_per_tile / 32;
         if (k == 8) rc = launch_place_k<8>(h, pp, pl.max_width);
         else if (k == 4) rc = launch_place_k<4>(h, pp, pl.max_width);
