@@ -41,15 +41,33 @@ __device__ __forceinline__ uint64_t sw_mix(uint64_t x) {   // splitmix64 finalis
     return x ^ (x >> 31);
 }
 
+constexpr int SW_CHUNKS = 64;              // chunks a list is walked in (one warp's lane 0 each)
+struct ChunkNet {
+    int32_t n;                              // active positions at the chunk's end when started from an empty context
+    uint32_t pos[SW_MAX_ACTIVE];
+    uint64_t tab[SW_MAX_ACTIVE];
+};
+
+// chunk k of a list of n entries starts at k * ceil(n / SW_CHUNKS), moved forward to a boundary entry so that a
+// leaf's point entries are never split (the same rule in every pass)
+__device__ __forceinline__ int sw_chunk_begin(const Entry* e, int n, int k) {
+    if (k >= SW_CHUNKS) return n;
+    const int cs = (n + SW_CHUNKS - 1) / SW_CHUNKS;
+    int c = min(n, k * cs);
+    while (c < n && (__ldg(&e[c].x) & ENT_POINT)) ++c;
+    return c;
+}
+
 struct StateWalkParams {
     const Entry* lists;
     const ListDesc* list_desc;
     int32_t n_lists;
-    int32_t pass;                 // 0: hashes ; 1: representatives' entries
+    int32_t pass;                 // -1: chunk nets ; 0: hashes ; 1: representatives' entries
     // pass 0 out (per list entry)
     uint64_t* key;                // (list << 51 | hash >> 13), SW_NOT_EVAL for entries that are not evaluated
     uint64_t* h2;                 // second hash (size in the low byte)
     int32_t* overflow;            // per list: 1 = more than SW_MAX_ACTIVE active positions (state path unusable)
+    ChunkNet* nets;               // [n_lists][SW_CHUNKS]: net effect of each chunk on the context (pass -1 out, passes 0/1 in)
     // pass 1 in / out
     const int32_t* rep_state;     // per list entry: global state index it represents, or -1
     const int64_t* state_eoff;    // [S + 1]
@@ -76,12 +94,16 @@ __global__ void iota_kernel(uint32_t* __restrict__ v, int64_t n) {
     if (i < n) v[i] = (uint32_t)i;
 }
 
-// one block per list, lane 0 walks (the walk is sequential; hundreds of lists keep the SMs' schedulers busy enough)
+// one warp per (list, chunk), lane 0 walks: the walk is sequential and branchy, tens of thousands of independent
+// walks keep the schedulers busy.  Pass -1 walks every chunk from an empty context and stores its net effect;
+// passes 0 and 1 start from the sum of the earlier chunks' nets.
 __global__ void state_walk_kernel(const StateWalkParams p) {
-    const int l = blockIdx.x;
-    if (l >= p.n_lists || threadIdx.x != 0) return;
+    const int wid = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5);
+    const int l = wid / SW_CHUNKS, ck = wid % SW_CHUNKS;
+    if (l >= p.n_lists || (threadIdx.x & 31) != 0) return;
     const ListDesc ld = p.list_desc[l];
     const Entry* e = p.lists + ld.off;
+    const int i_begin = sw_chunk_begin(e, ld.n, ck), i_end = sw_chunk_begin(e, ld.n, ck + 1);
     uint32_t pos[SW_MAX_ACTIVE];
     uint64_t tab[SW_MAX_ACTIVE];
     int n_act = 0;
@@ -116,7 +138,13 @@ __global__ void state_walk_kernel(const StateWalkParams p) {
             H2 += sw_mix((((uint64_t)ps << 40) | d) ^ 0x5851F42D4C957F2Dull);
         }
     };
-    for (int i = 0; i < ld.n && !over; ++i) {
+    if (p.pass >= 0) {   // context at the chunk's start
+        for (int c = 0; c < ck && !over; ++c) {
+            const ChunkNet& cn = p.nets[(size_t)l * SW_CHUNKS + c];
+            for (int a = 0; a < cn.n; ++a) apply(cn.pos[a], cn.tab[a]);
+        }
+    }
+    for (int i = i_begin; i < i_end && !over; ++i) {
         const uint4 en = ld_entry(e + i);
         const uint64_t d = sw_pack(en.z, en.w);
         const uint32_t ps = en.w >> 16;
@@ -125,7 +153,7 @@ __global__ void state_walk_kernel(const StateWalkParams p) {
             if (p.pass == 0) {
                 p.key[ld.off + i] = ((uint64_t)l << 51) | (H1 >> 13);
                 p.h2[ld.off + i] = (H2 & ~0xFFull) | (uint64_t)n_act;
-            } else {
+            } else if (p.pass == 1) {
                 const int s = p.rep_state[ld.off + i];
                 if (s >= 0) {
                     // the state as entries sorted by position (insertion sort of <= SW_MAX_ACTIVE items)
@@ -168,11 +196,15 @@ __global__ void state_walk_kernel(const StateWalkParams p) {
             }
         }
     }
-    if (p.pass == 0) {
-        p.overflow[l] = over ? 1 : 0;
-        if (over)
-            for (int i = 0; i < ld.n; ++i) p.key[ld.off + i] = SW_NOT_EVAL;
+    if (p.pass == -1) {
+        ChunkNet& cn = p.nets[(size_t)l * SW_CHUNKS + ck];
+        cn.n = n_act;
+        for (int a = 0; a < n_act; ++a) {
+            cn.pos[a] = pos[a];
+            cn.tab[a] = tab[a];
+        }
     }
+    if (over) p.overflow[l] = 1;   // zeroed by the host before pass -1; any pass may raise it
 }
 
 // sorted (key, entry) pairs -> "starts a new state" flags

@@ -145,6 +145,7 @@ struct wepp_handle {
         bool final_for_mask = false;
         // distinct window-restricted haplotypes of the lists (state_place.cuh; built on demand, no mask)
         bool states_ready = false, states_usable = false;
+        std::vector<std::pair<int32_t, int32_t>> state_ranges;   // (qs, qe) of the lists the states were built for
         int32_t n_states = 0;
         int64_t sacc_total = 0;
         DevBuf<int32_t> sid, state_first;
@@ -251,7 +252,14 @@ int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp, bool host_perm) {
         CU(cudaGetLastError());
     }
     dp.final_for_mask = false;
-    dp.states_ready = false;
+    // the states (state_place.cuh) are a function of the tree and of the lists' stripe ranges only: they stay
+    // valid while consecutive read sets map to the same sequence of window lists
+    if (dp.states_ready) {
+        bool same = dp.state_ranges.size() == pl.lists.size();
+        for (size_t i = 0; same && i < pl.lists.size(); ++i)
+            same = dp.state_ranges[i].first == pl.lists[i].qs && dp.state_ranges[i].second == pl.lists[i].qe;
+        if (!same) dp.states_ready = false;
+    }
     return WEPP_OK;
 }
 
@@ -321,6 +329,8 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     dp.states_ready = true;
     dp.states_usable = false;
     const ReadPlan& pl = dp.plan;
+    dp.state_ranges.clear();
+    for (const ListDesc& l : pl.lists) dp.state_ranges.emplace_back(l.qs, l.qe);
     const int n_lists = (int)pl.lists.size();
     const int64_t E = pl.list_entries_total;
     if (n_lists == 0 || n_lists > SW_MAX_LISTS || E <= 0 || E > 0x7FFFFFFFll) return WEPP_OK;
@@ -333,10 +343,18 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     CU(val.ensure((size_t)E)); CU(val2.ensure((size_t)E));
     CU(overflow.ensure((size_t)n_lists)); CU(flag.ensure((size_t)E)); CU(incl.ensure((size_t)E));
     CU(dp.sid.ensure((size_t)E));
+    DevBuf<ChunkNet> nets;
+    CU(nets.ensure((size_t)n_lists * SW_CHUNKS));
+    CU(cudaMemsetAsync(overflow.p, 0, (size_t)n_lists * 4, st));
     StateWalkParams wp = {};
-    wp.lists = dp.entries.p; wp.list_desc = dp.lists.p; wp.n_lists = n_lists; wp.pass = 0;
-    wp.key = key.p; wp.h2 = h2.p; wp.overflow = overflow.p;
-    state_walk_kernel<<<n_lists, 32, 0, st>>>(wp);
+    wp.lists = dp.entries.p; wp.list_desc = dp.lists.p; wp.n_lists = n_lists;
+    wp.key = key.p; wp.h2 = h2.p; wp.overflow = overflow.p; wp.nets = nets.p;
+    const unsigned walk_blocks = (unsigned)(((int64_t)n_lists * SW_CHUNKS * 32 + 127) / 128);
+    wp.pass = -1;
+    state_walk_kernel<<<walk_blocks, 128, 0, st>>>(wp);
+    CU(cudaGetLastError());
+    wp.pass = 0;
+    state_walk_kernel<<<walk_blocks, 128, 0, st>>>(wp);
     CU(cudaGetLastError());
     std::vector<int32_t> ov((size_t)n_lists);
     CU(cudaMemcpyAsync(ov.data(), overflow.p, (size_t)n_lists * 4, cudaMemcpyDeviceToHost, st));
@@ -384,7 +402,7 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     wp.pass = 1;
     wp.rep_state = rep_state.p; wp.state_eoff = dp.state_eoff.p; wp.state_ucnt = state_ucnt.p;
     wp.state_first = dp.state_first.p; wp.state_ent = dp.state_ent.p;
-    state_walk_kernel<<<n_lists, 32, 0, st>>>(wp);
+    state_walk_kernel<<<walk_blocks, 128, 0, st>>>(wp);
     CU(cudaGetLastError());
     std::vector<int64_t> sacc((size_t)pl.buckets.size());
     int64_t acc = 0;
@@ -682,6 +700,8 @@ int wepp_set_arena(wepp_handle* h, int32_t n_nodes, const int32_t* parent, const
     h->has_mask = false;
     h->has_results = false;
     h->rank_tab_d = 0;
+    h->full.states_ready = false;
+    h->sub.states_ready = false;
     h->tree_on_device = false;
     h->st_cache.clear();
     h->st_cache_pos.clear();
