@@ -453,11 +453,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         "touched_read_entries_per_s": st["scanned_read_entries"] * 2 * world / (ms_per_step / 1e3),
         "e2e": e2e, "e2e_full_counts": e2e_full, "gpu_launches": int(st["kernel_launches"] * args.steps),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "place_kernel", "kernel_ms": k_ms,
+                     "traffic": traffic, "kernel": "state_place_kernel" if os.environ.get("WEPP_STATE_PLACE", "1") != "0" else "place_kernel",
+                     "kernel_ms": k_ms,
                      "algorithmic_bytes_per_launch": int(alg), "peak_source": peak_src,
-                     "note": "not HBM-bound: the per-window Euler lists are L2-resident and every tile re-reads them; "
-                             "the kernel is co-limited by warp-instruction issue and shared-memory wavefronts "
-                             "(see bottleneck and DESIGN.md section 3)",
+                     "note": "not HBM-bound: the per-window lists are L2-resident and every tile re-reads them; the kernel "
+                             "(state_place_kernel: the distinct window-restricted haplotypes of a window are scored once "
+                             "each, about half the entries of the Euler list the algorithmic bytes are counted on) is "
+                             "limited by warp-instruction issue (see bottleneck and DESIGN.md section 3)",
                      "bottleneck": bottleneck},
         "roofline_node_kernels": node_roofline(st, arena, peak),
         "clocks": clocks, "c5_rescore": c5,

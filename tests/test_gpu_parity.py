@@ -308,6 +308,14 @@ def test_state_place_matches_oracle(name, q, k, monkeypatch):
     _check_state_path(arena, reads, q, k)
 
 
+@pytest.mark.parametrize("name,q,k", [("tiny0", 8, 8), ("star", 32, 0), ("small", 16, 0)])
+def test_euler_scan_accumulate_without_epp_lists(name, q, k, monkeypatch):
+    """WEPP_STATE_PLACE=0: the same call through place_kernel's accumulate-only variant."""
+    monkeypatch.setenv("WEPP_STATE_PLACE", "0")
+    arena, reads = _rescore_case(name)
+    _check_state_path(arena, reads, q, k)
+
+
 def test_state_place_medium_c2_shape(monkeypatch):
     monkeypatch.setenv("WEPP_STATE_PLACE", "1")
     arena, reads, _ = synth.config_shape("C2", scale=0.02)

@@ -1,5 +1,6 @@
-// state_place.cuh — placement over the DISTINCT window-restricted haplotypes of every read window
-// (experimental, WEPP_STATE_PLACE=1; the default path is place_kernel in kernels.cuh).
+// state_place.cuh — placement over the DISTINCT window-restricted haplotypes of every read window: the default for
+// wepp_place over the whole read set with nothing mapped and no explicit EPP lists (WEPP_STATE_PLACE=0 selects
+// place_kernel, kernels.cuh, which also serves masks, EPP lists, subsets and lists that opt out here).
 //
 // A read's parsimony score at a node depends on the node only through the node's haplotype restricted to the
 // read's window (the last event per window position on the root path).  A window of ~170 bases
@@ -67,7 +68,8 @@ struct StateWalkParams {
     uint64_t* key;                // (list << 51 | hash >> 13), SW_NOT_EVAL for entries that are not evaluated
     uint64_t* h2;                 // second hash (size in the low byte)
     int32_t* overflow;            // per list: 1 = more than SW_MAX_ACTIVE active positions (state path unusable)
-    ChunkNet* nets;               // [n_lists][SW_CHUNKS]: net effect of each chunk on the context (pass -1 out, passes 0/1 in)
+    ChunkNet* nets;               // [n_lists][SW_CHUNKS]: net effect of each chunk on the context (pass -1 out)
+    const ChunkNet* ctx;          // [n_lists][SW_CHUNKS]: context at each chunk's start (passes 0 / 1 in)
     // pass 1 in / out
     const int32_t* rep_state;     // per list entry: global state index it represents, or -1
     const int64_t* state_eoff;    // [S + 1]
@@ -138,11 +140,9 @@ __global__ void state_walk_kernel(const StateWalkParams p) {
             H2 += sw_mix((((uint64_t)ps << 40) | d) ^ 0x5851F42D4C957F2Dull);
         }
     };
-    if (p.pass >= 0) {   // context at the chunk's start
-        for (int c = 0; c < ck && !over; ++c) {
-            const ChunkNet& cn = p.nets[(size_t)l * SW_CHUNKS + c];
-            for (int a = 0; a < cn.n; ++a) apply(cn.pos[a], cn.tab[a]);
-        }
+    if (p.pass >= 0) {   // context at the chunk's start (state_ctx_kernel)
+        const ChunkNet& cn = p.ctx[(size_t)l * SW_CHUNKS + ck];
+        for (int a = 0; a < cn.n; ++a) apply(cn.pos[a], cn.tab[a]);
     }
     for (int i = i_begin; i < i_end && !over; ++i) {
         const uint4 en = ld_entry(e + i);
@@ -205,6 +205,42 @@ __global__ void state_walk_kernel(const StateWalkParams p) {
         }
     }
     if (over) p.overflow[l] = 1;   // zeroed by the host before pass -1; any pass may raise it
+}
+
+// context at every chunk's start = sum of the earlier chunks' nets (one thread per list: 64 small sparse adds)
+__global__ void state_ctx_kernel(const ChunkNet* __restrict__ nets, int n_lists, ChunkNet* __restrict__ ctx, int32_t* __restrict__ overflow) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_lists) return;
+    uint32_t pos[SW_MAX_ACTIVE];
+    uint64_t tab[SW_MAX_ACTIVE];
+    int n_act = 0;
+    for (int k = 0; k < SW_CHUNKS; ++k) {
+        ChunkNet& out = ctx[(size_t)l * SW_CHUNKS + k];
+        out.n = n_act;
+        for (int a = 0; a < n_act; ++a) {
+            out.pos[a] = pos[a];
+            out.tab[a] = tab[a];
+        }
+        const ChunkNet& cn = nets[(size_t)l * SW_CHUNKS + k];
+        for (int a = 0; a < cn.n; ++a) {
+            int j = 0;
+            while (j < n_act && pos[j] != cn.pos[a]) ++j;
+            if (j < n_act) {
+                tab[j] = sw_add_bytes(tab[j], cn.tab[a]);
+                if (tab[j] == 0ull) {
+                    --n_act;
+                    pos[j] = pos[n_act];
+                    tab[j] = tab[n_act];
+                }
+            } else if (n_act < SW_MAX_ACTIVE) {
+                pos[n_act] = cn.pos[a];
+                tab[n_act] = cn.tab[a];
+                ++n_act;
+            } else {
+                overflow[l] = 1;
+            }
+        }
+    }
 }
 
 // sorted (key, entry) pairs -> "starts a new state" flags

@@ -335,6 +335,7 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     const int64_t E = pl.list_entries_total;
     if (n_lists == 0 || n_lists > SW_MAX_LISTS || E <= 0 || E > 0x7FFFFFFFll) return WEPP_OK;
     cudaStream_t st = h->stream;
+    const auto t_build = std::chrono::steady_clock::now();
     DevBuf<uint64_t> key, key2, h2;
     DevBuf<uint32_t> val, val2;
     DevBuf<int32_t> overflow, flag, incl, rep_state, state_ucnt, state_rep, state_list;
@@ -343,8 +344,9 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     CU(val.ensure((size_t)E)); CU(val2.ensure((size_t)E));
     CU(overflow.ensure((size_t)n_lists)); CU(flag.ensure((size_t)E)); CU(incl.ensure((size_t)E));
     CU(dp.sid.ensure((size_t)E));
-    DevBuf<ChunkNet> nets;
+    DevBuf<ChunkNet> nets, ctx;
     CU(nets.ensure((size_t)n_lists * SW_CHUNKS));
+    CU(ctx.ensure((size_t)n_lists * SW_CHUNKS));
     CU(cudaMemsetAsync(overflow.p, 0, (size_t)n_lists * 4, st));
     StateWalkParams wp = {};
     wp.lists = dp.entries.p; wp.list_desc = dp.lists.p; wp.n_lists = n_lists;
@@ -353,6 +355,9 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     wp.pass = -1;
     state_walk_kernel<<<walk_blocks, 128, 0, st>>>(wp);
     CU(cudaGetLastError());
+    state_ctx_kernel<<<(n_lists + 31) / 32, 32, 0, st>>>(nets.p, n_lists, ctx.p, overflow.p);
+    CU(cudaGetLastError());
+    wp.ctx = ctx.p;
     wp.pass = 0;
     state_walk_kernel<<<walk_blocks, 128, 0, st>>>(wp);
     CU(cudaGetLastError());
@@ -416,8 +421,9 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     dp.n_states = n_states;
     dp.states_usable = true;
     if (getenv("WEPP_TIMING") && atoi(getenv("WEPP_TIMING")) != 0)
-        fprintf(stderr, "[wepp timing] states: %d lists, %lld list entries -> %d distinct restricted haplotypes, %lld state entries\n",
-                n_lists, (long long)E, n_states, (long long)total_ent);
+        fprintf(stderr, "[wepp timing] states: %d lists, %lld list entries -> %d distinct restricted haplotypes, %lld state entries, built in %.1f ms\n",
+                n_lists, (long long)E, n_states, (long long)total_ent,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build).count());
     return WEPP_OK;
 }
 
@@ -495,9 +501,9 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     pp.epp_off = want_epp ? h->d_epp_off.p : nullptr;
     pp.epp_nodes = want_epp ? h->d_epp_nodes.p : nullptr;
 
-    // experimental: score the distinct window-restricted haplotypes instead of scanning the Euler lists
-    // (state_place.cuh; the whole read set, nothing mapped, no explicit EPP lists)
-    const bool state_env = getenv("WEPP_STATE_PLACE") && atoi(getenv("WEPP_STATE_PLACE")) != 0;
+    // score the distinct window-restricted haplotypes instead of scanning the Euler lists (state_place.cuh) when the
+    // whole read set is placed with nothing mapped and no explicit EPP lists; WEPP_STATE_PLACE=0 keeps place_kernel
+    const bool state_env = !(getenv("WEPP_STATE_PLACE") && atoi(getenv("WEPP_STATE_PLACE")) == 0);
     bool by_states = false;
     if (state_env && accumulate && !want_epp && !h->has_mask && &dp == &h->full && pp.n_tiles > 0) {
         rc = build_states(h, dp);
