@@ -320,15 +320,20 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) state_place_kernel(const 
     constexpr int P = K / 2;
     constexpr int SHIFT = Sel<K>::SHIFT;
     constexpr int T = 32 * K;
-    constexpr int CODES = RtLayout<K>::CODES;
+    constexpr int TBL = RtLayout<K>::CODES;            // pass-2 pattern tables PatEntry[2][16][32] (as place_kernel)
+    constexpr int CODES = TBL + 2 * TBL_HALF;          // the selector table follows them
+    static_assert(CODES <= 65536, "pattern tables must be addressable with 16-bit offsets");
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_s = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t ebuf_s = smem_s + warp * 512;
     int* xch = reinterpret_cast<int*>(smem + RT_XCH);
+    PatEntry* tbl = reinterpret_cast<PatEntry*>(smem + TBL);
     unsigned char* codes = smem + CODES;
     const uint32_t col = smem_s + CODES + lane * K;
     const unsigned FULL = 0xFFFFFFFFu;
+    if (smem_s + CODES > 0xFFFFu) __trap();
+    const uint32_t tbase2 = (smem_s + TBL + lane * 16) | ((smem_s + TBL + TBL_HALF + lane * 16) << 16);
 
     const TileDesc td = p.tiles[blockIdx.x];
     const BucketDesc bd = p.buckets[td.bucket];
@@ -469,6 +474,26 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) state_place_kernel(const 
         if (j & 1) bestp[j >> 1] = (bestp[j >> 1] & 0x0000FFFFu) | (b << 16);
         else bestp[j >> 1] = (bestp[j >> 1] & 0xFFFF0000u) | b;
     }
+    // pattern tables: for the lane's even reads (low halves) and odd reads (high halves), the weight / degree sums
+    // of the reads whose NOT-at-min bit is clear, indexed by the P-bit pattern; the warps split the 2 x 2^P patterns
+    for (int hp = warp; hp < 2 * (1 << P); hp += PLACE_WARPS) {
+        const int hh = hp >> P, pat = hp & ((1 << P) - 1);
+        double ws = 0.0;
+        int ds = 0;
+#pragma unroll
+        for (int q = 0; q < P; ++q) {
+            if (!((pat >> q) & 1)) {
+                ws += hh ? wgt[2 * q + 1] : wgt[2 * q];
+                ds += hh ? deg[2 * q + 1] : deg[2 * q];
+            }
+        }
+        PatEntry pe;
+        pe.w = ws;
+        pe.c = ds;
+        pe.pad = 0;
+        tbl[(hh * 16 + pat) * 32 + lane] = pe;
+    }
+    __syncthreads();
     // ---- pass 2 -----------------------------------------------------------------------------------------
     double* accS = p.saccS + p.sacc_off[td.bucket];
     int32_t* accC = p.saccC + p.sacc_off[td.bucket];
@@ -496,25 +521,25 @@ __global__ void __launch_bounds__(PLACE_WARPS * 32, 2) state_place_kernel(const 
 #pragma unroll
                     for (int q = 0; q < P; ++q) S[q] = __vadd2(S[q], prmt(e.z, e.w, sel[q]));
                     if (eg & (1u << i)) {
-                        double ws = 0.0;
-                        int ds = 0;
+                        uint32_t ti = tbase2;
 #pragma unroll
                         for (int q = 0; q < P; ++q) {
-                            const uint32_t x = S[q] ^ bestp[q];
-                            if ((x & 0xFFFFu) == 0u) { ws += wgt[2 * q]; ds += deg[2 * q]; }
-                            if ((x >> 16) == 0u) { ws += wgt[2 * q + 1]; ds += deg[2 * q + 1]; }
+                            // per half: 0 = the read is at its minimum here, 1 = it is not
+                            ti += __vminu2(S[q] ^ bestp[q], 0x00010001u) * (uint32_t)(TBL_PAT_STRIDE << q);
                             S[q] = S0[q];
                         }
-                        if (__any_sync(FULL, ds != 0 || ws != 0.0)) {
+                        const uint4 pa = lds128(ti & 0xFFFFu), pb = lds128(ti >> 16);
+                        double ws = __hiloint2double((int)pa.y, (int)pa.x) + __hiloint2double((int)pb.y, (int)pb.x);
+                        // degrees first (one REDUX): a zero total means no read of the tile is at its minimum here
+                        // (a read's weight is non-zero only with its degree)
+                        const int ds = __reduce_add_sync(FULL, (int)(pa.z + pb.z));
+                        if (ds != 0) {
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                ws += __shfl_xor_sync(FULL, ws, o);
-                                ds += __shfl_xor_sync(FULL, ds, o);
-                            }
+                            for (int o = 16; o > 0; o >>= 1) ws += __shfl_xor_sync(FULL, ws, o);
                             if (lane == 0) {
                                 const uint32_t s = e.x & ~RT_END;
                                 if (ws != 0.0) atomicAdd(accS + s, ws);
-                                if (ds != 0) atomicAdd(accC + s, ds);
+                                atomicAdd(accC + s, ds);
                             }
                         }
                     }

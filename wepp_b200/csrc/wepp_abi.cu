@@ -429,7 +429,7 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
 
 template <int K>
 int launch_state_place(wepp_handle* h, const StatePlaceParams& p, int n_tiles, int width) {
-    const size_t smem = (size_t)RtLayout<K>::CODES + (((size_t)width * 32 * K + 15) & ~(size_t)15);
+    const size_t smem = (size_t)RtLayout<K>::CODES + 2 * TBL_HALF + (((size_t)width * 32 * K + 15) & ~(size_t)15);
     if (smem > h->smem_optin || width > MAX_WINDOW)
         return fail(WEPP_E_INVALID, "read window too wide for shared memory (" + std::to_string(width) + " bases)");
     CU(cudaFuncSetAttribute(state_place_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
