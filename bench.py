@@ -8,8 +8,9 @@ Workload (BASELINE.json configs[2], the one the metric is quoted on): a syntheti
 public-scale SARS-CoV-2 MAT (8M arena nodes, genome 29,903) x ARTIC-like 150-bp amplicon
 reads, read-sharded: every GPU places 1.25M collapsed reads against the replicated tree
 (weak scaling; 8 GPUs = the full 10M reads).  One step = one cartesian_map over the rank's
-shard: placement kernel + segment expansion + per-node scans, and for N>1 the NCCL
-all-reduce of the per-node score / read-count arrays.
+shard: placement kernel (state_place_kernel: the distinct window-restricted haplotypes of every
+window scored once) + expansion + per-node scans, and for N>1 the exchange step (one kernel over
+NVLink peer memory, or --exchange nccl: the all-reduce of the per-node score / read-count arrays).
 
 One JSON line is printed by rank 0 (see README / DESIGN.md for the keys).
 """
