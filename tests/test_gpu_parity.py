@@ -316,6 +316,25 @@ def test_euler_scan_accumulate_without_epp_lists(name, q, k, monkeypatch):
     _check_state_path(arena, reads, q, k)
 
 
+def test_state_place_across_read_sets():
+    """The states are kept while consecutive read sets map to the same window lists and buckets, and rebuilt
+    otherwise: alternate between a read set, a subset of it and the set again."""
+    arena, reads = cases.small_case(seed=31)
+    sub = reads.take(np.arange(0, reads.n_reads, 3))
+    p = Placer(0)
+    p.set_arena(arena)
+    for r in (reads, sub, reads, reads, sub):
+        o = oracle.cartesian_map(arena, r, None, n_threads=4)
+        p.set_reads(r)
+        p.place(0, 0)
+        mp, mu = p.read_results()
+        sc, ct = p.node_results()
+        assert np.array_equal(mp, o["max_parsimony"]) and np.array_equal(mu, o["multiplicity"])
+        assert np.array_equal(ct, o["counts"])
+        np.testing.assert_allclose(sc, o["score"], rtol=SCORE_RTOL, atol=1e-15)
+    p.close()
+
+
 def test_state_place_medium_c2_shape(monkeypatch):
     monkeypatch.setenv("WEPP_STATE_PLACE", "1")
     arena, reads, _ = synth.config_shape("C2", scale=0.02)

@@ -146,6 +146,7 @@ struct wepp_handle {
         // distinct window-restricted haplotypes of the lists (state_place.cuh; built on demand, no mask)
         bool states_ready = false, states_usable = false;
         std::vector<std::pair<int32_t, int32_t>> state_ranges;   // (qs, qe) of the lists the states were built for
+        std::vector<std::pair<int32_t, int32_t>> state_buckets;  // (list, bin) of the buckets their accumulators were laid out for
         int32_t n_states = 0;
         int64_t sacc_total = 0;
         DevBuf<int32_t> sid, state_first;
@@ -254,10 +255,13 @@ int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp, bool host_perm) {
     dp.final_for_mask = false;
     // the states (state_place.cuh) are a function of the tree and of the lists' stripe ranges only: they stay
     // valid while consecutive read sets map to the same sequence of window lists
+    // (and to the same (list, bin) buckets: the per-(bucket, state) accumulator offsets were laid out for them)
     if (dp.states_ready) {
-        bool same = dp.state_ranges.size() == pl.lists.size();
+        bool same = dp.state_ranges.size() == pl.lists.size() && dp.state_buckets.size() == pl.buckets.size();
         for (size_t i = 0; same && i < pl.lists.size(); ++i)
             same = dp.state_ranges[i].first == pl.lists[i].qs && dp.state_ranges[i].second == pl.lists[i].qe;
+        for (size_t i = 0; same && i < pl.buckets.size(); ++i)
+            same = dp.state_buckets[i].first == pl.buckets[i].list && dp.state_buckets[i].second == pl.buckets[i].bin;
         if (!same) dp.states_ready = false;
     }
     return WEPP_OK;
@@ -331,6 +335,8 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     const ReadPlan& pl = dp.plan;
     dp.state_ranges.clear();
     for (const ListDesc& l : pl.lists) dp.state_ranges.emplace_back(l.qs, l.qe);
+    dp.state_buckets.clear();
+    for (const BucketDesc& b : pl.buckets) dp.state_buckets.emplace_back(b.list, b.bin);
     const int n_lists = (int)pl.lists.size();
     const int64_t E = pl.list_entries_total;
     if (n_lists == 0 || n_lists > SW_MAX_LISTS || E <= 0 || E > 0x7FFFFFFFll) return WEPP_OK;
