@@ -192,6 +192,10 @@ typedef struct wepp_stats {
     float   ms_node_kernels;                        /* expand + prefix scans */
     int32_t reads_per_tile;
     int32_t stripe_width;
+    int32_t place_path;                             /* 0 Euler-list scan, 1 distinct states, 2 sparse corrections over the states */
+    int32_t n_states;                               /* distinct window-restricted haplotypes (paths 1, 2) */
+    int32_t n_window_groups;                        /* (bucket, window) groups of the read set (path 2) */
+    int32_t reserved;
 } wepp_stats;
 int wepp_get_stats(wepp_handle* h, wepp_stats* out);
 

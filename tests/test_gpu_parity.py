@@ -281,8 +281,9 @@ def test_rescore_tile_kernel_matches_oracle(name, q, k, n_cand):
     p.close()
 
 
-def _check_state_path(arena, reads, q=None, k=None):
-    """place(0, 0) — no mask, no explicit EPP lists — with WEPP_STATE_PLACE=1 against the oracle."""
+def _check_state_path(arena, reads, q=None, k=None, path=None):
+    """place(0, 0) — no mask, no explicit EPP lists — against the oracle; `path` = the wepp_stats.place_path the
+    call must have taken (0 Euler-list scan, 1 distinct states, 2 sparse corrections over the states)."""
     o = oracle.cartesian_map(arena, reads, None, n_threads=4, want_node=True)
     p = Placer(0, stripe_width=q, reads_per_lane=k)
     p.set_arena(arena)
@@ -295,6 +296,8 @@ def _check_state_path(arena, reads, q=None, k=None):
         assert np.array_equal(mu, o["multiplicity"])
         assert np.array_equal(ct, o["counts"])
         np.testing.assert_allclose(sc, o["score"], rtol=SCORE_RTOL, atol=1e-15)
+        if path is not None:   # an int, or the set of paths allowed (tiny trees can overflow the states' position cap)
+            assert p.stats()["place_path"] in (path if isinstance(path, tuple) else (path,))
     p.close()
 
 
@@ -302,10 +305,30 @@ def _check_state_path(arena, reads, q=None, k=None):
                                       ("tiny5", 1, 2), ("star", 32, 8), ("star", 16, 0), ("small", 32, 0), ("small", 16, 4),
                                       ("c4", 16, 0)])
 def test_state_place_matches_oracle(name, q, k, monkeypatch):
-    """Experimental path (state_place.cuh): scoring the distinct window-restricted haplotypes of every window list."""
+    """state_place.cuh: scoring the distinct window-restricted haplotypes of every window list (dense over the states)."""
     monkeypatch.setenv("WEPP_STATE_PLACE", "1")
+    monkeypatch.setenv("WEPP_DELTA_PLACE", "0")
     arena, reads = _rescore_case(name)
-    _check_state_path(arena, reads, q, k)
+    _check_state_path(arena, reads, q, k, path=(0, 1) if name.startswith("tiny") or name == "c4" else 1)   # tiny / wide windows may exceed the states' position cap
+
+
+@pytest.mark.parametrize("cand", [None, 0, 3])
+@pytest.mark.parametrize("name,q,k", [("tiny0", 8, 8), ("tiny1", 8, 4), ("tiny2", 16, 2), ("tiny3", 4, 0), ("tiny4", 32, 8),
+                                      ("tiny5", 1, 2), ("star", 32, 8), ("star", 16, 0), ("small", 32, 0), ("small", 16, 4)])
+def test_delta_place_matches_oracle(name, q, k, cand, monkeypatch):
+    """delta_place.cuh: sparse corrections per read over the states.  WEPP_DELTA_PLACE=2 forces the path on read sets
+    with a window per read (the tiny cases: all-N reads and reads with dozens of mutations take the byte-scratch
+    route); WEPP_DELTA_CAND shrinks the candidate queue so that the posting re-walk runs too."""
+    monkeypatch.setenv("WEPP_DELTA_PLACE", "2")
+    if cand is not None:
+        monkeypatch.setenv("WEPP_DELTA_CAND", str(cand))
+    arena, reads = _rescore_case(name)
+    _check_state_path(arena, reads, q, k, path=(0, 2) if name.startswith("tiny") else 2)
+
+
+def test_delta_place_is_the_default_for_amplicon_reads():
+    arena, reads = cases.small_case(seed=23, n_reads=4000)
+    _check_state_path(arena, reads, path=2)
 
 
 @pytest.mark.parametrize("name,q,k", [("tiny0", 8, 8), ("star", 32, 0), ("small", 16, 0)])
@@ -335,10 +358,12 @@ def test_state_place_across_read_sets():
     p.close()
 
 
-def test_state_place_medium_c2_shape(monkeypatch):
+@pytest.mark.parametrize("delta,path", [("0", 1), ("1", 2)])
+def test_state_place_medium_c2_shape(delta, path, monkeypatch):
     monkeypatch.setenv("WEPP_STATE_PLACE", "1")
+    monkeypatch.setenv("WEPP_DELTA_PLACE", delta)
     arena, reads, _ = synth.config_shape("C2", scale=0.02)
-    _check_state_path(arena, reads)
+    _check_state_path(arena, reads, path=path)
 
 
 def test_rescore_tile_and_generic_kernels_agree_at_size():

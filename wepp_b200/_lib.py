@@ -24,7 +24,8 @@ class WeppStats(C.Structure):
         "list_entries_total", "scanned_entries", "scanned_read_entries", "algorithmic_bytes",
         "kernel_launches")] + [("ms_place_total", C.c_float), ("ms_scan_kernel", C.c_float),
                                ("ms_node_kernels", C.c_float), ("reads_per_tile", C.c_int32),
-                               ("stripe_width", C.c_int32)]
+                               ("stripe_width", C.c_int32), ("place_path", C.c_int32), ("n_states", C.c_int32),
+                               ("n_window_groups", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -1,0 +1,489 @@
+// delta_place.cuh — placement by SPARSE CORRECTIONS over the distinct window-restricted haplotypes ("states",
+// state_place.cuh): the default for wepp_place over the whole read set with nothing mapped and no EPP lists
+// (WEPP_DELTA_PLACE=0 keeps state_place_kernel, which also serves the lists / read sets that opt out here).
+//
+// A state s of a window list is a set of (position, allele) pairs — its net mutations inside the list's range — and
+// a read r is a window [a, b] plus a few mutations M_r (allele classes A/C/G/T/N).  SURVEY Appendix A then reads
+//
+//     parsimony(r, s) = k_r + base_w(s) - red(r, s)
+//       k_r       = non-N mutations of the read                       (the seed set, initial_filter.cpp:118-123)
+//       base_w(s) = mutated positions of s inside the window [a, b]   (a read as the reference mismatches each)
+//       red(r, s) = sum over the read's mutations (p, c) that s also mutates: 1, or 2 when the alleles agree
+//                   (an N, or another allele, takes back the state's mismatch; the same allele also takes back
+//                   the read's own seed mismatch)
+//
+// (each table of a state entry is "final allele X vs reference R": delta[ref] = (X != R), delta[c] = -(c == X),
+// delta[N] = 0, checked entry by entry when the posting lists are built — any other table and the plan opts out; a
+// reversion X == R keeps an entry with delta[ref] = 0 that only a read carrying the reference base as a "mutation"
+// would see, so base_w sums delta[ref] and red = delta[ref] - delta[c] may be 0).  base_w is the
+// same for every read of a window and red touches only the states that mutate one of the read's few positions:
+// ~550-1,500 states per read on the 8 M-node bench tree instead of the 37 k entries of the list's 15 k states.
+// Per read: start from the window's histogram "countable nodes per base score", move the touched states down by
+// their red, read off the minimum and its node count (initial_filter.cpp:89-99, :126-134).  Per-node weights
+// (:167-177): all states at base == min that the read does not touch get the read's weight through a per-(window,
+// score) sum G that is expanded once per step; touched states that end at the minimum get it directly.  A touched
+// state can never leave the minimum (red > 0 only lowers it), so there is nothing to subtract.
+//
+//   post_*_kernel          posting lists: per (list, position) the states that mutate it (state, allele class, nodes)
+//   delta_keys_kernel      sort key (bucket, window) per read -> cub sort + run-length encode = window groups
+//   window_base_kernel     base_w(s) for every group of a list, and the groups' histograms
+//   delta_place_kernel     persistent CTAs pull work units (<= 128 reads of one group); a warp takes a read
+//   delta_finalize_kernel  per-(bucket, state) accumulators += sum over the bucket's groups of G[group][base(s)]
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_run_length_encode.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include "kernels.cuh"
+#include "rescore_tiles.cuh"
+#include "state_place.cuh"
+
+namespace wepp {
+
+constexpr int DP_WARPS = 16;          // warps per CTA (one CTA per SM: the shared memory is the limit)
+constexpr int DP_BINS = 64;           // score bins: bin = base - red + DP_VOFF
+constexpr int DP_VOFF = SW_MAX_ACTIVE;   // base <= SW_MAX_ACTIVE and red <= 2 * base
+constexpr int DP_CAND = 192;          // candidate queue entries per warp
+constexpr int DP_FAST_MUTS = 7;       // reads with more mutations use byte scratch in global memory (nibbles hold <= 15)
+constexpr int DP_UNIT = 256;          // reads per work unit (a group of up to 2 * DP_UNIT reads stays whole)
+constexpr int DP_FIXED = 16 + DP_BINS * 4 + DP_WARPS * 128 * 4 + DP_WARPS * DP_CAND * 4;   // ctrl, whist, mv, cand
+static_assert(DP_VOFF + SW_MAX_ACTIVE + 1 <= DP_BINS, "score bins");
+constexpr uint32_t DP_X_NONE = 7u;    // allele class of a state entry that equals no read allele (IUPAC union)
+
+struct DeltaGroup {     // reads of one bucket with the same window
+    int64_t base_off;   // first byte of base_w in the base buffer (S_list bytes, 16-byte aligned)
+    int32_t list, bucket;
+    int32_t a_rel, b_rel;   // window relative to the list's first position
+    int32_t m0;         // smallest occupied bin of the window's histogram
+    int32_t pad;
+};
+struct DeltaUnit {
+    int32_t group, first, count, pad;   // reads order[first .. first + count)
+};
+
+// ---- posting lists -----------------------------------------------------------------------------------------------
+// A state entry's table is "final allele X vs reference R": delta[ref] = (X != R), delta[c] = -(c == X), delta[N] = 0
+// (host_prep.cpp mismatch_after / mismatch_seed).  Returns bit 3 = delta[ref], bits 0..2 = the class of X (1..4, or
+// DP_X_NONE when X is an IUPAC union no read allele equals), or 0xFF when the table is of another form.
+__device__ __forceinline__ uint32_t dp_table_class(uint32_t z, uint32_t w) {
+    const uint32_t bref = z & 0xFFu;
+    if (bref > 1u) return 0xFFu;
+    const uint32_t b[4] = {(z >> 8) & 0xFFu, (z >> 16) & 0xFFu, z >> 24, w & 0xFFu};
+    uint32_t xc = DP_X_NONE;
+    int n_match = 0;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (b[c] == 0xFFu) {
+            xc = (uint32_t)c + 1u;
+            ++n_match;
+        } else if (b[c] != 0u) {
+            return 0xFFu;
+        }
+    }
+    return n_match <= 1 ? (xc | (bref << 3)) : 0xFFu;
+}
+
+// One thread per state: a (sort key, posting) pair per state entry, at the entry's own index, and the entries per
+// (list, position) slot.  Sorting by key = slot << 16 | allele class << 8 | entries of the state groups the postings by
+// slot and, inside a slot, puts states with the same allele and the same number of mutations next to each other: the
+// 32 states a warp touches together then mostly share one (base score, red), and their nodes move between the
+// histogram bins with one warp sum.  The empty state's placeholder entry sorts to the end (key = all ones).
+__global__ void post_pairs_kernel(const Entry* __restrict__ state_ent, const int64_t* __restrict__ state_eoff,
+                                  const int32_t* __restrict__ state_list, const int32_t* __restrict__ state_first,
+                                  const int32_t* __restrict__ lpos_base, int32_t n_states, uint32_t* __restrict__ slot_count,
+                                  uint64_t* __restrict__ pkey, uint64_t* __restrict__ pval, int32_t* __restrict__ bad) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_states) return;
+    const int l = state_list[s];
+    const uint32_t local = (uint32_t)(s - state_first[l]);
+    const int32_t lp = lpos_base[l];
+    const int64_t e0 = state_eoff[s], e1 = state_eoff[s + 1];
+    const uint32_t len = (uint32_t)min((int64_t)255, e1 - e0);
+    for (int64_t k = e0; k < e1; ++k) {
+        const Entry e = state_ent[k];
+        pkey[k] = ~0ull;
+        pval[k] = 0ull;
+        if (e.z == 0u && (e.w & 0xFFu) == 0u) continue;   // the empty state's placeholder entry
+        const uint32_t xc = dp_table_class(e.z, e.w);
+        if (xc == 0xFFu || local >= (1u << 24)) {
+            *bad = 1;
+            continue;
+        }
+        const uint32_t slot = (uint32_t)lp + (e.w >> 16);
+        atomicAdd(slot_count + slot, 1u);
+        pkey[k] = ((uint64_t)slot << 16) | ((uint64_t)xc << 8) | (uint64_t)len;
+        pval[k] = (uint64_t)(local | (xc << 24)) | ((uint64_t)e.y << 32);   // uint2 {state | class << 24, nodes}
+    }
+}
+
+// ---- window groups -----------------------------------------------------------------------------------------------
+constexpr int DP_COST_BITS = 8;
+// one block per tile: key = (bucket << 24 | (start - b0) << 12 | (end - b0)) << 8 | 255 - min(255, touches / 64),
+// value = read index.  Sorted ascending, the reads of a window come heaviest first (touches = states the read's
+// mutations reach): the warps of a CTA pull reads from the front, so the last ones to finish are the cheapest.
+__global__ void delta_keys_kernel(const TileDesc* __restrict__ tiles, const BucketDesc* __restrict__ buckets,
+                                  const ListDesc* __restrict__ list_desc, const int64_t* __restrict__ perm,
+                                  const int32_t* __restrict__ start, const int32_t* __restrict__ end,
+                                  const int64_t* __restrict__ rm_off, const int32_t* __restrict__ rm_pos,
+                                  const uint32_t* __restrict__ post_off, const int32_t* __restrict__ lpos_base,
+                                  uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+    const TileDesc td = tiles[blockIdx.x];
+    const int32_t list = buckets[td.bucket].list;
+    const int32_t b0 = list_desc[list].b0, lp = lpos_base[list];
+    for (int i = threadIdx.x; i < td.count; i += blockDim.x) {
+        const int64_t rid = perm[td.first + i];
+        uint32_t cost = 0;
+        for (int64_t k = rm_off[rid]; k < rm_off[rid + 1]; ++k) {
+            const int slot = lp + rm_pos[k] - b0;
+            cost += post_off[slot + 1] - post_off[slot] + 16u;
+        }
+        const uint64_t w = ((uint64_t)td.bucket << 24) | ((uint64_t)(start[rid] - b0) << 12) | (uint64_t)(end[rid] - b0);
+        key[td.first + i] = (w << DP_COST_BITS) | (uint64_t)(255u - min(255u, cost >> 6));
+        val[td.first + i] = (uint32_t)rid;
+    }
+}
+
+__global__ void delta_window_of_key_kernel(const uint64_t* __restrict__ key, int64_t n, uint64_t* __restrict__ window) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) window[i] = key[i] >> DP_COST_BITS;
+}
+
+struct WindowBaseParams {
+    const Entry* state_ent;
+    const int64_t* state_eoff;
+    const int32_t* state_first;
+    const int32_t* list_goff;     // [n_lists + 1] groups of each list ...
+    const int32_t* list_gids;     // ... as indices into groups
+    const DeltaGroup* groups;
+    uint8_t* base;
+    int32_t* whist;               // [n_groups][DP_BINS], zeroed
+};
+
+// grid (state chunks, lists): a thread takes one state and evaluates base_w for every group of its list; the
+// countable nodes go to the groups' histograms warp-aggregated (the base scores of a warp take a handful of values)
+__global__ void __launch_bounds__(256) window_base_kernel(const WindowBaseParams p) {
+    const int l = blockIdx.y;
+    const int s_lo = p.state_first[l], s_n = p.state_first[l + 1] - s_lo;
+    const int g0 = p.list_goff[l], g1 = p.list_goff[l + 1];
+    if ((int)(blockIdx.x * blockDim.x) >= s_n || g0 == g1) return;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = s < s_n;
+    const unsigned FULL = 0xFFFFFFFFu;
+    int64_t e0 = 0, e1 = 0;
+    int ucnt = 0;
+    if (valid) {
+        e0 = p.state_eoff[s_lo + s];
+        e1 = p.state_eoff[s_lo + s + 1];
+        ucnt = (int)p.state_ent[e0].y;
+    }
+    for (int gi = g0; gi < g1; ++gi) {
+        const int g = p.list_gids[gi];
+        const DeltaGroup dg = p.groups[g];
+        int cnt = 0;
+        for (int64_t k = e0; k < e1; ++k) {
+            const uint32_t z = __ldg(&p.state_ent[k].z), w = __ldg(&p.state_ent[k].w);
+            const int pos = (int)(w >> 16);
+            cnt += (pos >= dg.a_rel && pos <= dg.b_rel) ? (int)(z & 0xFFu) : 0;   // delta[ref] is 0 or 1
+        }
+        if (valid) p.base[dg.base_off + s] = (uint8_t)cnt;
+        const int vmax = __reduce_max_sync(FULL, valid ? cnt : 0);
+        for (int v = 0; v <= vmax; ++v) {
+            const int sum = __reduce_add_sync(FULL, (valid && cnt == v) ? ucnt : 0);
+            if (sum != 0 && (threadIdx.x & 31) == 0) atomicAdd(p.whist + (size_t)g * DP_BINS + DP_VOFF + v, sum);
+        }
+    }
+}
+
+// smallest occupied bin per group (one thread per group)
+__global__ void window_m0_kernel(const int32_t* __restrict__ whist, int n_groups, DeltaGroup* __restrict__ groups) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    int m0 = DP_BINS - 1;
+    for (int v = DP_BINS - 1; v >= 0; --v)
+        if (whist[(size_t)g * DP_BINS + v] > 0) m0 = v;
+    groups[g].m0 = m0;
+}
+
+// ---- the placement kernel ----------------------------------------------------------------------------------------
+struct DeltaPlaceParams {
+    const DeltaUnit* units;
+    int32_t n_units;
+    int32_t smem_bytes;           // dynamic shared memory of the launch
+    int32_t cand_cap;             // candidate queue entries in use (<= DP_CAND; tests shrink it to reach the re-walk)
+    int* unit_counter;
+    const DeltaGroup* groups;
+    const uint8_t* base;
+    const int32_t* whist;
+    const uint2* post;
+    const uint32_t* post_off;
+    const int32_t* lpos_base;
+    const int32_t* state_first;
+    const ListDesc* list_desc;
+    const int64_t* sacc_off;
+    const uint32_t* order;        // reads sorted by (bucket, window)
+    const int32_t* degree;
+    const int64_t* rm_off;
+    const int32_t* rm_pos;
+    const uint8_t* rm_code;
+    int32_t* max_pars;
+    int32_t* mult;
+    double* saccS;
+    int32_t* saccC;
+    double* Gw;                   // [n_groups][DP_BINS]
+    int32_t* Gc;
+    uint32_t* gscratch;           // [grid][DP_WARPS][gscratch_words]: byte scratch of the reads with many mutations
+    int64_t gscratch_words;
+};
+
+// FAST: nibble scratch in shared memory + candidate queue; else byte scratch in global memory, postings re-walked
+template <bool FAST>
+__device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGroup& dg, int32_t rid, int lane,
+                                        const unsigned char* base_s, uint32_t* scr, int scr_words, int* mv, uint32_t* cand,
+                                        const int* whist_s, int lp, int64_t so, double (&gw)[2], int (&gc)[2]) {
+    const unsigned FULL = 0xFFFFFFFFu;
+    const int64_t ra = p.rm_off[rid], rb = p.rm_off[rid + 1];
+    const int nm = (int)(rb - ra);
+    const int b0 = p.list_desc[dg.list].b0;
+    int k_non_n = 0, n_cand = 0;
+    for (int j0 = 0; j0 < nm; j0 += 32) {
+        const bool have = j0 + lane < nm;
+        const int my_pos = have ? p.rm_pos[ra + j0 + lane] - b0 : 0;
+        const uint32_t my_code = have ? p.rm_code[ra + j0 + lane] : 5u;
+        k_non_n += __popc(__ballot_sync(FULL, have && my_code <= 4u));   // seed set: non-N mutations
+        const uint32_t my_lo = have ? p.post_off[lp + my_pos] : 0u, my_hi = have ? p.post_off[lp + my_pos + 1] : 0u;
+        const int cnt = min(32, nm - j0);
+        for (int j = 0; j < cnt; ++j) {
+            const uint32_t c = __shfl_sync(FULL, my_code, j);
+            const uint32_t lo = __shfl_sync(FULL, my_lo, j), hi = __shfl_sync(FULL, my_hi, j);
+            uint2 nxt = make_uint2(0u, 0u);
+            if (lo + lane < hi) nxt = __ldg(p.post + lo + lane);
+            for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
+                const uint2 e = nxt;
+                const bool in = i0 + lane < hi;
+                nxt = make_uint2(0u, 0u);
+                if (i0 + 32 + lane < hi) nxt = __ldg(p.post + i0 + 32 + lane);
+                const uint32_t s = e.x & 0xFFFFFFu;
+                const int d = (int)((e.x >> 27) & 1u) + (int)(((e.x >> 24) & 7u) == c);   // delta[ref] - delta[c]
+                const bool act = in && d > 0;
+                uint32_t key = 0xFFFFFFFFu;
+                int v_new = DP_BINS;
+                if (act) {
+                    int oldred;
+                    if (FAST) {
+                        const int sh = (int)(s & 7u) * 4;
+                        oldred = (int)((atomicAdd(scr + (s >> 3), (uint32_t)d << sh) >> sh) & 15u);
+                    } else {
+                        const int sh = (int)(s & 3u) * 8;
+                        oldred = (int)((atomicAdd(scr + (s >> 2), (uint32_t)d << sh) >> sh) & 255u);
+                    }
+                    const int v_old = (int)base_s[s] + DP_VOFF - oldred;
+                    key = ((uint32_t)v_old << 1) | (uint32_t)(d - 1);
+                    v_new = v_old - d;
+                }
+                // the moves "u nodes leave bin v_old by d", summed per distinct (v_old, d) of the warp; the postings
+                // are sorted so that most of the time there is one
+                uint32_t rem = __ballot_sync(FULL, act);
+                if (rem) {
+                    const int ld0 = __ffs(rem) - 1;
+                    const uint32_t k0 = __shfl_sync(FULL, key, ld0);
+                    const uint32_t other = __ballot_sync(FULL, act && key != k0);
+                    const int sum0 = __reduce_add_sync(FULL, (act && key == k0) ? (int)e.y : 0);
+                    if (lane == ld0) mv[k0] += sum0;
+                    rem = other;
+                    while (rem) {
+                        const int ld = __ffs(rem) - 1;
+                        const uint32_t k = __shfl_sync(FULL, key, ld);
+                        const bool mine = key == k;
+                        const uint32_t m = __ballot_sync(FULL, mine);
+                        const int sum = __reduce_add_sync(FULL, mine ? (int)e.y : 0);
+                        if (lane == ld) mv[k] += sum;
+                        rem &= ~m;
+                    }
+                }
+                if (FAST) {
+                    // a touched state that ends at the read's minimum is at or below the window's own minimum
+                    // after its last hit: remember those, the weights go to them once the minimum is known
+                    const bool is_c = act && v_new <= dg.m0;
+                    const uint32_t cm = __ballot_sync(FULL, is_c);
+                    if (cm) {
+                        const int slot = n_cand + __popc(cm & ((1u << lane) - 1u));
+                        if (is_c && slot < p.cand_cap) cand[slot] = s;
+                        n_cand += __popc(cm);
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // histogram of the read = the window's + the moves; minimum and its countable nodes
+    int tot[2];
+#pragma unroll
+    for (int hf = 0; hf < 2; ++hf) {
+        const int v = lane + 32 * hf;
+        int t = whist_s[v] - mv[2 * v] - mv[2 * v + 1];
+        if (v + 1 < DP_BINS) t += mv[2 * (v + 1)];
+        if (v + 2 < DP_BINS) t += mv[2 * (v + 2) + 1];
+        tot[hf] = t;
+    }
+    __syncwarp();
+    mv[lane] = 0; mv[lane + 32] = 0; mv[lane + 64] = 0; mv[lane + 96] = 0;
+    const uint32_t o0 = __ballot_sync(FULL, tot[0] > 0), o1 = __ballot_sync(FULL, tot[1] > 0);
+    const int mV = o0 ? __ffs(o0) - 1 : (o1 ? 32 + __ffs(o1) - 1 : DP_VOFF);
+    const int n_epp = (o0 | o1) ? __shfl_sync(FULL, mV < 32 ? tot[0] : tot[1], mV & 31) : 0;
+    const int pars = k_non_n + mV - DP_VOFF;
+    const int deg = p.degree[rid];
+    double wgt = 0.0;
+    if (n_epp > 0) wgt = (double)deg / ((double)(1 + pars) * (double)n_epp);   // node_score, initial_filter.hpp:54-57
+    if (lane == 0) {
+        p.max_pars[rid] = pars;
+        p.mult[rid] = n_epp;
+    }
+    if (n_epp > 0 && lane == (mV & 31)) {
+        gw[mV >> 5] += wgt;
+        gc[mV >> 5] += deg;
+    }
+    // touched states at the minimum; scratch back to zero
+    if (FAST && n_cand <= p.cand_cap) {
+        for (int i = lane; i < n_cand; i += 32) {
+            const uint32_t s = cand[i];
+            const int sh = (int)(s & 7u) * 4;
+            const int red = (int)((atomicAnd(scr + (s >> 3), ~(15u << sh)) >> sh) & 15u);   // duplicates see 0
+            if (red && n_epp > 0 && (int)base_s[s] + DP_VOFF - red == mV) {
+                atomicAdd(p.saccS + so + s, wgt);
+                atomicAdd(p.saccC + so + s, deg);
+            }
+        }
+        if (nm > 0) {
+            __syncwarp();
+            uint4* z = reinterpret_cast<uint4*>(scr);
+            for (int i = lane; i < scr_words / 4; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    } else {
+        for (int j0 = 0; j0 < nm; j0 += 32) {
+            const bool have = j0 + lane < nm;
+            const int my_pos = have ? p.rm_pos[ra + j0 + lane] - b0 : 0;
+            const uint32_t my_lo = have ? p.post_off[lp + my_pos] : 0u, my_hi = have ? p.post_off[lp + my_pos + 1] : 0u;
+            const int cnt = min(32, nm - j0);
+            for (int j = 0; j < cnt; ++j) {
+                const uint32_t lo = __shfl_sync(FULL, my_lo, j), hi = __shfl_sync(FULL, my_hi, j);
+                for (uint32_t i = lo + lane; i < hi; i += 32) {
+                    const uint32_t s = __ldg(p.post + i).x & 0xFFFFFFu;
+                    int red;
+                    if (FAST) {
+                        const int sh = (int)(s & 7u) * 4;
+                        red = (int)((atomicAnd(scr + (s >> 3), ~(15u << sh)) >> sh) & 15u);
+                    } else {
+                        const int sh = (int)(s & 3u) * 8;
+                        red = (int)((atomicAnd(scr + (s >> 2), ~(255u << sh)) >> sh) & 255u);
+                    }
+                    if (red && n_epp > 0 && (int)base_s[s] + DP_VOFF - red == mV) {
+                        atomicAdd(p.saccS + so + s, wgt);
+                        atomicAdd(p.saccC + so + s, deg);
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(DP_WARPS * 32, 1) delta_place_kernel(const DeltaPlaceParams p) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int* ctrl = reinterpret_cast<int*>(smem);                       // [0] unit, [1] next read of the unit
+    int* whist_s = reinterpret_cast<int*>(smem + 16);
+    int* mv_all = whist_s + DP_BINS;
+    uint32_t* cand_all = reinterpret_cast<uint32_t*>(mv_all + DP_WARPS * 128);
+    unsigned char* base_s = smem + DP_FIXED;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned FULL = 0xFFFFFFFFu;
+    int* mv = mv_all + warp * 128;
+    uint32_t* cand = cand_all + warp * DP_CAND;
+    for (int i = threadIdx.x; i < DP_WARPS * 128; i += blockDim.x) mv_all[i] = 0;
+    uint32_t* gscr = p.gscratch + ((size_t)blockIdx.x * DP_WARPS + warp) * (size_t)p.gscratch_words;
+    int scr_list = -1;   // the list this warp's nibble scratch is laid out (and zero) for
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            ctrl[0] = atomicAdd(p.unit_counter, 1);
+            ctrl[1] = 0;
+        }
+        __syncthreads();
+        const int u = ctrl[0];
+        if (u >= p.n_units) break;
+        const DeltaUnit du = p.units[u];
+        const DeltaGroup dg = p.groups[du.group];
+        const int s_n = p.state_first[dg.list + 1] - p.state_first[dg.list];
+        const int s_pad = (s_n + 15) & ~15;
+        const int stride = ((s_n + 7) / 8 * 4 + 15) & ~15;          // nibble scratch bytes per warp
+        const int aw = min(DP_WARPS, (p.smem_bytes - DP_FIXED - s_pad) / stride);
+        {   // the window's base scores and histogram
+            const uint4* src = reinterpret_cast<const uint4*>(p.base + dg.base_off);
+            uint4* dst = reinterpret_cast<uint4*>(base_s);
+            for (int i = threadIdx.x; i < s_pad / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+            if (threadIdx.x < DP_BINS) whist_s[threadIdx.x] = p.whist[(size_t)du.group * DP_BINS + threadIdx.x];
+        }
+        uint32_t* scr = reinterpret_cast<uint32_t*>(base_s + s_pad + (size_t)warp * stride);
+        if (warp < aw && dg.list != scr_list) {   // another list: the layout moved, its scratch area starts out zero
+            uint4* z = reinterpret_cast<uint4*>(scr);
+            for (int i = lane; i < stride / 16; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        scr_list = warp < aw ? dg.list : -1;
+        __syncthreads();
+        if (warp < aw) {
+            const int lp = p.lpos_base[dg.list];
+            const int64_t so = p.sacc_off[dg.bucket];
+            double gw[2] = {0.0, 0.0};
+            int gc[2] = {0, 0};
+            for (;;) {
+                int r = 0;
+                if (lane == 0) r = atomicAdd(&ctrl[1], 1);
+                r = __shfl_sync(FULL, r, 0);
+                if (r >= du.count) break;
+                const int32_t rid = (int32_t)p.order[du.first + r];
+                const int nm = (int)(p.rm_off[rid + 1] - p.rm_off[rid]);
+                if (nm <= DP_FAST_MUTS) dp_read<true>(p, dg, rid, lane, base_s, scr, stride / 4, mv, cand, whist_s, lp, so, gw, gc);
+                else dp_read<false>(p, dg, rid, lane, base_s, gscr, 0, mv, cand, whist_s, lp, so, gw, gc);
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                if (gc[hf] != 0) {
+                    atomicAdd(p.Gw + (size_t)du.group * DP_BINS + lane + 32 * hf, gw[hf]);
+                    atomicAdd(p.Gc + (size_t)du.group * DP_BINS + lane + 32 * hf, gc[hf]);
+                }
+            }
+        }
+    }
+}
+
+// per-(bucket, state) accumulators += the weights of the reads whose minimum is the state's base score in their
+// window and that do not touch the state: sum over the bucket's groups of G[group][base_group(s)]
+__global__ void delta_finalize_kernel(const DeltaGroup* __restrict__ groups, const int32_t* __restrict__ bucket_goff,
+                                      const int32_t* __restrict__ state_first, const BucketDesc* __restrict__ buckets,
+                                      const uint8_t* __restrict__ base, const double* __restrict__ Gw,
+                                      const int32_t* __restrict__ Gc, const int64_t* __restrict__ sacc_off,
+                                      double* __restrict__ saccS, int32_t* __restrict__ saccC) {
+    const int b = blockIdx.y;
+    const int g0 = bucket_goff[b], g1 = bucket_goff[b + 1];
+    if (g0 == g1) return;
+    const int l = buckets[b].list;
+    const int s_n = state_first[l + 1] - state_first[l];
+    const int64_t so = sacc_off[b];
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < s_n; s += gridDim.x * blockDim.x) {
+        double ws = 0.0;
+        int cs = 0;
+        for (int g = g0; g < g1; ++g) {
+            const int v = (int)base[groups[g].base_off + s] + DP_VOFF;
+            ws += Gw[(size_t)g * DP_BINS + v];
+            cs += Gc[(size_t)g * DP_BINS + v];
+        }
+        if (cs != 0) {
+            saccS[so + s] += ws;
+            saccC[so + s] += cs;
+        }
+    }
+}
+
+}  // namespace wepp

@@ -19,6 +19,7 @@
 #include "rescore.cuh"
 #include "rescore_tiles.cuh"
 #include "state_place.cuh"
+#include "delta_place.cuh"
 #include "peaks.cuh"
 
 using namespace wepp;
@@ -152,10 +153,31 @@ struct wepp_handle {
         DevBuf<int32_t> sid, state_first;
         DevBuf<int64_t> state_eoff, sacc_off;
         DevBuf<Entry> state_ent;
+        // sparse corrections over the states (delta_place.cuh): posting lists per (list, position), kept with the
+        // states; window groups of the current read set, rebuilt when the reads change
+        bool delta_usable = false, delta_groups_ready = false, delta_groups_usable = false;
+        std::vector<int32_t> h_state_first;
+        int32_t max_list_states = 0;
+        DevBuf<int32_t> state_list, lpos_base;
+        DevBuf<uint32_t> post_off;
+        DevBuf<uint2> post;
+        int32_t n_groups = 0, n_units = 0;
+        int64_t delta_touch_est = 0;
+        DevBuf<uint32_t> order;
+        DevBuf<DeltaGroup> groups;
+        DevBuf<DeltaUnit> units;
+        DevBuf<uint8_t> base;
+        DevBuf<int32_t> whist, list_goff, list_gids, bucket_goff, Gc;
+        DevBuf<double> Gw;
+        DevBuf<uint32_t> gscratch;
+        int64_t gscratch_words = 0;
         void release() {
             perm.release(); lists.release(); buckets.release(); tiles.release(); entries.release();
             prev_boundary.release(); chunk_start.release();
             sid.release(); state_first.release(); state_eoff.release(); sacc_off.release(); state_ent.release();
+            state_list.release(); lpos_base.release(); post_off.release(); post.release(); order.release();
+            groups.release(); units.release(); base.release(); whist.release(); list_goff.release();
+            list_gids.release(); bucket_goff.release(); Gc.release(); Gw.release(); gscratch.release();
         }
     };
     DevPlan full, sub;
@@ -253,6 +275,7 @@ int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp, bool host_perm) {
         CU(cudaGetLastError());
     }
     dp.final_for_mask = false;
+    dp.delta_groups_ready = false;   // the window groups (delta_place.cuh) belong to the read set
     // the states (state_place.cuh) are a function of the tree and of the lists' stripe ranges only: they stay
     // valid while consecutive read sets map to the same sequence of window lists
     // (and to the same (list, bin) buckets: the per-(bucket, state) accumulator offsets were laid out for them)
@@ -344,8 +367,10 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     const auto t_build = std::chrono::steady_clock::now();
     DevBuf<uint64_t> key, key2, h2;
     DevBuf<uint32_t> val, val2;
-    DevBuf<int32_t> overflow, flag, incl, rep_state, state_ucnt, state_rep, state_list;
+    DevBuf<int32_t> overflow, flag, incl, rep_state, state_ucnt, state_rep;
+    DevBuf<int32_t>& state_list = dp.state_list;
     DevBuf<int64_t> state_len;
+    dp.delta_usable = false;
     CU(key.ensure((size_t)E)); CU(key2.ensure((size_t)E)); CU(h2.ensure((size_t)E));
     CU(val.ensure((size_t)E)); CU(val2.ensure((size_t)E));
     CU(overflow.ensure((size_t)n_lists)); CU(flag.ensure((size_t)E)); CU(incl.ensure((size_t)E));
@@ -422,6 +447,57 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
         acc += first[(size_t)pl.buckets[b].list + 1] - first[(size_t)pl.buckets[b].list];
     }
     CU(upload(dp.sacc_off, sacc, st));
+    dp.h_state_first = first;
+    dp.max_list_states = 0;
+    for (int l = 0; l < n_lists; ++l) dp.max_list_states = std::max(dp.max_list_states, first[(size_t)l + 1] - first[(size_t)l]);
+    {   // posting lists per (list, position): delta_place.cuh
+        std::vector<int32_t> lpos((size_t)n_lists + 1);
+        int64_t slots = 0;
+        for (int l = 0; l < n_lists; ++l) {
+            lpos[(size_t)l] = (int32_t)slots;
+            slots += pl.lists[(size_t)l].width;
+        }
+        lpos[(size_t)n_lists] = (int32_t)slots;
+        const bool fits = slots < (1ll << 30) && total_ent < (1ll << 31);
+        if (fits) {
+            DevBuf<uint32_t> slot_count;
+            DevBuf<uint64_t> pkey, pkey2, pval;
+            DevBuf<int32_t> bad;
+            const size_t TE = (size_t)std::max<int64_t>(total_ent, 1);
+            CU(upload(dp.lpos_base, lpos, st));
+            CU(slot_count.ensure((size_t)slots + 1)); CU(bad.ensure(1));
+            CU(pkey.ensure(TE)); CU(pkey2.ensure(TE)); CU(pval.ensure(TE));
+            CU(dp.post_off.ensure((size_t)slots + 1));
+            CU(dp.post.ensure(TE));
+            CU(cudaMemsetAsync(slot_count.p, 0, ((size_t)slots + 1) * 4, st));
+            CU(cudaMemsetAsync(bad.p, 0, 4, st));
+            post_pairs_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(dp.state_ent.p, dp.state_eoff.p, state_list.p, dp.state_first.p,
+                                                                          dp.lpos_base.p, n_states, slot_count.p, pkey.p, pval.p, bad.p);
+            CU(cudaGetLastError());
+            CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, slot_count.p, dp.post_off.p, (int)(slots + 1), st));
+            CU(h->d_cub_tmp.ensure(tmp));
+            CU(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, slot_count.p, dp.post_off.p, (int)(slots + 1), st));
+            int slot_bits = 1;
+            while ((1ll << slot_bits) < slots + 1) ++slot_bits;
+            static_assert(sizeof(uint2) == sizeof(uint64_t), "postings are sorted as 64-bit values");
+            CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, pkey.p, pkey2.p, pval.p, reinterpret_cast<uint64_t*>(dp.post.p),
+                                               (int)total_ent, 0, 16 + slot_bits, st));
+            CU(h->d_cub_tmp.ensure(tmp));
+            CU(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp.p, tmp, pkey.p, pkey2.p, pval.p, reinterpret_cast<uint64_t*>(dp.post.p),
+                                               (int)total_ent, 0, 16 + slot_bits, st));
+            int32_t h_bad = 0;
+            CU(cudaMemcpyAsync(&h_bad, bad.p, 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            // shared memory of delta_place_kernel: the widest list's base scores + at least 4 warps' nibble scratch
+            const int64_t s_max = dp.max_list_states;
+            const int64_t need = DP_FIXED + ((s_max + 15) & ~15ll) + 4 * ((((s_max + 7) / 8 * 4) + 15) & ~15ll);
+            dp.delta_usable = h_bad == 0 && need <= (int64_t)h->smem_optin;
+            if (getenv("WEPP_TIMING") && atoi(getenv("WEPP_TIMING")) != 0)
+                fprintf(stderr, "[wepp timing] postings: %lld slots, %lld entries, tables %s, widest list %lld states, shared memory %lld of %lld -> %s\n",
+                        (long long)slots, (long long)total_ent, h_bad ? "NOT of the allele form" : "ok", (long long)s_max, (long long)need,
+                        (long long)h->smem_optin, dp.delta_usable ? "usable" : "unusable");
+        }
+    }
     CU(cudaStreamSynchronize(st));   // the temporaries above go out of scope
     dp.sacc_total = acc;
     dp.n_states = n_states;
@@ -430,6 +506,115 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
         fprintf(stderr, "[wepp timing] states: %d lists, %lld list entries -> %d distinct restricted haplotypes, %lld state entries, built in %.1f ms\n",
                 n_lists, (long long)E, n_states, (long long)total_ent,
                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_build).count());
+    return WEPP_OK;
+}
+
+// Window groups of the current read set for delta_place_kernel: the reads sorted by (bucket, window), one group per
+// distinct key, base scores + histogram per group, work units of <= DP_UNIT reads.
+int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
+    if (dp.delta_groups_ready) return WEPP_OK;
+    dp.delta_groups_ready = true;
+    dp.delta_groups_usable = false;
+    const ReadPlan& pl = dp.plan;
+    const int64_t R = pl.n_reads;
+    const int n_lists = (int)pl.lists.size(), n_buckets = (int)pl.buckets.size(), n_tiles = (int)pl.tiles.size();
+    if (!dp.delta_usable || R <= 0 || R > 0x7FFFFFFFll || n_tiles == 0 || n_buckets >= (1 << 20)) return WEPP_OK;
+    cudaStream_t st = h->stream;
+    DevBuf<uint64_t> key, key2, ukey;
+    DevBuf<uint32_t> val;
+    DevBuf<int32_t> ucount, nruns;
+    CU(key.ensure((size_t)R)); CU(key2.ensure((size_t)R)); CU(ukey.ensure((size_t)R));
+    CU(val.ensure((size_t)R)); CU(dp.order.ensure((size_t)R)); CU(ucount.ensure((size_t)R)); CU(nruns.ensure(1));
+    delta_keys_kernel<<<n_tiles, 256, 0, st>>>(dp.tiles.p, dp.buckets.p, dp.lists.p, dp.perm.p, h->d_rstart.p, h->d_rend.p, h->d_roff.p,
+                                               h->d_rpos.p, dp.post_off.p, dp.lpos_base.p, key.p, val.p);
+    CU(cudaGetLastError());
+    int key_bits = 24 + DP_COST_BITS;
+    while ((1ll << (key_bits - 24 - DP_COST_BITS)) < n_buckets) ++key_bits;
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, key.p, key2.p, val.p, dp.order.p, (int)R, 0, key_bits, st));
+    CU(h->d_cub_tmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp.p, tmp, key.p, key2.p, val.p, dp.order.p, (int)R, 0, key_bits, st));
+    delta_window_of_key_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(key2.p, R, key.p);   // the sort is done with key
+    CU(cudaGetLastError());
+    CU(cub::DeviceRunLengthEncode::Encode(nullptr, tmp, key.p, ukey.p, ucount.p, nruns.p, (int)R, st));
+    CU(h->d_cub_tmp.ensure(tmp));
+    CU(cub::DeviceRunLengthEncode::Encode(h->d_cub_tmp.p, tmp, key.p, ukey.p, ucount.p, nruns.p, (int)R, st));
+    int32_t n_groups = 0;
+    CU(cudaMemcpyAsync(&n_groups, nruns.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    // many distinct windows per read: the per-group work (base scores of every state) outweighs the sparse reads
+    const bool force = getenv("WEPP_DELTA_PLACE") && atoi(getenv("WEPP_DELTA_PLACE")) == 2;   // tests
+    if (n_groups <= 0 || (!force && (int64_t)n_groups * 2 > R + 64)) return WEPP_OK;
+    std::vector<uint64_t> hk((size_t)n_groups);
+    std::vector<int32_t> hc((size_t)n_groups);
+    CU(cudaMemcpyAsync(hk.data(), ukey.p, (size_t)n_groups * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(hc.data(), ucount.p, (size_t)n_groups * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::vector<DeltaGroup> groups((size_t)n_groups);
+    std::vector<DeltaUnit> units;
+    std::vector<int32_t> bucket_goff((size_t)n_buckets + 1, 0), list_goff((size_t)n_lists + 1, 0), list_gids((size_t)n_groups);
+    int64_t base_total = 0, first = 0;
+    for (int g = 0; g < n_groups; ++g) {
+        DeltaGroup& dg = groups[(size_t)g];
+        dg.bucket = (int32_t)(hk[(size_t)g] >> 24);
+        dg.list = pl.buckets[(size_t)dg.bucket].list;
+        dg.a_rel = (int32_t)((hk[(size_t)g] >> 12) & 0xFFFu);
+        dg.b_rel = (int32_t)(hk[(size_t)g] & 0xFFFu);
+        dg.m0 = 0;
+        dg.pad = 0;
+        dg.base_off = base_total;
+        const int64_t s_n = dp.h_state_first[(size_t)dg.list + 1] - dp.h_state_first[(size_t)dg.list];
+        base_total += (s_n + 15) & ~15ll;
+        ++bucket_goff[(size_t)dg.bucket + 1];
+        ++list_goff[(size_t)dg.list + 1];
+        for (int32_t o = 0; o < hc[(size_t)g];) {   // units of DP_UNIT reads; a remainder of up to 2 * DP_UNIT stays whole
+            const int32_t left = hc[(size_t)g] - o;
+            const int32_t take = left <= 2 * DP_UNIT ? left : DP_UNIT;
+            units.push_back(DeltaUnit{g, (int32_t)(first + o), take, 0});
+            o += take;
+        }
+        first += hc[(size_t)g];
+    }
+    if (base_total > (8ll << 30)) return WEPP_OK;
+    for (int b = 0; b < n_buckets; ++b) bucket_goff[(size_t)b + 1] += bucket_goff[(size_t)b];
+    for (int l = 0; l < n_lists; ++l) list_goff[(size_t)l + 1] += list_goff[(size_t)l];
+    {
+        std::vector<int32_t> cur(list_goff.begin(), list_goff.end() - 1);
+        for (int g = 0; g < n_groups; ++g) list_gids[(size_t)cur[(size_t)groups[(size_t)g].list]++] = g;
+    }
+    CU(upload(dp.groups, groups, st));
+    CU(upload(dp.units, units, st));
+    CU(upload(dp.bucket_goff, bucket_goff, st));
+    CU(upload(dp.list_goff, list_goff, st));
+    CU(upload(dp.list_gids, list_gids, st));
+    CU(dp.base.ensure((size_t)std::max<int64_t>(base_total, 16)));
+    CU(dp.whist.ensure((size_t)n_groups * DP_BINS));
+    CU(dp.Gw.ensure((size_t)n_groups * DP_BINS));
+    CU(dp.Gc.ensure((size_t)n_groups * DP_BINS));
+    CU(cudaMemsetAsync(dp.whist.p, 0, (size_t)n_groups * DP_BINS * 4, st));
+    CU(cudaMemsetAsync(dp.base.p, 0, (size_t)std::max<int64_t>(base_total, 16), st));
+    WindowBaseParams wb = {};
+    wb.state_ent = dp.state_ent.p; wb.state_eoff = dp.state_eoff.p; wb.state_first = dp.state_first.p;
+    wb.list_goff = dp.list_goff.p; wb.list_gids = dp.list_gids.p; wb.groups = dp.groups.p; wb.base = dp.base.p; wb.whist = dp.whist.p;
+    dim3 grid((unsigned)((dp.max_list_states + 255) / 256), (unsigned)n_lists);
+    window_base_kernel<<<grid, 256, 0, st>>>(wb);
+    CU(cudaGetLastError());
+    window_m0_kernel<<<(n_groups + 255) / 256, 256, 0, st>>>(dp.whist.p, n_groups, dp.groups.p);
+    CU(cudaGetLastError());
+    // byte scratch in global memory for the reads with many mutations: one area per warp of the persistent grid
+    const int64_t words = ((int64_t)dp.max_list_states + 3) / 4 + 4;
+    const size_t need = (size_t)h->n_sms * DP_WARPS * (size_t)words;
+    if (need > dp.gscratch.cap) {
+        CU(dp.gscratch.ensure(need));
+        CU(cudaMemsetAsync(dp.gscratch.p, 0, dp.gscratch.cap * 4, st));   // the kernel leaves it zero
+    }
+    dp.gscratch_words = words;
+    CU(cudaStreamSynchronize(st));   // the host vectors and temporaries above go out of scope
+    dp.n_groups = n_groups;
+    dp.n_units = (int32_t)units.size();
+    dp.delta_groups_usable = true;
+    if (getenv("WEPP_TIMING") && atoi(getenv("WEPP_TIMING")) != 0)
+        fprintf(stderr, "[wepp timing] window groups: %d groups, %d units, %.1f MB of base scores\n", n_groups, dp.n_units, base_total / 1e6);
     return WEPP_OK;
 }
 
@@ -516,12 +701,58 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         if (rc) return rc;
         by_states = dp.states_usable;
     }
+    // ... and, when the reads share few distinct windows, by sparse corrections per read (delta_place.cuh);
+    // WEPP_DELTA_PLACE=0 keeps state_place_kernel
+    const bool delta_env = !(getenv("WEPP_DELTA_PLACE") && atoi(getenv("WEPP_DELTA_PLACE")) == 0);
+    bool by_delta = false;
+    if (by_states && delta_env && dp.delta_usable) {
+        rc = build_delta_groups(h, dp);
+        if (rc) return rc;
+        by_delta = dp.delta_groups_usable;
+    }
+    h->stats.place_path = by_delta ? 2 : (by_states ? 1 : 0);
+    h->stats.n_states = by_states ? dp.n_states : 0;
+    h->stats.n_window_groups = by_delta ? dp.n_groups : 0;
     CU(cudaEventRecord(h->ev[0], h->stream));
     if (by_states) {
         CU(h->d_saccS.ensure((size_t)std::max<int64_t>(dp.sacc_total, 1)));
         CU(h->d_saccC.ensure((size_t)std::max<int64_t>(dp.sacc_total, 1)));
         CU(cudaMemsetAsync(h->d_saccS.p, 0, (size_t)dp.sacc_total * sizeof(double), h->stream));
         CU(cudaMemsetAsync(h->d_saccC.p, 0, (size_t)dp.sacc_total * sizeof(int32_t), h->stream));
+    }
+    if (by_delta) {
+        CU(cudaMemsetAsync(dp.Gw.p, 0, (size_t)dp.n_groups * DP_BINS * sizeof(double), h->stream));
+        CU(cudaMemsetAsync(dp.Gc.p, 0, (size_t)dp.n_groups * DP_BINS * sizeof(int32_t), h->stream));
+        DeltaPlaceParams dq = {};
+        dq.units = dp.units.p; dq.n_units = dp.n_units; dq.unit_counter = h->d_tile_counter.p;
+        dq.groups = dp.groups.p; dq.base = dp.base.p; dq.whist = dp.whist.p; dq.post = dp.post.p; dq.post_off = dp.post_off.p;
+        dq.lpos_base = dp.lpos_base.p; dq.state_first = dp.state_first.p; dq.list_desc = dp.lists.p; dq.sacc_off = dp.sacc_off.p;
+        dq.order = dp.order.p; dq.degree = h->d_rdegree.p; dq.rm_off = h->d_roff.p; dq.rm_pos = h->d_rpos.p; dq.rm_code = h->d_rcode.p;
+        dq.max_pars = h->d_maxpars.p; dq.mult = h->d_mult.p; dq.saccS = h->d_saccS.p; dq.saccC = h->d_saccC.p;
+        dq.Gw = dp.Gw.p; dq.Gc = dp.Gc.p; dq.gscratch = dp.gscratch.p; dq.gscratch_words = dp.gscratch_words;
+        // shared memory: fixed areas + the widest list's base scores + 16 warps' nibble scratch, as far as it fits
+        const int64_t s_max = dp.max_list_states;
+        const int64_t want = DP_FIXED + ((s_max + 15) & ~15ll) + (int64_t)DP_WARPS * ((((s_max + 7) / 8 * 4) + 15) & ~15ll);
+        const int smem = (int)std::min<int64_t>(want, (int64_t)h->smem_optin);
+        dq.smem_bytes = smem;
+        dq.cand_cap = DP_CAND;
+        if (getenv("WEPP_DELTA_CAND")) dq.cand_cap = std::max(0, std::min(DP_CAND, atoi(getenv("WEPP_DELTA_CAND"))));
+        CU(cudaFuncSetAttribute(delta_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int grid_dp = std::max(1, std::min(dp.n_units, h->n_sms));
+        delta_place_kernel<<<grid_dp, DP_WARPS * 32, smem, h->stream>>>(dq);
+        CU(cudaGetLastError());
+        dim3 fgrid((unsigned)std::min<int64_t>((s_max + 255) / 256, 1024), (unsigned)pl.buckets.size());
+        delta_finalize_kernel<<<fgrid, 256, 0, h->stream>>>(dp.groups.p, dp.bucket_goff.p, dp.state_first.p, dp.buckets.p, dp.base.p,
+                                                           dp.Gw.p, dp.Gc.p, dp.sacc_off.p, h->d_saccS.p, h->d_saccC.p);
+        CU(cudaGetLastError());
+        int max_n = 0;
+        for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
+        dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
+        state_scatter_kernel<<<grid, 256, 0, h->stream>>>(dp.lists.p, dp.buckets.p, dp.sid.p, dp.state_first.p, dp.sacc_off.p,
+                                                          h->d_saccS.p, h->d_saccC.p, h->d_accS.p, h->d_accC.p);
+        CU(cudaGetLastError());
+        launches += 3;
+    } else if (by_states) {
         StatePlaceParams sp = {};
         sp.state_ent = dp.state_ent.p; sp.state_eoff = dp.state_eoff.p; sp.state_first = dp.state_first.p;
         sp.sacc_off = dp.sacc_off.p; sp.list_desc = dp.lists.p; sp.buckets = dp.buckets.p; sp.tiles = dp.tiles.p;
