@@ -49,7 +49,7 @@ constexpr int DP_VOFF = SW_MAX_ACTIVE;   // base <= SW_MAX_ACTIVE and red <= 2 *
 constexpr int DP_CAND = 192;          // candidate queue entries per warp
 constexpr int DP_FAST_MUTS = 7;       // reads with more mutations use byte scratch in global memory (nibbles hold <= 15)
 constexpr int DP_UNIT = 256;          // reads per work unit (a group of up to 2 * DP_UNIT reads stays whole)
-constexpr int DP_FIXED = 16 + DP_BINS * 4 + DP_WARPS * 128 * 4 + DP_WARPS * DP_CAND * 4;   // ctrl, whist, mv, cand
+constexpr int DP_FIXED = 16 + DP_BINS * 4 + DP_WARPS * DP_BINS * 4 + DP_WARPS * DP_CAND * 4;   // ctrl, whist, mv, cand
 static_assert(DP_VOFF + SW_MAX_ACTIVE + 1 <= DP_BINS, "score bins");
 constexpr uint32_t DP_X_NONE = 7u;    // allele class of a state entry that equals no read allele (IUPAC union)
 
@@ -258,59 +258,58 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
         for (int j = 0; j < cnt; ++j) {
             const uint32_t c = __shfl_sync(FULL, my_code, j);
             const uint32_t lo = __shfl_sync(FULL, my_lo, j), hi = __shfl_sync(FULL, my_hi, j);
-            uint2 nxt = make_uint2(0u, 0u);
-            if (lo + lane < hi) nxt = __ldg(p.post + lo + lane);
-            for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
-                const uint2 e = nxt;
-                const bool in = i0 + lane < hi;
-                nxt = make_uint2(0u, 0u);
-                if (i0 + 32 + lane < hi) nxt = __ldg(p.post + i0 + 32 + lane);
-                const uint32_t s = e.x & 0xFFFFFFu;
-                const int d = (int)((e.x >> 27) & 1u) + (int)(((e.x >> 24) & 7u) == c);   // delta[ref] - delta[c]
-                const bool act = in && d > 0;
-                uint32_t key = 0xFFFFFFFFu;
-                int v_new = DP_BINS;
-                if (act) {
-                    int oldred;
-                    if (FAST) {
-                        const int sh = (int)(s & 7u) * 4;
-                        oldred = (int)((atomicAdd(scr + (s >> 3), (uint32_t)d << sh) >> sh) & 15u);
-                    } else {
-                        const int sh = (int)(s & 3u) * 8;
-                        oldred = (int)((atomicAdd(scr + (s >> 2), (uint32_t)d << sh) >> sh) & 255u);
-                    }
-                    const int v_old = (int)base_s[s] + DP_VOFF - oldred;
-                    key = ((uint32_t)v_old << 1) | (uint32_t)(d - 1);
-                    v_new = v_old - d;
+            // two chunks of 32 postings per iteration (independent dependency chains), loaded one iteration ahead
+            uint2 nxt[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                nxt[h] = make_uint2(0u, 0u);
+                if (lo + 32 * h + lane < hi) nxt[h] = __ldg(p.post + lo + 32 * h + lane);
+            }
+            for (uint32_t i0 = lo; i0 < hi; i0 += 64) {
+                uint2 e[2];
+                bool act[2], is_c[2];
+                uint32_t s[2];
+                int d[2], v_new[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    e[h] = nxt[h];
+                    const bool in = i0 + 32 * h + lane < hi;
+                    nxt[h] = make_uint2(0u, 0u);
+                    if (i0 + 64 + 32 * h + lane < hi) nxt[h] = __ldg(p.post + i0 + 64 + 32 * h + lane);
+                    s[h] = e[h].x & 0xFFFFFFu;
+                    d[h] = (int)((e[h].x >> 27) & 1u) + (int)(((e[h].x >> 24) & 7u) == c);   // delta[ref] - delta[c]
+                    act[h] = in && d[h] > 0;
                 }
-                // the moves "u nodes leave bin v_old by d", summed per distinct (v_old, d) of the warp; the postings
-                // are sorted so that most of the time there is one
-                uint32_t rem = __ballot_sync(FULL, act);
-                if (rem) {
-                    const int ld0 = __ffs(rem) - 1;
-                    const uint32_t k0 = __shfl_sync(FULL, key, ld0);
-                    const uint32_t other = __ballot_sync(FULL, act && key != k0);
-                    const int sum0 = __reduce_add_sync(FULL, (act && key == k0) ? (int)e.y : 0);
-                    if (lane == ld0) mv[k0] += sum0;
-                    rem = other;
-                    while (rem) {
-                        const int ld = __ffs(rem) - 1;
-                        const uint32_t k = __shfl_sync(FULL, key, ld);
-                        const bool mine = key == k;
-                        const uint32_t m = __ballot_sync(FULL, mine);
-                        const int sum = __reduce_add_sync(FULL, mine ? (int)e.y : 0);
-                        if (lane == ld) mv[k] += sum;
-                        rem &= ~m;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    v_new[h] = DP_BINS;
+                    if (act[h]) {
+                        int oldred;
+                        if (FAST) {
+                            const int sh = (int)(s[h] & 7u) * 4;
+                            oldred = (int)((atomicAdd(scr + (s[h] >> 3), (uint32_t)d[h] << sh) >> sh) & 15u);
+                        } else {
+                            const int sh = (int)(s[h] & 3u) * 8;
+                            oldred = (int)((atomicAdd(scr + (s[h] >> 2), (uint32_t)d[h] << sh) >> sh) & 255u);
+                        }
+                        v_new[h] = (int)base_s[s[h]] + DP_VOFF - oldred - d[h];
                     }
+                    // Only the bins at or below the window's own minimum m0 can hold the read's minimum (a touched
+                    // state only moves down), so only hits that end there are tracked: the state's nodes leave the
+                    // tracked bin they were in (if any) and enter the new one, and the state is remembered — the
+                    // read's weight goes to it once the minimum is known.  ~30 such hits per read against ~700 hits.
+                    is_c[h] = v_new[h] <= dg.m0;
                 }
-                if (FAST) {
-                    // a touched state that ends at the read's minimum is at or below the window's own minimum
-                    // after its last hit: remember those, the weights go to them once the minimum is known
-                    const bool is_c = act && v_new <= dg.m0;
-                    const uint32_t cm = __ballot_sync(FULL, is_c);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint32_t cm = __ballot_sync(FULL, is_c[h]);
                     if (cm) {
-                        const int slot = n_cand + __popc(cm & ((1u << lane) - 1u));
-                        if (is_c && slot < p.cand_cap) cand[slot] = s;
+                        if (is_c[h]) {
+                            if (v_new[h] + d[h] <= dg.m0) atomicSub(&mv[v_new[h] + d[h]], (int)e[h].y);
+                            atomicAdd(&mv[v_new[h]], (int)e[h].y);
+                            const int slot = n_cand + __popc(cm & ((1u << lane) - 1u));
+                            if (FAST && slot < p.cand_cap) cand[slot] = s[h];
+                        }
                         n_cand += __popc(cm);
                     }
                 }
@@ -318,18 +317,16 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
         }
     }
     __syncwarp();
-    // histogram of the read = the window's + the moves; minimum and its countable nodes
+    // occupied bins at or below m0 = the window's (m0 itself) + the tracked moves; minimum and its countable nodes
     int tot[2];
 #pragma unroll
     for (int hf = 0; hf < 2; ++hf) {
         const int v = lane + 32 * hf;
-        int t = whist_s[v] - mv[2 * v] - mv[2 * v + 1];
-        if (v + 1 < DP_BINS) t += mv[2 * (v + 1)];
-        if (v + 2 < DP_BINS) t += mv[2 * (v + 2) + 1];
-        tot[hf] = t;
+        tot[hf] = v <= dg.m0 ? whist_s[v] + mv[v] : 0;
     }
     __syncwarp();
-    mv[lane] = 0; mv[lane + 32] = 0; mv[lane + 64] = 0; mv[lane + 96] = 0;
+    mv[lane] = 0;
+    mv[lane + 32] = 0;
     const uint32_t o0 = __ballot_sync(FULL, tot[0] > 0), o1 = __ballot_sync(FULL, tot[1] > 0);
     const int mV = o0 ? __ffs(o0) - 1 : (o1 ? 32 + __ffs(o1) - 1 : DP_VOFF);
     const int n_epp = (o0 | o1) ? __shfl_sync(FULL, mV < 32 ? tot[0] : tot[1], mV & 31) : 0;
@@ -395,13 +392,13 @@ __global__ void __launch_bounds__(DP_WARPS * 32, 1) delta_place_kernel(const Del
     int* ctrl = reinterpret_cast<int*>(smem);                       // [0] unit, [1] next read of the unit
     int* whist_s = reinterpret_cast<int*>(smem + 16);
     int* mv_all = whist_s + DP_BINS;
-    uint32_t* cand_all = reinterpret_cast<uint32_t*>(mv_all + DP_WARPS * 128);
+    uint32_t* cand_all = reinterpret_cast<uint32_t*>(mv_all + DP_WARPS * DP_BINS);
     unsigned char* base_s = smem + DP_FIXED;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xFFFFFFFFu;
-    int* mv = mv_all + warp * 128;
+    int* mv = mv_all + warp * DP_BINS;
     uint32_t* cand = cand_all + warp * DP_CAND;
-    for (int i = threadIdx.x; i < DP_WARPS * 128; i += blockDim.x) mv_all[i] = 0;
+    for (int i = threadIdx.x; i < DP_WARPS * DP_BINS; i += blockDim.x) mv_all[i] = 0;
     uint32_t* gscr = p.gscratch + ((size_t)blockIdx.x * DP_WARPS + warp) * (size_t)p.gscratch_words;
     int scr_list = -1;   // the list this warp's nibble scratch is laid out (and zero) for
     for (;;) {
