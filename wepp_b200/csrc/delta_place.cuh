@@ -46,10 +46,10 @@ namespace wepp {
 constexpr int DP_WARPS = 16;          // warps per CTA (one CTA per SM: the shared memory is the limit)
 constexpr int DP_BINS = 64;           // score bins: bin = base - red + DP_VOFF
 constexpr int DP_VOFF = SW_MAX_ACTIVE;   // base <= SW_MAX_ACTIVE and red <= 2 * base
-constexpr int DP_CAND = 192;          // candidate queue entries per warp
+constexpr int DP_CAND_MIN = 64;       // candidate queue entries per warp: at least this many (the rest of the shared memory is split)
 constexpr int DP_FAST_MUTS = 7;       // reads with more mutations use byte scratch in global memory (nibbles hold <= 15)
 constexpr int DP_UNIT = 256;          // reads per work unit (a group of up to 2 * DP_UNIT reads stays whole)
-constexpr int DP_FIXED = 16 + DP_BINS * 4 + DP_WARPS * DP_BINS * 4 + DP_WARPS * DP_CAND * 4;   // ctrl, whist, mv, cand
+constexpr int DP_FIXED = 16 + DP_BINS * 4 + DP_WARPS * DP_BINS * 4;   // ctrl, whist, mv
 static_assert(DP_VOFF + SW_MAX_ACTIVE + 1 <= DP_BINS, "score bins");
 constexpr uint32_t DP_X_NONE = 7u;    // allele class of a state entry that equals no read allele (IUPAC union)
 
@@ -212,7 +212,7 @@ struct DeltaPlaceParams {
     const DeltaUnit* units;
     int32_t n_units;
     int32_t smem_bytes;           // dynamic shared memory of the launch
-    int32_t cand_cap;             // candidate queue entries in use (<= DP_CAND; tests shrink it to reach the re-walk)
+    int32_t cand_cap;             // upper bound on the candidate queue entries per warp (tests shrink it to reach the re-walk)
     int* unit_counter;
     const DeltaGroup* groups;
     const uint8_t* base;
@@ -242,7 +242,7 @@ struct DeltaPlaceParams {
 template <bool FAST>
 __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGroup& dg, int32_t rid, int lane,
                                         const unsigned char* base_s, uint32_t* scr, int scr_words, int* mv, uint32_t* cand,
-                                        const int* whist_s, int lp, int64_t so, double (&gw)[2], int (&gc)[2]) {
+                                        int cand_cap, const int* whist_s, int lp, int64_t so, double (&gw)[2], int (&gc)[2]) {
     const unsigned FULL = 0xFFFFFFFFu;
     const int64_t ra = p.rm_off[rid], rb = p.rm_off[rid + 1];
     const int nm = (int)(rb - ra);
@@ -308,7 +308,7 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
                             if (v_new[h] + d[h] <= dg.m0) atomicSub(&mv[v_new[h] + d[h]], (int)e[h].y);
                             atomicAdd(&mv[v_new[h]], (int)e[h].y);
                             const int slot = n_cand + __popc(cm & ((1u << lane) - 1u));
-                            if (FAST && slot < p.cand_cap) cand[slot] = s[h];
+                            if (FAST && slot < cand_cap) cand[slot] = s[h];
                         }
                         n_cand += __popc(cm);
                     }
@@ -343,7 +343,7 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
         gc[mV >> 5] += deg;
     }
     // touched states at the minimum; scratch back to zero
-    if (FAST && n_cand <= p.cand_cap) {
+    if (FAST && n_cand <= cand_cap) {
         for (int i = lane; i < n_cand; i += 32) {
             const uint32_t s = cand[i];
             const int sh = (int)(s & 7u) * 4;
@@ -366,8 +366,11 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
             const int cnt = min(32, nm - j0);
             for (int j = 0; j < cnt; ++j) {
                 const uint32_t lo = __shfl_sync(FULL, my_lo, j), hi = __shfl_sync(FULL, my_hi, j);
+                uint32_t nx = 0u;
+                if (lo + lane < hi) nx = __ldg(&p.post[lo + lane].x);
                 for (uint32_t i = lo + lane; i < hi; i += 32) {
-                    const uint32_t s = __ldg(p.post + i).x & 0xFFFFFFu;
+                    const uint32_t s = nx & 0xFFFFFFu;
+                    if (i + 32 < hi) nx = __ldg(&p.post[i + 32].x);
                     int red;
                     if (FAST) {
                         const int sh = (int)(s & 7u) * 4;
@@ -392,12 +395,10 @@ __global__ void __launch_bounds__(DP_WARPS * 32, 1) delta_place_kernel(const Del
     int* ctrl = reinterpret_cast<int*>(smem);                       // [0] unit, [1] next read of the unit
     int* whist_s = reinterpret_cast<int*>(smem + 16);
     int* mv_all = whist_s + DP_BINS;
-    uint32_t* cand_all = reinterpret_cast<uint32_t*>(mv_all + DP_WARPS * DP_BINS);
     unsigned char* base_s = smem + DP_FIXED;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned FULL = 0xFFFFFFFFu;
     int* mv = mv_all + warp * DP_BINS;
-    uint32_t* cand = cand_all + warp * DP_CAND;
     for (int i = threadIdx.x; i < DP_WARPS * DP_BINS; i += blockDim.x) mv_all[i] = 0;
     uint32_t* gscr = p.gscratch + ((size_t)blockIdx.x * DP_WARPS + warp) * (size_t)p.gscratch_words;
     int scr_list = -1;   // the list this warp's nibble scratch is laid out (and zero) for
@@ -415,7 +416,9 @@ __global__ void __launch_bounds__(DP_WARPS * 32, 1) delta_place_kernel(const Del
         const int s_n = p.state_first[dg.list + 1] - p.state_first[dg.list];
         const int s_pad = (s_n + 15) & ~15;
         const int stride = ((s_n + 7) / 8 * 4 + 15) & ~15;          // nibble scratch bytes per warp
-        const int aw = min(DP_WARPS, (p.smem_bytes - DP_FIXED - s_pad) / stride);
+        const int aw = min(DP_WARPS, (p.smem_bytes - DP_FIXED - s_pad) / (stride + DP_CAND_MIN * 4));
+        // the shared memory the scratch areas leave is the warps' candidate queues
+        const int cand_cap = min(p.cand_cap, (p.smem_bytes - DP_FIXED - s_pad - aw * stride) / (aw * 16) * 4);
         {   // the window's base scores and histogram
             const uint4* src = reinterpret_cast<const uint4*>(p.base + dg.base_off);
             uint4* dst = reinterpret_cast<uint4*>(base_s);
@@ -423,6 +426,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32, 1) delta_place_kernel(const Del
             if (threadIdx.x < DP_BINS) whist_s[threadIdx.x] = p.whist[(size_t)du.group * DP_BINS + threadIdx.x];
         }
         uint32_t* scr = reinterpret_cast<uint32_t*>(base_s + s_pad + (size_t)warp * stride);
+        uint32_t* cand = reinterpret_cast<uint32_t*>(base_s + s_pad + (size_t)aw * stride) + (size_t)warp * cand_cap;
         if (warp < aw && dg.list != scr_list) {   // another list: the layout moved, its scratch area starts out zero
             uint4* z = reinterpret_cast<uint4*>(scr);
             for (int i = lane; i < stride / 16; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -441,8 +445,8 @@ __global__ void __launch_bounds__(DP_WARPS * 32, 1) delta_place_kernel(const Del
                 if (r >= du.count) break;
                 const int32_t rid = (int32_t)p.order[du.first + r];
                 const int nm = (int)(p.rm_off[rid + 1] - p.rm_off[rid]);
-                if (nm <= DP_FAST_MUTS) dp_read<true>(p, dg, rid, lane, base_s, scr, stride / 4, mv, cand, whist_s, lp, so, gw, gc);
-                else dp_read<false>(p, dg, rid, lane, base_s, gscr, 0, mv, cand, whist_s, lp, so, gw, gc);
+                if (nm <= DP_FAST_MUTS) dp_read<true>(p, dg, rid, lane, base_s, scr, stride / 4, mv, cand, cand_cap, whist_s, lp, so, gw, gc);
+                else dp_read<false>(p, dg, rid, lane, base_s, gscr, 0, mv, cand, 0, whist_s, lp, so, gw, gc);
             }
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {

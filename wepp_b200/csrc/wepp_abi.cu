@@ -490,7 +490,7 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
             CU(cudaStreamSynchronize(st));
             // shared memory of delta_place_kernel: the widest list's base scores + at least 4 warps' nibble scratch
             const int64_t s_max = dp.max_list_states;
-            const int64_t need = DP_FIXED + ((s_max + 15) & ~15ll) + 4 * ((((s_max + 7) / 8 * 4) + 15) & ~15ll);
+            const int64_t need = DP_FIXED + ((s_max + 15) & ~15ll) + 4 * (((((s_max + 7) / 8 * 4) + 15) & ~15ll) + DP_CAND_MIN * 4);
             dp.delta_usable = h_bad == 0 && need <= (int64_t)h->smem_optin;
             if (getenv("WEPP_TIMING") && atoi(getenv("WEPP_TIMING")) != 0)
                 fprintf(stderr, "[wepp timing] postings: %lld slots, %lld entries, tables %s, widest list %lld states, shared memory %lld of %lld -> %s\n",
@@ -732,11 +732,11 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         dq.Gw = dp.Gw.p; dq.Gc = dp.Gc.p; dq.gscratch = dp.gscratch.p; dq.gscratch_words = dp.gscratch_words;
         // shared memory: fixed areas + the widest list's base scores + 16 warps' nibble scratch, as far as it fits
         const int64_t s_max = dp.max_list_states;
-        const int64_t want = DP_FIXED + ((s_max + 15) & ~15ll) + (int64_t)DP_WARPS * ((((s_max + 7) / 8 * 4) + 15) & ~15ll);
-        const int smem = (int)std::min<int64_t>(want, (int64_t)h->smem_optin);
+        // (one CTA per SM: all of it — what the scratch areas leave is the warps' candidate queues)
+        const int smem = (int)h->smem_optin;
         dq.smem_bytes = smem;
-        dq.cand_cap = DP_CAND;
-        if (getenv("WEPP_DELTA_CAND")) dq.cand_cap = std::max(0, std::min(DP_CAND, atoi(getenv("WEPP_DELTA_CAND"))));
+        dq.cand_cap = 1 << 20;
+        if (getenv("WEPP_DELTA_CAND")) dq.cand_cap = std::max(0, atoi(getenv("WEPP_DELTA_CAND")));
         CU(cudaFuncSetAttribute(delta_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         const int grid_dp = std::max(1, std::min(dp.n_units, h->n_sms));
         delta_place_kernel<<<grid_dp, DP_WARPS * 32, smem, h->stream>>>(dq);
