@@ -151,6 +151,31 @@ __global__ void delta_window_of_key_kernel(const uint64_t* __restrict__ key, int
     if (i < n) window[i] = key[i] >> DP_COST_BITS;
 }
 
+// What the placement kernel reads per read, in sorted order: {read index, degree, first mutation, mutations | non-N
+// mutations << 16}; and per read mutation (at its index in the caller's mutation arrays) the posting range it
+// touches: {first posting, postings | allele class << 28}.
+__global__ void delta_records_kernel(const uint64_t* __restrict__ sorted_key, const uint32_t* __restrict__ order, int64_t n,
+                                     const BucketDesc* __restrict__ buckets, const ListDesc* __restrict__ list_desc,
+                                     const int32_t* __restrict__ lpos_base, const uint32_t* __restrict__ post_off,
+                                     const int32_t* __restrict__ degree, const int64_t* __restrict__ rm_off,
+                                     const int32_t* __restrict__ rm_pos, const uint8_t* __restrict__ rm_code,
+                                     uint4* __restrict__ rec, uint2* __restrict__ mrec) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t rid = order[i];
+    const int32_t list = buckets[(int32_t)(sorted_key[i] >> (24 + DP_COST_BITS))].list;
+    const int32_t b0 = list_desc[list].b0, lp = lpos_base[list];
+    const int64_t a = rm_off[rid], b = rm_off[rid + 1];
+    uint32_t non_n = 0;
+    for (int64_t k = a; k < b; ++k) {
+        const uint32_t c = rm_code[k];
+        non_n += c <= 4u;
+        const uint32_t lo = post_off[lp + rm_pos[k] - b0], hi = post_off[lp + rm_pos[k] - b0 + 1];
+        mrec[k] = make_uint2(lo, (hi - lo) | (c << 28));
+    }
+    rec[i] = make_uint4(rid, (uint32_t)degree[rid], (uint32_t)a, (uint32_t)(b - a) | (non_n << 16));
+}
+
 struct WindowBaseParams {
     const Entry* state_ent;
     const int64_t* state_eoff;
@@ -218,16 +243,10 @@ struct DeltaPlaceParams {
     const uint8_t* base;
     const int32_t* whist;
     const uint2* post;
-    const uint32_t* post_off;
-    const int32_t* lpos_base;
     const int32_t* state_first;
-    const ListDesc* list_desc;
     const int64_t* sacc_off;
-    const uint32_t* order;        // reads sorted by (bucket, window)
-    const int32_t* degree;
-    const int64_t* rm_off;
-    const int32_t* rm_pos;
-    const uint8_t* rm_code;
+    const uint4* rec;             // per read in (bucket, window, heaviest first) order: delta_records_kernel
+    const uint2* mrec;            // per read mutation: the posting range it touches
     int32_t* max_pars;
     int32_t* mult;
     double* saccS;
@@ -238,50 +257,51 @@ struct DeltaPlaceParams {
     int64_t gscratch_words;
 };
 
-// FAST: nibble scratch in shared memory + candidate queue; else byte scratch in global memory, postings re-walked
+// One read by one warp.  FAST: nibble scratch in shared memory + candidate queue; else byte scratch in global memory
+// and the postings are walked again for the weights.  rec / m = the read's record and this lane's mutation record
+// (mutations 0..31; reads with more fetch the rest here).
+constexpr int DP_U = 4;   // chunks of 32 postings per loop iteration (independent dependency chains)
 template <bool FAST>
-__device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGroup& dg, int32_t rid, int lane,
+__device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGroup& dg, const uint4 rec, const uint2 m, int lane,
                                         const unsigned char* base_s, uint32_t* scr, int scr_words, int* mv, uint32_t* cand,
-                                        int cand_cap, const int* whist_s, int lp, int64_t so, double (&gw)[2], int (&gc)[2]) {
+                                        int cand_cap, const int* whist_s, int64_t so, double (&gw)[2], int (&gc)[2]) {
     const unsigned FULL = 0xFFFFFFFFu;
-    const int64_t ra = p.rm_off[rid], rb = p.rm_off[rid + 1];
-    const int nm = (int)(rb - ra);
-    const int b0 = p.list_desc[dg.list].b0;
-    int k_non_n = 0, n_cand = 0;
+    const int nm = (int)(rec.w & 0xFFFFu), k_non_n = (int)(rec.w >> 16);
+    int* n_cand_s = mv + (DP_BINS - 1);   // bins above DP_VOFF + SW_MAX_ACTIVE are never used: the last one counts candidates
     for (int j0 = 0; j0 < nm; j0 += 32) {
-        const bool have = j0 + lane < nm;
-        const int my_pos = have ? p.rm_pos[ra + j0 + lane] - b0 : 0;
-        const uint32_t my_code = have ? p.rm_code[ra + j0 + lane] : 5u;
-        k_non_n += __popc(__ballot_sync(FULL, have && my_code <= 4u));   // seed set: non-N mutations
-        const uint32_t my_lo = have ? p.post_off[lp + my_pos] : 0u, my_hi = have ? p.post_off[lp + my_pos + 1] : 0u;
+        uint2 mm = m;
+        if (j0 > 0) {
+            mm = make_uint2(0u, 0u);
+            if (j0 + lane < nm) mm = __ldg(p.mrec + rec.z + j0 + lane);
+        }
         const int cnt = min(32, nm - j0);
         for (int j = 0; j < cnt; ++j) {
-            const uint32_t c = __shfl_sync(FULL, my_code, j);
-            const uint32_t lo = __shfl_sync(FULL, my_lo, j), hi = __shfl_sync(FULL, my_hi, j);
-            // two chunks of 32 postings per iteration (independent dependency chains), loaded one iteration ahead
-            uint2 nxt[2];
+            const uint32_t lo = __shfl_sync(FULL, mm.x, j), lc = __shfl_sync(FULL, mm.y, j);
+            const uint32_t hi = lo + (lc & 0x0FFFFFFFu), c = lc >> 28;
+            // DP_U chunks of 32 postings per iteration, loaded one iteration ahead
+            uint2 nxt[DP_U];
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            for (int h = 0; h < DP_U; ++h) {
                 nxt[h] = make_uint2(0u, 0u);
                 if (lo + 32 * h + lane < hi) nxt[h] = __ldg(p.post + lo + 32 * h + lane);
             }
-            for (uint32_t i0 = lo; i0 < hi; i0 += 64) {
-                uint2 e[2];
-                bool act[2], is_c[2];
-                uint32_t s[2];
-                int d[2], v_new[2];
+            for (uint32_t i0 = lo; i0 < hi; i0 += 32 * DP_U) {
+                uint2 e[DP_U];
+                bool act[DP_U];
+                uint32_t s[DP_U];
+                int d[DP_U], v_new[DP_U];
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < DP_U; ++h) {
                     e[h] = nxt[h];
                     const bool in = i0 + 32 * h + lane < hi;
                     nxt[h] = make_uint2(0u, 0u);
-                    if (i0 + 64 + 32 * h + lane < hi) nxt[h] = __ldg(p.post + i0 + 64 + 32 * h + lane);
+                    if (i0 + 32 * (DP_U + h) + lane < hi) nxt[h] = __ldg(p.post + i0 + 32 * (DP_U + h) + lane);
                     s[h] = e[h].x & 0xFFFFFFu;
                     d[h] = (int)((e[h].x >> 27) & 1u) + (int)(((e[h].x >> 24) & 7u) == c);   // delta[ref] - delta[c]
                     act[h] = in && d[h] > 0;
                 }
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
+                for (int h = 0; h < DP_U; ++h) {
                     v_new[h] = DP_BINS;
                     if (act[h]) {
                         int oldred;
@@ -294,23 +314,20 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
                         }
                         v_new[h] = (int)base_s[s[h]] + DP_VOFF - oldred - d[h];
                     }
-                    // Only the bins at or below the window's own minimum m0 can hold the read's minimum (a touched
-                    // state only moves down), so only hits that end there are tracked: the state's nodes leave the
-                    // tracked bin they were in (if any) and enter the new one, and the state is remembered — the
-                    // read's weight goes to it once the minimum is known.  ~30 such hits per read against ~700 hits.
-                    is_c[h] = v_new[h] <= dg.m0;
                 }
+                // Only the bins at or below the window's own minimum m0 can hold the read's minimum (a touched state
+                // only moves down), so only hits that end there are tracked: the state's nodes leave the tracked bin
+                // they were in (if any) and enter the new one, and the state is remembered — the read's weight goes
+                // to it once the minimum is known.  ~30 such hits per read against ~700 hits.
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const uint32_t cm = __ballot_sync(FULL, is_c[h]);
-                    if (cm) {
-                        if (is_c[h]) {
-                            if (v_new[h] + d[h] <= dg.m0) atomicSub(&mv[v_new[h] + d[h]], (int)e[h].y);
-                            atomicAdd(&mv[v_new[h]], (int)e[h].y);
-                            const int slot = n_cand + __popc(cm & ((1u << lane) - 1u));
-                            if (FAST && slot < cand_cap) cand[slot] = s[h];
+                for (int h = 0; h < DP_U; ++h) {
+                    if (v_new[h] <= dg.m0) {
+                        if (v_new[h] + d[h] <= dg.m0) atomicSub(&mv[v_new[h] + d[h]], (int)e[h].y);
+                        atomicAdd(&mv[v_new[h]], (int)e[h].y);
+                        if (FAST) {
+                            const int slot = atomicAdd(n_cand_s, 1);
+                            if (slot < cand_cap) cand[slot] = s[h];
                         }
-                        n_cand += __popc(cm);
                     }
                 }
             }
@@ -324,6 +341,7 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
         const int v = lane + 32 * hf;
         tot[hf] = v <= dg.m0 ? whist_s[v] + mv[v] : 0;
     }
+    const int n_cand = *n_cand_s;
     __syncwarp();
     mv[lane] = 0;
     mv[lane + 32] = 0;
@@ -331,12 +349,12 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
     const int mV = o0 ? __ffs(o0) - 1 : (o1 ? 32 + __ffs(o1) - 1 : DP_VOFF);
     const int n_epp = (o0 | o1) ? __shfl_sync(FULL, mV < 32 ? tot[0] : tot[1], mV & 31) : 0;
     const int pars = k_non_n + mV - DP_VOFF;
-    const int deg = p.degree[rid];
+    const int deg = (int)rec.y;
     double wgt = 0.0;
     if (n_epp > 0) wgt = (double)deg / ((double)(1 + pars) * (double)n_epp);   // node_score, initial_filter.hpp:54-57
     if (lane == 0) {
-        p.max_pars[rid] = pars;
-        p.mult[rid] = n_epp;
+        p.max_pars[rec.x] = pars;
+        p.mult[rec.x] = n_epp;
     }
     if (n_epp > 0 && lane == (mV & 31)) {
         gw[mV >> 5] += wgt;
@@ -360,12 +378,11 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
         }
     } else {
         for (int j0 = 0; j0 < nm; j0 += 32) {
-            const bool have = j0 + lane < nm;
-            const int my_pos = have ? p.rm_pos[ra + j0 + lane] - b0 : 0;
-            const uint32_t my_lo = have ? p.post_off[lp + my_pos] : 0u, my_hi = have ? p.post_off[lp + my_pos + 1] : 0u;
+            uint2 mm = make_uint2(0u, 0u);
+            if (j0 + lane < nm) mm = __ldg(p.mrec + rec.z + j0 + lane);
             const int cnt = min(32, nm - j0);
             for (int j = 0; j < cnt; ++j) {
-                const uint32_t lo = __shfl_sync(FULL, my_lo, j), hi = __shfl_sync(FULL, my_hi, j);
+                const uint32_t lo = __shfl_sync(FULL, mm.x, j), hi = lo + (__shfl_sync(FULL, mm.y, j) & 0x0FFFFFFFu);
                 uint32_t nx = 0u;
                 if (lo + lane < hi) nx = __ldg(&p.post[lo + lane].x);
                 for (uint32_t i = lo + lane; i < hi; i += 32) {
@@ -434,19 +451,34 @@ __global__ void __launch_bounds__(DP_WARPS * 32, 1) delta_place_kernel(const Del
         scr_list = warp < aw ? dg.list : -1;
         __syncthreads();
         if (warp < aw) {
-            const int lp = p.lpos_base[dg.list];
             const int64_t so = p.sacc_off[dg.bucket];
             double gw[2] = {0.0, 0.0};
             int gc[2] = {0, 0};
-            for (;;) {
+            // the warps claim the unit's reads (sorted heaviest first) from a shared counter, two reads ahead: the
+            // record of the read after next and the mutation records of the next read are in flight while a read
+            // is processed
+            const uint4* rec = p.rec + du.first;
+            auto claim = [&]() {
                 int r = 0;
                 if (lane == 0) r = atomicAdd(&ctrl[1], 1);
-                r = __shfl_sync(FULL, r, 0);
-                if (r >= du.count) break;
-                const int32_t rid = (int32_t)p.order[du.first + r];
-                const int nm = (int)(p.rm_off[rid + 1] - p.rm_off[rid]);
-                if (nm <= DP_FAST_MUTS) dp_read<true>(p, dg, rid, lane, base_s, scr, stride / 4, mv, cand, cand_cap, whist_s, lp, so, gw, gc);
-                else dp_read<false>(p, dg, rid, lane, base_s, gscr, 0, mv, cand, 0, whist_s, lp, so, gw, gc);
+                return __shfl_sync(FULL, r, 0);
+            };
+            int i1 = claim(), i2 = claim();
+            uint4 r1 = make_uint4(0u, 0u, 0u, 0u), r2 = r1;
+            uint2 m1 = make_uint2(0u, 0u);
+            if (i1 < du.count) r1 = __ldg(rec + i1);
+            if (i2 < du.count) r2 = __ldg(rec + i2);
+            if (lane < (int)(r1.w & 0xFFFFu)) m1 = __ldg(p.mrec + r1.z + lane);
+            while (i1 < du.count) {
+                const int i3 = claim();
+                uint4 r3 = make_uint4(0u, 0u, 0u, 0u);
+                if (i3 < du.count) r3 = __ldg(rec + i3);
+                uint2 m2 = make_uint2(0u, 0u);
+                if (lane < (int)(r2.w & 0xFFFFu)) m2 = __ldg(p.mrec + r2.z + lane);
+                if ((int)(r1.w & 0xFFFFu) <= DP_FAST_MUTS) dp_read<true>(p, dg, r1, m1, lane, base_s, scr, stride / 4, mv, cand, cand_cap, whist_s, so, gw, gc);
+                else dp_read<false>(p, dg, r1, m1, lane, base_s, gscr, 0, mv, cand, 0, whist_s, so, gw, gc);
+                i1 = i2; r1 = r2; m1 = m2;
+                i2 = i3; r2 = r3;
             }
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {

@@ -164,6 +164,8 @@ struct wepp_handle {
         int32_t n_groups = 0, n_units = 0;
         int64_t delta_touch_est = 0;
         DevBuf<uint32_t> order;
+        DevBuf<uint4> rec;
+        DevBuf<uint2> mrec;
         DevBuf<DeltaGroup> groups;
         DevBuf<DeltaUnit> units;
         DevBuf<uint8_t> base;
@@ -176,7 +178,7 @@ struct wepp_handle {
             prev_boundary.release(); chunk_start.release();
             sid.release(); state_first.release(); state_eoff.release(); sacc_off.release(); state_ent.release();
             state_list.release(); lpos_base.release(); post_off.release(); post.release(); order.release();
-            groups.release(); units.release(); base.release(); whist.release(); list_goff.release();
+            rec.release(); mrec.release(); groups.release(); units.release(); base.release(); whist.release(); list_goff.release();
             list_gids.release(); bucket_goff.release(); Gc.release(); Gw.release(); gscratch.release();
         }
     };
@@ -534,6 +536,13 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
     CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, key.p, key2.p, val.p, dp.order.p, (int)R, 0, key_bits, st));
     CU(h->d_cub_tmp.ensure(tmp));
     CU(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp.p, tmp, key.p, key2.p, val.p, dp.order.p, (int)R, 0, key_bits, st));
+    if (h->n_read_muts >= (1ll << 32)) return WEPP_OK;   // 32-bit mutation offsets in the read records
+    CU(dp.rec.ensure((size_t)R));
+    CU(dp.mrec.ensure((size_t)std::max<int64_t>(h->n_read_muts, 1)));
+    delta_records_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(key2.p, dp.order.p, R, dp.buckets.p, dp.lists.p, dp.lpos_base.p,
+                                                                      dp.post_off.p, h->d_rdegree.p, h->d_roff.p, h->d_rpos.p, h->d_rcode.p,
+                                                                      dp.rec.p, dp.mrec.p);
+    CU(cudaGetLastError());
     delta_window_of_key_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(key2.p, R, key.p);   // the sort is done with key
     CU(cudaGetLastError());
     CU(cub::DeviceRunLengthEncode::Encode(nullptr, tmp, key.p, ukey.p, ucount.p, nruns.p, (int)R, st));
@@ -725,9 +734,8 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         CU(cudaMemsetAsync(dp.Gc.p, 0, (size_t)dp.n_groups * DP_BINS * sizeof(int32_t), h->stream));
         DeltaPlaceParams dq = {};
         dq.units = dp.units.p; dq.n_units = dp.n_units; dq.unit_counter = h->d_tile_counter.p;
-        dq.groups = dp.groups.p; dq.base = dp.base.p; dq.whist = dp.whist.p; dq.post = dp.post.p; dq.post_off = dp.post_off.p;
-        dq.lpos_base = dp.lpos_base.p; dq.state_first = dp.state_first.p; dq.list_desc = dp.lists.p; dq.sacc_off = dp.sacc_off.p;
-        dq.order = dp.order.p; dq.degree = h->d_rdegree.p; dq.rm_off = h->d_roff.p; dq.rm_pos = h->d_rpos.p; dq.rm_code = h->d_rcode.p;
+        dq.groups = dp.groups.p; dq.base = dp.base.p; dq.whist = dp.whist.p; dq.post = dp.post.p;
+        dq.state_first = dp.state_first.p; dq.sacc_off = dp.sacc_off.p; dq.rec = dp.rec.p; dq.mrec = dp.mrec.p;
         dq.max_pars = h->d_maxpars.p; dq.mult = h->d_mult.p; dq.saccS = h->d_saccS.p; dq.saccC = h->d_saccC.p;
         dq.Gw = dp.Gw.p; dq.Gc = dp.Gc.p; dq.gscratch = dp.gscratch.p; dq.gscratch_words = dp.gscratch_words;
         // shared memory: fixed areas + the widest list's base scores + 16 warps' nibble scratch, as far as it fits
