@@ -20,6 +20,7 @@
 #include "rescore_tiles.cuh"
 #include "state_place.cuh"
 #include "delta_place.cuh"
+#include "node_tile.cuh"
 #include "peaks.cuh"
 
 using namespace wepp;
@@ -133,6 +134,7 @@ struct wepp_handle {
     uint8_t* h_div_stage = nullptr;   // pinned: per-node divergence bin counts (wepp_get_node_summary)
     size_t h_div_cap = 0;
     DevBuf<uint8_t> d_div_count;
+    bool div_count_valid = false;     // d_div_count holds the bin counts of the last place (node_tile_kernel)
 
     struct DevPlan {
         ReadPlan plan;
@@ -144,6 +146,9 @@ struct wepp_handle {
         DevBuf<int32_t> prev_boundary;   // per list entry: enclosing / previous boundary entry
         DevBuf<int32_t> chunk_start;     // [n_lists][PLACE_WARPS + 1]
         bool final_for_mask = false;
+        DevBuf<int32_t> tile_ptr, tile_enc;   // [n_tiles + 1][n_lists]: node_tile.cuh
+        DevBuf<uint32_t> ent_x;               // per list entry: idx | flags
+        bool tile_ptr_ready = false;
         // distinct window-restricted haplotypes of the lists (state_place.cuh; built on demand, no mask)
         bool states_ready = false, states_usable = false;
         std::vector<std::pair<int32_t, int32_t>> state_ranges;   // (qs, qe) of the lists the states were built for
@@ -175,7 +180,7 @@ struct wepp_handle {
         int64_t gscratch_words = 0;
         void release() {
             perm.release(); lists.release(); buckets.release(); tiles.release(); entries.release();
-            prev_boundary.release(); chunk_start.release();
+            prev_boundary.release(); chunk_start.release(); tile_ptr.release(); tile_enc.release(); ent_x.release();
             sid.release(); state_first.release(); state_eoff.release(); sacc_off.release(); state_ent.release();
             state_list.release(); lpos_base.release(); post_off.release(); post.release(); order.release();
             rec.release(); mrec.release(); groups.release(); units.release(); base.release(); whist.release(); list_goff.release();
@@ -277,6 +282,7 @@ int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp, bool host_perm) {
         CU(cudaGetLastError());
     }
     dp.final_for_mask = false;
+    dp.tile_ptr_ready = false;
     dp.delta_groups_ready = false;   // the window groups (delta_place.cuh) belong to the read set
     // the states (state_place.cuh) are a function of the tree and of the lists' stripe ranges only: they stay
     // valid while consecutive read sets map to the same sequence of window lists
@@ -659,19 +665,45 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         CU(h->d_epp_nodes.ensure((size_t)epp_capacity));
         CU(cudaMemsetAsync(h->d_epp_off.p, 0xFF, (size_t)h->n_reads * sizeof(int64_t), h->stream));
     }
+    // per-node results: one pass over node tiles (node_tile.cuh); WEPP_NODE_TILES=0 keeps the difference arrays in
+    // HBM (expand_kernel + scans), as does a tile pointer table over 2 GiB
+    const int n_node_tiles = (n + NT_TILE - 1) / NT_TILE;
+    const bool tiles_env = !(getenv("WEPP_NODE_TILES") && atoi(getenv("WEPP_NODE_TILES")) == 0);
+    const bool node_tiles = accumulate && tiles_env && !pl.lists.empty() &&
+                            (double)pl.lists.size() * (n_node_tiles + 1) * 8.0 <= 2.0 * 1024 * 1024 * 1024;
+    if (node_tiles && !dp.tile_ptr_ready) {
+        CU(dp.tile_ptr.ensure(pl.lists.size() * ((size_t)n_node_tiles + 1)));
+        CU(dp.tile_enc.ensure(pl.lists.size() * ((size_t)n_node_tiles + 1)));
+        CU(dp.ent_x.ensure((size_t)pl.list_entries_total));
+        int max_n = 0;
+        for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
+        dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.lists.size());
+        tile_ptr_kernel<<<grid, 256, 0, h->stream>>>(dp.entries.p, dp.lists.p, dp.prev_boundary.p, n_node_tiles, (int)pl.lists.size(),
+                                                     dp.tile_ptr.p, dp.tile_enc.p, dp.ent_x.p);
+        CU(cudaGetLastError());
+        dp.tile_ptr_ready = true;
+    }
     if (accumulate) {
         CU(h->d_accS.ensure((size_t)pl.acc_total));
         CU(h->d_accC.ensure((size_t)pl.acc_total));
-        CU(cudaMemsetAsync(h->d_accS.p, 0, (size_t)pl.acc_total * sizeof(double), h->stream));
-        CU(cudaMemsetAsync(h->d_accC.p, 0, (size_t)pl.acc_total * sizeof(int32_t), h->stream));
         CU(h->d_score.ensure((size_t)n));
         CU(h->d_counts.ensure(((size_t)n + 1) * NBINS));
-        CU(h->d_diff_lo.ensure((size_t)n + 1));
-        CU(h->d_diff_hi.ensure((size_t)n + 1));
-        if (with_counts) CU(cudaMemsetAsync(h->d_counts.p, 0, ((size_t)n + 1) * NBINS * sizeof(int32_t), h->stream));
-        CU(cudaMemsetAsync(h->d_diff_lo.p, 0, ((size_t)n + 1) * sizeof(unsigned long long), h->stream));
-        CU(cudaMemsetAsync(h->d_diff_hi.p, 0, ((size_t)n + 1) * sizeof(unsigned long long), h->stream));
+        if (!node_tiles) {
+            CU(h->d_diff_lo.ensure((size_t)n + 1));
+            CU(h->d_diff_hi.ensure((size_t)n + 1));
+            if (with_counts) CU(cudaMemsetAsync(h->d_counts.p, 0, ((size_t)n + 1) * NBINS * sizeof(int32_t), h->stream));
+            CU(cudaMemsetAsync(h->d_diff_lo.p, 0, ((size_t)n + 1) * sizeof(unsigned long long), h->stream));
+            CU(cudaMemsetAsync(h->d_diff_hi.p, 0, ((size_t)n + 1) * sizeof(unsigned long long), h->stream));
+        }
     }
+    bool acc_zeroed = false;
+    auto zero_acc = [&]() -> cudaError_t {   // the per-(bucket, entry) accumulators, for the paths that add into them
+        if (acc_zeroed) return cudaSuccess;
+        acc_zeroed = true;
+        cudaError_t e = cudaMemsetAsync(h->d_accS.p, 0, (size_t)pl.acc_total * sizeof(double), h->stream);
+        if (e != cudaSuccess) return e;
+        return cudaMemsetAsync(h->d_accC.p, 0, (size_t)pl.acc_total * sizeof(int32_t), h->stream);
+    };
 
     PlaceParams pp = {};
     pp.lists = dp.entries.p;
@@ -722,6 +754,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     h->stats.place_path = by_delta ? 2 : (by_states ? 1 : 0);
     h->stats.n_states = by_states ? dp.n_states : 0;
     h->stats.n_window_groups = by_delta ? dp.n_groups : 0;
+    if (accumulate && !by_states) CU(zero_acc());   // place_kernel adds into the per-(bucket, entry) accumulators
     CU(cudaEventRecord(h->ev[0], h->stream));
     if (by_states) {
         CU(h->d_saccS.ensure((size_t)std::max<int64_t>(dp.sacc_total, 1)));
@@ -753,13 +786,16 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         delta_finalize_kernel<<<fgrid, 256, 0, h->stream>>>(dp.groups.p, dp.bucket_goff.p, dp.state_first.p, dp.buckets.p, dp.base.p,
                                                            dp.Gw.p, dp.Gc.p, dp.sacc_off.p, h->d_saccS.p, h->d_saccC.p);
         CU(cudaGetLastError());
-        int max_n = 0;
-        for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
-        dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
-        state_scatter_kernel<<<grid, 256, 0, h->stream>>>(dp.lists.p, dp.buckets.p, dp.sid.p, dp.state_first.p, dp.sacc_off.p,
-                                                          h->d_saccS.p, h->d_saccC.p, h->d_accS.p, h->d_accC.p);
-        CU(cudaGetLastError());
-        launches += 3;
+        if (!node_tiles) {
+            int max_n = 0;
+            for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
+            dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
+            state_scatter_kernel<<<grid, 256, 0, h->stream>>>(dp.lists.p, dp.buckets.p, dp.sid.p, dp.state_first.p, dp.sacc_off.p,
+                                                              h->d_saccS.p, h->d_saccC.p, h->d_accS.p, h->d_accC.p);
+            CU(cudaGetLastError());
+            ++launches;
+        }
+        launches += 2;
     } else if (by_states) {
         StatePlaceParams sp = {};
         sp.state_ent = dp.state_ent.p; sp.state_eoff = dp.state_eoff.p; sp.state_first = dp.state_first.p;
@@ -772,13 +808,16 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         else if (k == 4) rc = launch_state_place<4>(h, sp, pp.n_tiles, pl.max_width);
         else rc = launch_state_place<2>(h, sp, pp.n_tiles, pl.max_width);
         if (rc) return rc;
-        int max_n = 0;
-        for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
-        dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
-        state_scatter_kernel<<<grid, 256, 0, h->stream>>>(dp.lists.p, dp.buckets.p, dp.sid.p, dp.state_first.p, dp.sacc_off.p,
-                                                          h->d_saccS.p, h->d_saccC.p, h->d_accS.p, h->d_accC.p);
-        CU(cudaGetLastError());
-        launches += 2;
+        if (!node_tiles) {
+            int max_n = 0;
+            for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
+            dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
+            state_scatter_kernel<<<grid, 256, 0, h->stream>>>(dp.lists.p, dp.buckets.p, dp.sid.p, dp.state_first.p, dp.sacc_off.p,
+                                                              h->d_saccS.p, h->d_saccC.p, h->d_accS.p, h->d_accC.p);
+            CU(cudaGetLastError());
+            ++launches;
+        }
+        ++launches;
     } else if (pp.n_tiles > 0) {
         const int k = pl.reads_per_tile / 32;
         if (k == 8) rc = launch_place_k<8>(h, pp, pl.max_width);
@@ -788,7 +827,37 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         ++launches;
     }
     CU(cudaEventRecord(h->ev[1], h->stream));
-    if (accumulate) {
+    h->div_count_valid = false;
+    if (accumulate && node_tiles) {
+        const bool by_state_acc = by_states;
+        NodeTileParams np = {};
+        np.list_desc = dp.lists.p; np.buckets = dp.buckets.p;
+        np.n_buckets = (int32_t)pl.buckets.size(); np.n_lists = (int32_t)pl.lists.size(); np.n_nodes = n; np.n_tiles = n_node_tiles;
+        np.ent_x = dp.ent_x.p; np.prev_boundary = dp.prev_boundary.p; np.tile_ptr = dp.tile_ptr.p; np.tile_enc = dp.tile_enc.p;
+        np.accS = h->d_accS.p; np.accC = h->d_accC.p;
+        np.sid = dp.sid.p; np.state_first = dp.state_first.p; np.sacc_off = dp.sacc_off.p;
+        np.saccS = h->d_saccS.p; np.saccC = h->d_saccC.p;
+        np.mapped = h->has_mask ? h->d_mapped.p : nullptr;
+        np.score = score_out ? score_out : h->d_score.p;
+        np.counts = with_counts ? h->d_counts.p : nullptr;
+        np.threshold = 0.5 / 100;
+        np.div_count = nullptr;
+        if (with_counts && !score_out && h->peer_world == 0) {   // dist_divergence's bin count from the finished rows
+            CU(h->d_div_count.ensure((size_t)n));
+            np.div_count = h->d_div_count.p;
+            for (int j = 0; j < NBINS; ++j) np.true_counts.v[j] = h->true_counts[j];
+            h->div_count_valid = true;
+        }
+        if (by_state_acc) {
+            CU(cudaFuncSetAttribute(node_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM));
+            node_tile_kernel<true><<<n_node_tiles, NT_THREADS, NT_SMEM, h->stream>>>(np);
+        } else {
+            CU(cudaFuncSetAttribute(node_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM));
+            node_tile_kernel<false><<<n_node_tiles, NT_THREADS, NT_SMEM, h->stream>>>(np);
+        }
+        CU(cudaGetLastError());
+        ++launches;
+    } else if (accumulate) {
         if (!pl.buckets.empty()) {
             int max_n = 0;
             for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
@@ -1257,7 +1326,7 @@ int wepp_get_node_summary(wepp_handle* h, double* score, double* dist_divergence
             tc.v[j] = merged ? (int32_t)h->peer_true_counts[j] : h->true_counts[j];
             active += tc.v[j] != 0;
         }
-        if (!merged) {
+        if (!merged && !h->div_count_valid) {
             divergence_count_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_counts.p, n, tc, 0.5 / 100, h->d_div_count.p);
             CU(cudaGetLastError());
         }
