@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
+#include <climits>
 #include <cmath>
 #include <cstring>
 #include <set>
@@ -190,6 +191,7 @@ struct wepp_handle {
     DevPlan full, sub;
 
     // accumulators and outputs
+    DevBuf<SAccPacked> d_sacc_packed;
     DevBuf<double> d_accS, d_saccS;
     DevBuf<int32_t> d_accC, d_saccC;
     DevBuf<int32_t> d_maxpars, d_mult;
@@ -669,7 +671,8 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     // HBM (expand_kernel + scans), as does a tile pointer table over 2 GiB
     const int n_node_tiles = (n + NT_TILE - 1) / NT_TILE;
     const bool tiles_env = !(getenv("WEPP_NODE_TILES") && atoi(getenv("WEPP_NODE_TILES")) == 0);
-    const bool node_tiles = accumulate && tiles_env && !pl.lists.empty() &&
+    const bool node_tiles = accumulate && tiles_env && !pl.lists.empty() && pl.acc_total < (1ll << 32) &&
+                            pl.list_entries_total < (1ll << 32) && pl.buckets.size() < (1u << 24) &&
                             (double)pl.lists.size() * (n_node_tiles + 1) * 8.0 <= 2.0 * 1024 * 1024 * 1024;
     if (node_tiles && !dp.tile_ptr_ready) {
         CU(dp.tile_ptr.ensure(pl.lists.size() * ((size_t)n_node_tiles + 1)));
@@ -836,24 +839,46 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         np.ent_x = dp.ent_x.p; np.prev_boundary = dp.prev_boundary.p; np.tile_ptr = dp.tile_ptr.p; np.tile_enc = dp.tile_enc.p;
         np.accS = h->d_accS.p; np.accC = h->d_accC.p;
         np.sid = dp.sid.p; np.state_first = dp.state_first.p; np.sacc_off = dp.sacc_off.p;
-        np.saccS = h->d_saccS.p; np.saccC = h->d_saccC.p;
+        if (by_state_acc) {   // (weight, degree) pairs side by side: one sector per look-up in the tile kernel
+            CU(h->d_sacc_packed.ensure((size_t)std::max<int64_t>(dp.sacc_total, 1)));
+            sacc_pack_kernel<<<(unsigned)((dp.sacc_total + 255) / 256), 256, 0, h->stream>>>(h->d_saccS.p, h->d_saccC.p, dp.sacc_total,
+                                                                                             h->d_sacc_packed.p);
+            CU(cudaGetLastError());
+            ++launches;
+        }
+        np.sacc = h->d_sacc_packed.p;
         np.mapped = h->has_mask ? h->d_mapped.p : nullptr;
         np.score = score_out ? score_out : h->d_score.p;
         np.counts = with_counts ? h->d_counts.p : nullptr;
-        np.threshold = 0.5 / 100;
         np.div_count = nullptr;
         if (with_counts && !score_out && h->peer_world == 0) {   // dist_divergence's bin count from the finished rows
             CU(h->d_div_count.ensure((size_t)n));
             np.div_count = h->d_div_count.p;
-            for (int j = 0; j < NBINS; ++j) np.true_counts.v[j] = h->true_counts[j];
+            // counts / true_counts > 0.5 % (initial_filter.cpp:214-231) as an integer threshold per bin: the smallest
+            // count whose IEEE quotient exceeds it, found with the very division (monotone in the count)
+            const double threshold = 0.5 / 100;
+            for (int j = 0; j < NBINS; ++j) {
+                const int32_t t = h->true_counts[j];
+                int32_t lo = 0, hi = t;   // (double)hi / t = 1 > threshold when t > 0
+                if (t <= 0) {
+                    np.min_count.v[j] = INT32_MAX;
+                    continue;
+                }
+                while (lo < hi) {
+                    const int32_t mid = lo + (hi - lo) / 2;
+                    if ((double)mid / (double)t > threshold) hi = mid;
+                    else lo = mid + 1;
+                }
+                np.min_count.v[j] = lo;
+            }
             h->div_count_valid = true;
         }
         if (by_state_acc) {
             CU(cudaFuncSetAttribute(node_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM));
-            node_tile_kernel<true><<<n_node_tiles, NT_THREADS, NT_SMEM, h->stream>>>(np);
+            node_tile_kernel<true><<<(n_node_tiles + NT_SUPER - 1) / NT_SUPER, NT_THREADS, NT_SMEM, h->stream>>>(np);
         } else {
             CU(cudaFuncSetAttribute(node_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM));
-            node_tile_kernel<false><<<n_node_tiles, NT_THREADS, NT_SMEM, h->stream>>>(np);
+            node_tile_kernel<false><<<(n_node_tiles + NT_SUPER - 1) / NT_SUPER, NT_THREADS, NT_SMEM, h->stream>>>(np);
         }
         CU(cudaGetLastError());
         ++launches;
