@@ -41,9 +41,12 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(VP)
 
 
-def cartesian_map(arena, reads, mapped=None, n_threads: int = 1, epp_cap: int = 2048, want_node: bool = True):
+def cartesian_map(arena, reads, mapped=None, n_threads: int = 1, epp_cap: int = 2048, want_node: bool = True,
+                  range_trees: bool = False, range_reads=None):
     """Restated wepp_filter::cartesian_map.  Returns dict(max_parsimony, multiplicity, score,
-    counts, epp_off, epp_nodes)."""
+    counts, epp_off, epp_nodes, seconds_map).  range_trees: score through the reference's range trees
+    (arena.cpp:68-169; same results, less work per read), built from the windows of `range_reads` (default: `reads`).
+    seconds_map = wall time of the read loop + merge alone (the reference's own timer boundary)."""
     lib = load()
     n, r = arena.n_nodes, reads.n_reads
     a = (_c(arena.parent, np.int32), _c(arena.mut_off, np.int64), _c(arena.mut_pos, np.int32),
@@ -58,13 +61,17 @@ def cartesian_map(arena, reads, mapped=None, n_threads: int = 1, epp_cap: int = 
     cap = int(min(r * min(epp_cap, n) + 1, 1 << 30))
     eo = np.zeros(r + 1, np.int64)
     en = np.zeros(cap, np.int32)
-    rc = lib.oracle_cartesian_map(C.c_int32(n), *[_p(x) for x in a], C.c_int32(arena.genome_size), C.c_int64(r),
-                                  *[_p(x) for x in rd], _p(m), C.c_int32(n_threads), _p(mp), _p(mu), _p(sc), _p(ct),
-                                  C.c_int32(epp_cap), C.c_int64(cap), _p(eo), _p(en))
+    rr = reads if range_reads is None else range_reads
+    rs, re_ = _c(rr.start, np.int32), _c(rr.end, np.int32)
+    secs = C.c_double(0.0)
+    rc = lib.oracle_cartesian_map_ex(C.c_int32(n), *[_p(x) for x in a], C.c_int32(arena.genome_size), C.c_int64(r),
+                                     *[_p(x) for x in rd], _p(m), C.c_int32(n_threads), _p(mp), _p(mu), _p(sc), _p(ct),
+                                     C.c_int32(epp_cap), C.c_int64(cap), _p(eo), _p(en), C.c_int32(1 if range_trees else 0),
+                                     C.c_int64(rr.n_reads), _p(rs), _p(re_), C.byref(secs))
     if rc != 0:
         raise RuntimeError("oracle EPP buffer overflow")
     return {"max_parsimony": mp, "multiplicity": mu, "score": sc, "counts": ct, "epp_off": eo,
-            "epp_nodes": en[: int(eo[-1])]}
+            "epp_nodes": en[: int(eo[-1])], "seconds_map": float(secs.value)}
 
 
 def read_scores(arena, start: int, end: int, rm_pos, rm_nuc):

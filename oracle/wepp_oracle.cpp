@@ -20,10 +20,12 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <queue>
 #include <thread>
 #include <vector>
@@ -144,6 +146,94 @@ void single_read_tree(const Arena& arena, const Read& read, const uint8_t* mappe
         if (!mapped || !mapped[v]) max_indices.push_back(v);  // :126-134
 }
 
+// ---- range trees (arena.cpp:68-169): an optimisation of the reference that does not change results — per genome
+// range (<= NUM_RANGE_TREES of them, from read-start quantiles) a compressed tree of the haplotypes with at least one
+// mutation inside the range; every other haplotype joins the `sources` of its nearest kept ancestor.
+constexpr int NUM_RANGE_TREES = 25;   // config.hpp:14
+struct RangedNode {                   // multi_haplotype, haplotype.hpp:245-260
+    int root;
+    std::vector<int> sources;
+    std::vector<int> children;
+};
+struct RangedArena {
+    std::vector<RangedNode> nodes;
+    std::map<std::pair<int, int>, int> root_map;   // ranged_root_map
+};
+
+bool has_mutations_in_range(const Arena& arena, int v, int start, int end) {   // haplotype.hpp:57-64
+    const std::vector<Mut>& m = arena.muts[v];
+    auto it = std::lower_bound(m.begin(), m.end(), start, [](const Mut& x, int p) { return x.position < p; });
+    return it != m.end() && it->position <= end;
+}
+
+int build_range_tree(const Arena& arena, RangedArena& ra, int parent, int curr, int start, int end) {   // arena.cpp:68-94
+    int ret;
+    if (parent == -1 || has_mutations_in_range(arena, curr, start, end)) {
+        ret = (int)ra.nodes.size();
+        ra.nodes.emplace_back();
+        ra.nodes[ret].root = curr;
+        ra.nodes[ret].sources = {curr};
+    } else {
+        ret = parent;
+        ra.nodes[parent].sources.push_back(curr);
+    }
+    for (int child : arena.children[curr]) {
+        const int sub = build_range_tree(arena, ra, ret, child, start, end);
+        if (sub != ret) ra.nodes[ret].children.push_back(sub);
+    }
+    return ret;
+}
+
+void build_range_trees(const Arena& arena, RangedArena& ra, int64_t n_reads, const int32_t* start, const int32_t* end) {   // arena.cpp:96-136
+    std::vector<std::pair<int, int>> read_ranges((size_t)n_reads);
+    for (int64_t r = 0; r < n_reads; ++r) read_ranges[(size_t)r] = {start[r], end[r]};
+    std::sort(read_ranges.begin(), read_ranges.end());
+    const int num = (int)std::min<int64_t>(n_reads, NUM_RANGE_TREES);
+    for (int i = 0; i < num; ++i) {
+        const size_t s = read_ranges.size() * (size_t)i / num, e = read_ranges.size() * (size_t)(i + 1) / num;
+        const int read_start = read_ranges[s].first;
+        int read_end = 0;
+        for (size_t j = s; j < e; ++j) read_end = std::max(read_end, read_ranges[j].second);
+        const std::pair<int, int> r{read_start, read_end};
+        if (ra.root_map.find(r) == ra.root_map.end()) ra.root_map[r] = build_range_tree(arena, ra, -1, 0, read_start, read_end);
+    }
+}
+
+int find_range_tree_for(const RangedArena& ra, const Read& read) {   // arena.cpp:154-169
+    auto it = ra.root_map.upper_bound({read.start, INT32_MAX});
+    do {
+        it = std::prev(it);
+        if (read.start >= it->first.first && read.end <= it->first.second) return it->second;
+    } while (it != ra.root_map.begin());
+    return -1;
+}
+
+void single_read_tree_ranged_rec(const Arena& arena, const RangedArena& ra, const std::vector<int>& parent_locations, int curr,
+                                 const Read& read, std::vector<int>& max_nodes, int& max_val) {   // initial_filter.cpp:41-105
+    std::vector<int> my_locations = node_locations(arena, parent_locations, ra.nodes[curr].root, read);
+    const int parsimony = (int)my_locations.size();
+    if (parsimony < max_val) {
+        max_val = parsimony;
+        max_nodes.clear();
+        max_nodes.push_back(curr);
+    } else if (parsimony == max_val) {
+        max_nodes.push_back(curr);
+    }
+    for (int child : ra.nodes[curr].children) single_read_tree_ranged_rec(arena, ra, my_locations, child, read, max_nodes, max_val);
+}
+
+void single_read_tree_ranged(const Arena& arena, const RangedArena& ra, const Read& read, const uint8_t* mapped,
+                             std::vector<int>& max_indices, int& max_val) {   // initial_filter.cpp:112-135
+    std::vector<int> root_mutations;
+    for (const Mut& m : read.mutations)
+        if (m.mut_nuc != NUC_N) root_mutations.push_back(m.position);
+    std::vector<int> max_nodes;
+    single_read_tree_ranged_rec(arena, ra, root_mutations, find_range_tree_for(ra, read), read, max_nodes, max_val);
+    for (int rn : max_nodes)
+        for (int src : ra.nodes[rn].sources)
+            if (!mapped || !mapped[src]) max_indices.push_back(src);
+}
+
 }  // namespace
 
 extern "C" {
@@ -155,13 +245,46 @@ extern "C" {
 // written to epp_nodes (capacity epp_capacity) with CSR offsets epp_off[R+1]; reads above
 // the cap (or overflowing the buffer) get an empty range, as the reference's cache does
 // (:189-196).  Returns 0, or -1 if the EPP buffer overflowed.
+// range_trees != 0: score through the reference's range trees (arena.cpp:68-169), built — as the reference builds
+// them, arena.cpp:96-136 — from the windows of range_n_reads reads (range_start / range_end; the whole sample's read
+// set, so that a bounded timing sample meets the same trees the full run would).  Same results, less work per read.
+// seconds_map (optional) receives the wall time of the read loop + merge alone: the reference's own "cartesian
+// mapping took" boundary (initial_filter.cpp:144,238), without the arena / range-tree construction.
+int oracle_cartesian_map_ex(int32_t n_nodes, const int32_t* parent, const int64_t* mut_off, const int32_t* mut_pos,
+                            const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size, int64_t n_reads,
+                            const int32_t* start, const int32_t* end, const int32_t* degree, const int64_t* rm_off,
+                            const int32_t* rm_pos, const uint8_t* rm_nuc, const uint8_t* mapped, int32_t n_threads,
+                            int32_t* max_parsimony, int32_t* multiplicity, double* score, int32_t* counts,
+                            int32_t epp_cap, int64_t epp_capacity, int64_t* epp_off, int32_t* epp_nodes,
+                            int32_t range_trees, int64_t range_n_reads, const int32_t* range_start, const int32_t* range_end,
+                            double* seconds_map);
+
 int oracle_cartesian_map(int32_t n_nodes, const int32_t* parent, const int64_t* mut_off, const int32_t* mut_pos,
                          const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size, int64_t n_reads,
                          const int32_t* start, const int32_t* end, const int32_t* degree, const int64_t* rm_off,
                          const int32_t* rm_pos, const uint8_t* rm_nuc, const uint8_t* mapped, int32_t n_threads,
                          int32_t* max_parsimony, int32_t* multiplicity, double* score, int32_t* counts,
                          int32_t epp_cap, int64_t epp_capacity, int64_t* epp_off, int32_t* epp_nodes) {
+    return oracle_cartesian_map_ex(n_nodes, parent, mut_off, mut_pos, mut_ref, mut_nuc, genome_size, n_reads, start, end, degree,
+                                   rm_off, rm_pos, rm_nuc, mapped, n_threads, max_parsimony, multiplicity, score, counts, epp_cap,
+                                   epp_capacity, epp_off, epp_nodes, 0, 0, nullptr, nullptr, nullptr);
+}
+
+int oracle_cartesian_map_ex(int32_t n_nodes, const int32_t* parent, const int64_t* mut_off, const int32_t* mut_pos,
+                            const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size, int64_t n_reads,
+                            const int32_t* start, const int32_t* end, const int32_t* degree, const int64_t* rm_off,
+                            const int32_t* rm_pos, const uint8_t* rm_nuc, const uint8_t* mapped, int32_t n_threads,
+                            int32_t* max_parsimony, int32_t* multiplicity, double* score, int32_t* counts,
+                            int32_t epp_cap, int64_t epp_capacity, int64_t* epp_off, int32_t* epp_nodes,
+                            int32_t range_trees, int64_t range_n_reads, const int32_t* range_start, const int32_t* range_end,
+                            double* seconds_map) {
     Arena arena = make_arena(n_nodes, parent, mut_off, mut_pos, mut_ref, mut_nuc);
+    RangedArena ranged;
+    if (range_trees) {
+        if (range_n_reads > 0 && range_start && range_end) build_range_trees(arena, ranged, range_n_reads, range_start, range_end);
+        else build_range_trees(arena, ranged, n_reads, start, end);
+    }
+    const auto t_map0 = std::chrono::steady_clock::now();
     int bin_size = genome_size / NUM_RANGE_BINS;  // :146
     if (n_threads < 1) n_threads = 1;
 
@@ -177,7 +300,8 @@ int oracle_cartesian_map(int32_t n_nodes, const int32_t* parent, const int64_t* 
             Read read = make_read(r, start, end, degree, rm_off, rm_pos, rm_nuc);
             std::vector<int> max_indices;
             int max_val = INT32_MAX;
-            single_read_tree(arena, read, mapped, max_indices, max_val);  // :165
+            if (range_trees) single_read_tree_ranged(arena, ranged, read, mapped, max_indices, max_val);
+            else single_read_tree(arena, read, mapped, max_indices, max_val);  // :165
             double delta = (double)read.degree / ((1 + max_val) * (double)max_indices.size());  // hpp:54-57
             int bucket = std::min(read.start / bin_size, NUM_RANGE_BINS - 1);                     // :169
             for (int v : max_indices) {                                                            // :171-177
@@ -210,6 +334,7 @@ int oracle_cartesian_map(int32_t n_nodes, const int32_t* parent, const int64_t* 
         for (int t = 0; t < n_threads; ++t)
             for (size_t k = 0; k < (size_t)n_nodes * NUM_RANGE_BINS; ++k) counts[k] += t_counts[t][k];
     }
+    if (seconds_map) *seconds_map = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_map0).count();
     int rc = 0;
     if (epp_off) {
         int64_t off = 0;

@@ -168,6 +168,19 @@ def amplicon_scheme(genome_size: int, n_amplicons: int, min_len: int, max_len: i
     return np.stack([starts, ends], axis=1).astype(np.int32)
 
 
+def primer_scheme(name: str, min_len: int = 0, max_len: int = 1 << 30) -> np.ndarray:
+    """Amplicon windows (1-based closed, int32[n,2]) of one of the reference's primer schemes — ARTICv4_1 (99 amplicons,
+    388-493 bp), midnight (29, 1080-1223 bp), RSVA_all_primers_best_hits (50) — from wepp_b200/data/<name>.amplicons.tsv
+    (derived from the reference's primers/<name>.bed by wepp_b200/data/make_amplicons.py).  Amplicons outside
+    [min_len, max_len] are dropped (the RSV-A "best hits" file pairs two primers wrongly: a 96-bp and a 5.6-kb window)."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", name + ".amplicons.tsv")
+    rows = [ln.split() for ln in open(path) if ln.strip() and not ln.startswith("#")]
+    a = np.array([[int(r[1]), int(r[2])] for r in rows], dtype=np.int32)
+    ln = a[:, 1] - a[:, 0] + 1
+    return a[(ln >= min_len) & (ln <= max_len)]
+
+
 def make_reads(arena: Arena, n_reads: int, seed: int = SEED, *, amplicons: np.ndarray | None = None,
                read_len: int = 150, jitter: int = 10, full_amplicon: bool = False, n_templates: int = 2000,
                err: float = 0.002, n_rate: float = 0.01, max_degree_geom: float = 0.5) -> Reads:
@@ -247,24 +260,28 @@ def make_reads(arena: Arena, n_reads: int, seed: int = SEED, *, amplicons: np.nd
 
 
 # ---- named shapes -------------------------------------------------------------
-def config_shape(name: str, scale: float = 1.0, seed: int = SEED) -> tuple[Arena, Reads, dict]:
-    """C1..C4 stand-ins.  `scale` shrinks node and read counts together (tests use tiny scales)."""
+def config_shape(name: str, scale: float = 1.0, seed: int = SEED, n_reads: int | None = None,
+                 read_seed: int | None = None) -> tuple[Arena, Reads, dict]:
+    """C1..C4 stand-ins (BASELINE.md section 2 / SURVEY.md section 8d): synthetic trees, reads on the reference's own
+    primer schemes.  `scale` shrinks node and read counts together (tests use tiny scales); n_reads overrides the
+    read count (bench.py: one GPU's shard), read_seed the reads' seed (one per rank)."""
+    rs = seed if read_seed is None else read_seed
     if name == "C1":      # RSV-A quick-start shape
         g, n, r = 15222, int(50_000 * scale), int(200_000 * scale)
         arena = make_arena(n, g, seed)
-        reads = make_reads(arena, r, seed, amplicons=amplicon_scheme(g, 50, 380, 480, seed))
+        reads = make_reads(arena, n_reads or r, rs, amplicons=primer_scheme("RSVA_all_primers_best_hits", 250, 600))
     elif name == "C2":    # SARS-CoV-2 quick-start shape
         g, n, r = 29903, int(1_000_000 * scale), int(1_000_000 * scale)
         arena = make_arena(n, g, seed)
-        reads = make_reads(arena, r, seed)
-    elif name == "C3":    # public-scale MAT x ARTIC v4.1-like reads
+        reads = make_reads(arena, n_reads or r, rs, amplicons=primer_scheme("ARTICv4_1"))
+    elif name == "C3":    # public-scale MAT x ARTIC v4.1 reads
         g, n, r = 29903, int(8_000_000 * scale), int(10_000_000 * scale)
         arena = make_arena(n, g, seed)
-        reads = make_reads(arena, r, seed)
-    elif name == "C4":    # ONT long reads, midnight-like 29 amplicons
+        reads = make_reads(arena, n_reads or r, rs, amplicons=primer_scheme("ARTICv4_1"))
+    elif name == "C4":    # ONT long reads, midnight primers
         g, n, r = 29903, int(8_000_000 * scale), int(1_000_000 * scale)
         arena = make_arena(n, g, seed)
-        reads = make_reads(arena, r, seed, amplicons=amplicon_scheme(g, 29, 1058, 1201, seed),
+        reads = make_reads(arena, n_reads or r, rs, amplicons=primer_scheme("midnight"),
                            full_amplicon=True, err=0.03, n_rate=0.05)
     else:
         raise ValueError(name)
