@@ -83,6 +83,44 @@ struct DevBuf {
     }
 };
 
+// Stream-ordered temporary from the device's memory pool (kept warm: wepp_create raises the pool's release
+// threshold): the builds that run once per read set must not pay a cudaMalloc + cudaFree (a device synchronisation)
+// per scratch array.
+template <typename T>
+struct TmpBuf {
+    T* p = nullptr;
+    cudaStream_t st = nullptr;
+    explicit TmpBuf(cudaStream_t s) : st(s) {}
+    TmpBuf(const TmpBuf&) = delete;
+    TmpBuf& operator=(const TmpBuf&) = delete;
+    ~TmpBuf() {
+        if (p) cudaFreeAsync(p, st);
+    }
+    cudaError_t ensure(size_t n) {
+        if (p) {
+            cudaFreeAsync(p, st);
+            p = nullptr;
+        }
+        return cudaMallocAsync(&p, std::max<size_t>(n, 1) * sizeof(T), st);
+    }
+};
+
+// WEPP_TIMING=2: wall time of the phases of a build on stderr (development aid; adds synchronisations)
+struct Laps {
+    bool on;
+    cudaStream_t st;
+    const char* who;
+    std::chrono::steady_clock::time_point t;
+    Laps(const char* w, cudaStream_t s) : on(getenv("WEPP_TIMING") && atoi(getenv("WEPP_TIMING")) == 2), st(s), who(w), t(std::chrono::steady_clock::now()) {}
+    void operator()(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[%s] %-34s %8.3f ms\n", who, what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
 }  // namespace
 
 struct wepp_handle {
@@ -147,6 +185,8 @@ struct wepp_handle {
         DevBuf<int32_t> prev_boundary;   // per list entry: enclosing / previous boundary entry
         DevBuf<int32_t> chunk_start;     // [n_lists][PLACE_WARPS + 1]
         bool final_for_mask = false;
+        bool lists_built = false;        // entries hold the lists of list_ranges (for the tree of the handle)
+        std::vector<std::pair<int32_t, int32_t>> list_ranges;
         DevBuf<int32_t> tile_ptr, tile_enc;   // [n_tiles + 1][n_lists]: node_tile.cuh
         DevBuf<uint32_t> ent_x;               // per list entry: idx | flags
         bool tile_ptr_ready = false;
@@ -253,6 +293,17 @@ int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp, bool host_perm) {
     CU(upload(dp.lists, pl.lists, h->stream));
     CU(upload(dp.buckets, pl.buckets, h->stream));
     CU(upload(dp.tiles, pl.tiles, h->stream));
+    // The Euler lists are a function of the tree and of the lists' stripe ranges only: a read set that maps to the
+    // same sequence of window lists as the one before (the next sample of the same protocol) finds them — and what
+    // was derived from them: finalisation under the same mask, tile tables — already on the device.
+    bool same_lists = dp.lists_built && dp.list_ranges.size() == pl.lists.size();
+    for (size_t i = 0; same_lists && i < pl.lists.size(); ++i)
+        same_lists = dp.list_ranges[i].first == pl.lists[i].qs && dp.list_ranges[i].second == pl.lists[i].qe;
+    if (getenv("WEPP_NO_LIST_REUSE") && atoi(getenv("WEPP_NO_LIST_REUSE")) != 0) same_lists = false;
+    if (same_lists) {
+        dp.delta_groups_ready = false;
+    } else {
+        dp.lists_built = false;
     CU(dp.entries.ensure((size_t)pl.list_entries_total));
     CU(dp.prev_boundary.ensure((size_t)pl.list_entries_total));
     CU(dp.chunk_start.ensure(pl.lists.size() * (PLACE_WARPS + 1)));
@@ -283,9 +334,13 @@ int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp, bool host_perm) {
                                                             h->es.stripe_width);
         CU(cudaGetLastError());
     }
+    dp.list_ranges.clear();
+    for (const ListDesc& l : pl.lists) dp.list_ranges.emplace_back(l.qs, l.qe);
+    dp.lists_built = true;
     dp.final_for_mask = false;
     dp.tile_ptr_ready = false;
     dp.delta_groups_ready = false;   // the window groups (delta_place.cuh) belong to the read set
+    }
     // the states (state_place.cuh) are a function of the tree and of the lists' stripe ranges only: they stay
     // valid while consecutive read sets map to the same sequence of window lists
     // (and to the same (list, bin) buckets: the per-(bucket, state) accumulator offsets were laid out for them)
@@ -375,17 +430,18 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     if (n_lists == 0 || n_lists > SW_MAX_LISTS || E <= 0 || E > 0x7FFFFFFFll) return WEPP_OK;
     cudaStream_t st = h->stream;
     const auto t_build = std::chrono::steady_clock::now();
-    DevBuf<uint64_t> key, key2, h2;
-    DevBuf<uint32_t> val, val2;
-    DevBuf<int32_t> overflow, flag, incl, rep_state, state_ucnt, state_rep;
+    Laps lap("build_states", st);
+    TmpBuf<uint64_t> key(st), key2(st), h2(st);
+    TmpBuf<uint32_t> val(st), val2(st);
+    TmpBuf<int32_t> overflow(st), flag(st), incl(st), rep_state(st), state_ucnt(st), state_rep(st);
     DevBuf<int32_t>& state_list = dp.state_list;
-    DevBuf<int64_t> state_len;
+    TmpBuf<int64_t> state_len(st);
     dp.delta_usable = false;
     CU(key.ensure((size_t)E)); CU(key2.ensure((size_t)E)); CU(h2.ensure((size_t)E));
     CU(val.ensure((size_t)E)); CU(val2.ensure((size_t)E));
     CU(overflow.ensure((size_t)n_lists)); CU(flag.ensure((size_t)E)); CU(incl.ensure((size_t)E));
     CU(dp.sid.ensure((size_t)E));
-    DevBuf<ChunkNet> nets, ctx;
+    TmpBuf<ChunkNet> nets(st), ctx(st);
     CU(nets.ensure((size_t)n_lists * SW_CHUNKS));
     CU(ctx.ensure((size_t)n_lists * SW_CHUNKS));
     CU(cudaMemsetAsync(overflow.p, 0, (size_t)n_lists * 4, st));
@@ -398,6 +454,7 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     CU(cudaGetLastError());
     state_ctx_kernel<<<(n_lists + 31) / 32, 32, 0, st>>>(nets.p, n_lists, ctx.p, overflow.p);
     CU(cudaGetLastError());
+    lap("walk: chunk nets + contexts");
     wp.ctx = ctx.p;
     wp.pass = 0;
     state_walk_kernel<<<walk_blocks, 128, 0, st>>>(wp);
@@ -407,6 +464,7 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     CU(cudaStreamSynchronize(st));
     for (int32_t o : ov)
         if (o) return WEPP_OK;   // a list with too many active positions: place_kernel serves this plan
+    lap("walk: hashes");
     iota_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(val.p, E);
     CU(cudaGetLastError());
     size_t tmp = 0;
@@ -421,6 +479,7 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     int32_t n_states = 0;
     CU(cudaMemcpyAsync(&n_states, incl.p + (E - 1), 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    lap("sort + flags + scan");
     if (n_states <= 0) return WEPP_OK;
     const size_t S = (size_t)n_states;
     CU(state_ucnt.ensure(S)); CU(state_rep.ensure(S)); CU(state_list.ensure(S)); CU(state_len.ensure(S + 1));
@@ -445,6 +504,7 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     CU(cudaMemcpyAsync(first.data(), dp.state_first.p, ((size_t)n_lists + 1) * 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     CU(dp.state_ent.ensure((size_t)std::max<int64_t>(total_ent, 1)));
+    lap("assign + offsets");
     wp.pass = 1;
     wp.rep_state = rep_state.p; wp.state_eoff = dp.state_eoff.p; wp.state_ucnt = state_ucnt.p;
     wp.state_first = dp.state_first.p; wp.state_ent = dp.state_ent.p;
@@ -457,6 +517,7 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
         acc += first[(size_t)pl.buckets[b].list + 1] - first[(size_t)pl.buckets[b].list];
     }
     CU(upload(dp.sacc_off, sacc, st));
+    lap("walk: representatives");
     dp.h_state_first = first;
     dp.max_list_states = 0;
     for (int l = 0; l < n_lists; ++l) dp.max_list_states = std::max(dp.max_list_states, first[(size_t)l + 1] - first[(size_t)l]);
@@ -470,9 +531,9 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
         lpos[(size_t)n_lists] = (int32_t)slots;
         const bool fits = slots < (1ll << 30) && total_ent < (1ll << 31);
         if (fits) {
-            DevBuf<uint32_t> slot_count;
-            DevBuf<uint64_t> pkey, pkey2, pval;
-            DevBuf<int32_t> bad;
+            TmpBuf<uint32_t> slot_count(st);
+            TmpBuf<uint64_t> pkey(st), pkey2(st), pval(st);
+            TmpBuf<int32_t> bad(st);
             const size_t TE = (size_t)std::max<int64_t>(total_ent, 1);
             CU(upload(dp.lpos_base, lpos, st));
             CU(slot_count.ensure((size_t)slots + 1)); CU(bad.ensure(1));
@@ -508,7 +569,8 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
                         (long long)h->smem_optin, dp.delta_usable ? "usable" : "unusable");
         }
     }
-    CU(cudaStreamSynchronize(st));   // the temporaries above go out of scope
+    CU(cudaStreamSynchronize(st));   // the host vectors above go out of scope
+    lap("posting lists");
     dp.sacc_total = acc;
     dp.n_states = n_states;
     dp.states_usable = true;
@@ -530,9 +592,10 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
     const int n_lists = (int)pl.lists.size(), n_buckets = (int)pl.buckets.size(), n_tiles = (int)pl.tiles.size();
     if (!dp.delta_usable || R <= 0 || R > 0x7FFFFFFFll || n_tiles == 0 || n_buckets >= (1 << 20)) return WEPP_OK;
     cudaStream_t st = h->stream;
-    DevBuf<uint64_t> key, key2, ukey;
-    DevBuf<uint32_t> val;
-    DevBuf<int32_t> ucount, nruns;
+    Laps lap("build_delta_groups", st);
+    TmpBuf<uint64_t> key(st), key2(st), ukey(st);
+    TmpBuf<uint32_t> val(st);
+    TmpBuf<int32_t> ucount(st), nruns(st);
     CU(key.ensure((size_t)R)); CU(key2.ensure((size_t)R)); CU(ukey.ensure((size_t)R));
     CU(val.ensure((size_t)R)); CU(dp.order.ensure((size_t)R)); CU(ucount.ensure((size_t)R)); CU(nruns.ensure(1));
     delta_keys_kernel<<<n_tiles, 256, 0, st>>>(dp.tiles.p, dp.buckets.p, dp.lists.p, dp.perm.p, h->d_rstart.p, h->d_rend.p, h->d_roff.p,
@@ -559,6 +622,7 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
     int32_t n_groups = 0;
     CU(cudaMemcpyAsync(&n_groups, nruns.p, 4, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    lap("keys + sort + records + run lengths");
     // many distinct windows per read: the per-group work (base scores of every state) outweighs the sparse reads
     const bool force = getenv("WEPP_DELTA_PLACE") && atoi(getenv("WEPP_DELTA_PLACE")) == 2;   // tests
     if (n_groups <= 0 || (!force && (int64_t)n_groups * 2 > R + 64)) return WEPP_OK;
@@ -599,6 +663,7 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
         std::vector<int32_t> cur(list_goff.begin(), list_goff.end() - 1);
         for (int g = 0; g < n_groups; ++g) list_gids[(size_t)cur[(size_t)groups[(size_t)g].list]++] = g;
     }
+    lap("group descriptors (host)");
     CU(upload(dp.groups, groups, st));
     CU(upload(dp.units, units, st));
     CU(upload(dp.bucket_goff, bucket_goff, st));
@@ -626,7 +691,8 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
         CU(cudaMemsetAsync(dp.gscratch.p, 0, dp.gscratch.cap * 4, st));   // the kernel leaves it zero
     }
     dp.gscratch_words = words;
-    CU(cudaStreamSynchronize(st));   // the host vectors and temporaries above go out of scope
+    CU(cudaStreamSynchronize(st));   // the host vectors above go out of scope
+    lap("base scores + histograms");
     dp.n_groups = n_groups;
     dp.n_units = (int32_t)units.size();
     dp.delta_groups_usable = true;
@@ -674,6 +740,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     const bool node_tiles = accumulate && tiles_env && !pl.lists.empty() && pl.acc_total < (1ll << 32) &&
                             pl.list_entries_total < (1ll << 32) && pl.buckets.size() < (1u << 24) &&
                             (double)pl.lists.size() * (n_node_tiles + 1) * 8.0 <= 2.0 * 1024 * 1024 * 1024;
+    Laps lap_place("run_place", h->stream);
     if (node_tiles && !dp.tile_ptr_ready) {
         CU(dp.tile_ptr.ensure(pl.lists.size() * ((size_t)n_node_tiles + 1)));
         CU(dp.tile_enc.ensure(pl.lists.size() * ((size_t)n_node_tiles + 1)));
@@ -685,6 +752,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
                                                      dp.tile_ptr.p, dp.tile_enc.p, dp.ent_x.p);
         CU(cudaGetLastError());
         dp.tile_ptr_ready = true;
+        lap_place("tile tables");
     }
     if (accumulate) {
         CU(h->d_accS.ensure((size_t)pl.acc_total));
@@ -754,6 +822,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         if (rc) return rc;
         by_delta = dp.delta_groups_usable;
     }
+    lap_place("states / window groups");
     h->stats.place_path = by_delta ? 2 : (by_states ? 1 : 0);
     h->stats.n_states = by_states ? dp.n_states : 0;
     h->stats.n_window_groups = by_delta ? dp.n_groups : 0;
@@ -980,6 +1049,14 @@ int wepp_create(int device, wepp_handle** out) {
     h->n_sms = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
     CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    {   // keep freed stream-ordered temporaries (TmpBuf) in the pool instead of handing them back at every synchronisation
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+    }
     for (auto& ev : h->ev) CU(cudaEventCreate(&ev));
     *out = h;
     return WEPP_OK;
@@ -1047,6 +1124,8 @@ int wepp_set_arena(wepp_handle* h, int32_t n_nodes, const int32_t* parent, const
     h->rank_tab_d = 0;
     h->full.states_ready = false;
     h->sub.states_ready = false;
+    h->full.lists_built = false;
+    h->sub.lists_built = false;
     h->tree_on_device = false;
     h->st_cache.clear();
     h->st_cache_pos.clear();
@@ -1264,6 +1343,7 @@ int wepp_set_mapped(wepp_handle* h, const uint8_t* mapped) {
     bool any = false;
     if (mapped)
         for (int32_t v = 0; v < h->n_nodes && !any; ++v) any = mapped[v] != 0;
+    if (!any && !h->has_mask) return WEPP_OK;   // nothing mapped before, nothing now: the finalised lists stay valid
     h->has_mask = any;
     if (any) {
         std::vector<uint8_t> m(mapped, mapped + h->n_nodes);
