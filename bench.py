@@ -54,8 +54,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed cross-checks of the step's results")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N>1: per-node exchange step — fused peer-memory merge kernel (default) or NCCL all-reduce")
+    ap.add_argument("--exchange", default="states", choices=["states", "peer", "nccl"],
+                    help="N>1 exchange step: states = one plan on all ranks, all-reduce of the per-(bucket, state) accumulators "
+                         "(default); peer = peer-memory merge kernel over the per-node arrays; nccl = all-reduce of the per-node arrays")
     ap.add_argument("--no-c5", action="store_true", help="skip the candidate re-scoring (C5) measurement")
     ap.add_argument("--c5-generic", action="store_true", help="also time the generic K4 kernel once (slow)")
     return ap.parse_args()
@@ -262,6 +263,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     t0 = time.perf_counter()
     p.set_arena(arena)
     t_arena = time.perf_counter() - t0
+    shared = None
+    if world > 1 and args.exchange == "states":
+        shared = multigpu.SharedPlan(p, dev)   # the library all-reduces the cell histogram (set_reads) and the accumulators (place)
     t0 = time.perf_counter()
     p.set_reads(reads)
     t_reads = time.perf_counter() - t0
@@ -280,7 +284,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         peer = multigpu.PeerMerge(p, rank, world, dev)
 
     def exchange(full_counts: bool = False):
-        if world == 1:
+        if world == 1 or shared is not None:   # shared plan: wepp_place exchanges the accumulators itself
             return
         if peer is not None and not full_counts:
             peer.merge()
@@ -319,7 +323,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     st = p.stats()
     # the exchange step alone: ranks aligned by a barrier first, CUDA events around it on the launching stream
     exch_ms = None
-    if world > 1:
+    if world > 1 and shared is not None:
+        t = torch.tensor([float(st["ms_exchange"])], device=f"cuda:{dev}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exch_ms = float(t.item())
+    elif world > 1:
         xs = []
         for _ in range(3):
             p.place(0, 0, sync=False)
@@ -436,8 +444,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                     "outputs": "as e2e, with mapped_read_counts[N][50] instead of dist_divergence"}
 
     parity = None
-    if not args.no_parity and rank == 0:
+    x_bytes = 0
+    if shared is not None:   # bytes one placement hands to the collective
+        b0 = shared.bytes
+        p.place(0, 0, sync=True)
+        x_bytes = shared.bytes - b0
+    if not args.no_parity and world == 1:
         parity = parity_block(p, arena, reads, dev)
+    elif not args.no_parity:
+        parity = multi_rank_checks(p, arena, reads, dev, world)
     e2e_cold = None
     if not args.no_e2e and rank == 0 and world == 1:
         e2e_cold = cold_sample(arena, reads, dev, q_env, k_env)
@@ -517,8 +532,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                      "bottleneck": bottleneck},
         "roofline_node_kernels": node_roofline(st, arena, peak),
         "clocks": clocks, "c5_rescore": c5,
-        "exchange": None if world == 1 else ("peer-memory merge kernel (wepp_peer_merge)" if peer is not None
-                                             else "NCCL all-reduce of score[N] + counts[N][50]"),
+        "exchange": None if world == 1 else (
+            "one plan on all ranks (cell histogram all-reduced in set_reads); NCCL all-reduce of the per-(bucket, state) "
+            f"accumulators inside wepp_place ({x_bytes} B per step)" if shared is not None
+            else ("peer-memory merge kernel (wepp_peer_merge)" if peer is not None else "NCCL all-reduce of score[N] + counts[N][50]")),
         "exchange_ms": exch_ms,
         "parity": parity, "e2e_cold": e2e_cold,
         "setup_s": {"flatten_tree": t_arena, "pack_reads_and_build_lists": t_reads},
@@ -622,6 +639,35 @@ def parity_block(p, arena, reads, dev):
             if v is not None:
                 os.environ[k] = v
     return out
+
+
+def multi_rank_checks(p, arena, reads, dev, world):
+    """N > 1 (all ranks call this): the merged per-node results are the same on every rank, and read support is
+    conserved over the whole job — for every count bin, sum over nodes of mapped_read_counts[v][b] equals the sum over
+    ALL ranks' reads in the bin of degree x multiplicity; the score mass equals the sum of degree / (1 + parsimony).
+    (The oracle cross-checks run at N = 1 and in tests/peer_worker.py on 2-4 GPUs.)"""
+    import torch
+    import torch.distributed as dist
+    p.place(0, 0, sync=True)
+    mp, mu = p.read_results()
+    sp, sb = p.device_buffer(1)
+    cp, cb = p.device_buffer(2)
+    score = cuda_view(sp, sb // 8, "<f8", dev)
+    counts = cuda_view(cp, cb // 4, "<i4", dev).view(-1, 50)
+    colsum = counts.sum(dim=0, dtype=torch.int64)
+    bins = np.minimum(reads.start // (arena.genome_size // 50), 49)
+    expect = torch.from_numpy(np.bincount(bins, weights=reads.degree.astype(np.float64) * mu, minlength=50).astype(np.int64)).to(colsum.device)
+    mass = torch.tensor([float((reads.degree / (1.0 + mp))[mu > 0].sum())], dtype=torch.float64, device=colsum.device)
+    dist.all_reduce(expect)
+    dist.all_reduce(mass)
+    sig = torch.cat([colsum.double(), score.sum().reshape(1), (score * torch.arange(1, score.numel() + 1, device=score.device)).sum().reshape(1)])
+    sigs = [torch.empty_like(sig) for _ in range(world)]
+    dist.all_gather(sigs, sig)
+    same = all(bool(torch.equal(s, sigs[0])) for s in sigs)
+    return {"ranks": world, "merged_results_identical_on_all_ranks": same,
+            "read_support_conserved": bool(torch.equal(colsum, expect)),
+            "score_mass_rel_err": float(abs(score.sum().item() - mass.item()) / mass.item()),
+            "all_green": bool(same and torch.equal(colsum, expect) and abs(score.sum().item() - mass.item()) <= 1e-9 * mass.item())}
 
 
 def cold_sample(arena, reads, dev, q_env, k_env):

@@ -178,6 +178,25 @@ int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, const int32_t* 
 #define WEPP_BUF_MULT       4   /* int32[R], read order */
 int wepp_device_buffer(wepp_handle* h, int32_t which, void** dev_ptr, int64_t* n_bytes);
 
+/* ---- Read-sharded ranks (one process per GPU): one plan, one exchange of accumulators ------------------
+ * The reference merges its threads' dense per-node arrays under a mutex (src/WEPP/initial_filter.cpp:199-211).
+ * Here ranks hold disjoint read shards and the same tree, and the caller lends the library ONE collective — an
+ * in-place sum all-reduce over the ranks, stream-ordered on `cuda_stream` (ncclAllReduce in a C++ driver;
+ * torch.distributed.all_reduce in wepp_b200/multigpu.py).  With the hook set,
+ *   wepp_set_reads  sums the (window, bin) cell histogram and the true read counts over the ranks before the plan is
+ *                   derived, so every rank builds the SAME window lists, buckets and distinct states (only the bucket
+ *                   sizes and tiles are the rank's own);
+ *   wepp_place      sums the per-(bucket, state) accumulators (~100 MB at 8 M nodes; per-(bucket, entry) ones when the
+ *                   states opt out) over the ranks — instead of the N x 208 B per-node arrays — and then finishes the
+ *                   per-node score / read counts / divergence from the merged accumulators on every rank.
+ * Per-read results stay on the rank that owns the read.  All ranks must issue the same calls in the same order.
+ * The hook returns 0 on success.  Pass fn = NULL to go back to single-rank behaviour.  */
+#define WEPP_DTYPE_I32 0
+#define WEPP_DTYPE_I64 1
+#define WEPP_DTYPE_F64 2
+typedef int (*wepp_allreduce_fn)(void* user, void* dev_ptr, int64_t count, int32_t dtype, void* cuda_stream);
+int wepp_set_allreduce(wepp_handle* h, wepp_allreduce_fn fn, void* user);
+
 /* Introspection for benchmarks: numbers describing the last wepp_place.  */
 typedef struct wepp_stats {
     int64_t n_nodes, n_events, n_euler_entries;     /* tree */
@@ -195,7 +214,7 @@ typedef struct wepp_stats {
     int32_t place_path;                             /* 0 Euler-list scan, 1 distinct states, 2 sparse corrections over the states */
     int32_t n_states;                               /* distinct window-restricted haplotypes (paths 1, 2) */
     int32_t n_window_groups;                        /* (bucket, window) groups of the read set (path 2) */
-    int32_t reserved;
+    float   ms_exchange;                            /* read-sharded ranks: the accumulator all-reduce (not in ms_node_kernels) */
 } wepp_stats;
 int wepp_get_stats(wepp_handle* h, wepp_stats* out);
 

@@ -60,6 +60,33 @@ def main():
         np.testing.assert_allclose(sc2, o["score"], rtol=1e-9, atol=1e-15)
         peer.close()
         p.close()
+        # (c) one plan for all ranks + exchange of the per-(bucket, state) accumulators (wepp_set_allreduce): every
+        #     rank ends up with the merged per-node arrays; per-read results are the rank's own slice
+        for env in ({}, {"WEPP_DELTA_PLACE": "2"}, {"WEPP_DELTA_PLACE": "0"}, {"WEPP_STATE_PLACE": "0"}):
+            for k in ("WEPP_DELTA_PLACE", "WEPP_STATE_PLACE"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            q = Placer(dev)
+            q.set_stream(torch.cuda.current_stream().cuda_stream)
+            q.set_arena(arena)
+            shared = multigpu.SharedPlan(q, dev)
+            for _ in range(2):
+                q.set_reads(reads.slice(lo, hi))
+                q.place(0, 0, sync=False)
+            torch.cuda.synchronize()
+            assert shared.calls >= 8, shared.calls
+            sc3, ct3 = q.node_results()
+            sc4, dv4 = q.node_summary()
+            mp3, mu3 = q.read_results()
+            assert np.array_equal(ct3, o["counts"]), f"rank {rank} {env}: counts differ"
+            np.testing.assert_allclose(sc3, o["score"], rtol=1e-9, atol=1e-15)
+            np.testing.assert_allclose(sc4, o["score"], rtol=1e-9, atol=1e-15)
+            assert np.array_equal(dv4, odv), f"rank {rank} {env}: dist_divergence differs"
+            assert np.array_equal(mp3, o["max_parsimony"][lo:hi]) and np.array_equal(mu3, o["multiplicity"][lo:hi])
+            shared.close()
+            q.close()
+        for k in ("WEPP_DELTA_PLACE", "WEPP_STATE_PLACE"):
+            os.environ.pop(k, None)
     dist.barrier()
     if rank == 0:
         print("PEER_OK", flush=True)

@@ -428,3 +428,28 @@ def test_full_size_properties():
     assert np.array_equal(mp, mp2) and np.array_equal(mu, mu2) and np.array_equal(ct, ct2)
     np.testing.assert_allclose(sc, sc2, rtol=1e-12)
     p.close()
+
+
+def test_allreduce_hook_single_rank_is_identity():
+    """wepp_set_allreduce with a hook that sums over ONE rank (nothing to add): same results, and the library asks for
+    the cell histogram + true counts in set_reads and for the accumulators in place (the multi-rank run is
+    tests/peer_worker.py, which needs >= 2 GPUs)."""
+    arena, reads = cases.small_case(seed=23, n_reads=4000)
+    o = oracle.cartesian_map(arena, reads, None, n_threads=4)
+    p = Placer(0)
+    p.set_arena(arena)
+    seen = []
+    p.set_allreduce(lambda ptr, count, dtype, stream: seen.append((count, dtype)) or 0)
+    p.set_reads(reads)
+    assert [d for _, d in seen] == [0, 1]           # int32 histogram, int64 true counts
+    p.place(0, 0)
+    assert [d for _, d in seen[2:]] == [2, 0]       # float64 weights, int32 degrees
+    assert p.stats()["place_path"] == 2
+    mp, mu = p.read_results()
+    sc, ct = p.node_results()
+    assert np.array_equal(mp, o["max_parsimony"]) and np.array_equal(mu, o["multiplicity"]) and np.array_equal(ct, o["counts"])
+    np.testing.assert_allclose(sc, o["score"], rtol=SCORE_RTOL, atol=1e-15)
+    p.set_allreduce(None)
+    with pytest.raises(Exception):
+        p.place(0, 0)                                # the plan has to be derived again
+    p.close()

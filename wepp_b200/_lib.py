@@ -25,7 +25,7 @@ class WeppStats(C.Structure):
         "kernel_launches")] + [("ms_place_total", C.c_float), ("ms_scan_kernel", C.c_float),
                                ("ms_node_kernels", C.c_float), ("reads_per_tile", C.c_int32),
                                ("stripe_width", C.c_int32), ("place_path", C.c_int32), ("n_states", C.c_int32),
-                               ("n_window_groups", C.c_int32), ("reserved", C.c_int32)]
+                               ("n_window_groups", C.c_int32), ("ms_exchange", C.c_float)]
 
     def as_dict(self) -> dict:
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -43,6 +43,7 @@ SIGNATURES = {
     "wepp_set_arena": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, C.c_int32]),
     "wepp_set_reads": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, VP]),
     "wepp_set_mapped": (C.c_int, [VP, VP]),
+    "wepp_set_allreduce": (C.c_int, [VP, VP, VP]),
     "wepp_place": (C.c_int, [VP, C.c_int32, C.c_int64]),
     "wepp_place_subset": (C.c_int, [VP, C.c_int64, VP, C.c_int32, C.c_int64]),
     "wepp_get_read_results": (C.c_int, [VP, VP, VP]),

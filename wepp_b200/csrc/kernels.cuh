@@ -430,6 +430,15 @@ __global__ void cells_assign_kernel(const unsigned long long* __restrict__ pairs
 
 // cursor[b] starts at the bucket's first sorted position.  The order inside a bucket is the order
 // the atomics land in: it only decides which reads share a tile, never a result.
+// shared plan (wepp_set_allreduce): this rank's reads per bucket, from its own cell histogram
+__global__ void cells_local_count_kernel(const unsigned long long* __restrict__ pairs, int n, const int32_t* __restrict__ local_table,
+                                         int32_t* __restrict__ bucket_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t c = local_table[pairs[i] >> 32];
+    if (c) atomicAdd(bucket_count + (uint32_t)pairs[i], c);
+}
+
 __global__ void read_scatter_kernel(int64_t n_reads, const int32_t* __restrict__ cell,
                                     const int32_t* __restrict__ bucket_of_cell, unsigned long long* __restrict__ cursor,
                                     int64_t* __restrict__ perm) {

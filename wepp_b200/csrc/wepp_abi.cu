@@ -255,6 +255,12 @@ struct wepp_handle {
     int32_t peer_rank = -1, peer_world = 0;
     int64_t peer_true_counts[NBINS] = {};
     bool peer_merged = false;   // d_score_merged / d_div_count hold the merged results of the last place
+    // read-sharded ranks that agree on one plan and exchange the per-(bucket, state) accumulators: wepp_set_allreduce
+    wepp_allreduce_fn allreduce = nullptr;
+    void* allreduce_user = nullptr;
+    DevBuf<int32_t> d_table_local, d_bucket_count;
+    bool shared_plan = false;   // the plan of the resident reads was derived from the all-reduced cell histogram
+    bool exchange_timed = false;   // ev[4] was recorded after the exchange of the last place
 
     // K4 over the resident reads (rescore_tiles.cuh): candidate stacks, per-window candidate entries, results
     DevBuf<int64_t> d_st_off, d_ccnt, d_coff, d_am_off;
@@ -899,6 +905,21 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         ++launches;
     }
     CU(cudaEventRecord(h->ev[1], h->stream));
+    h->exchange_timed = false;
+    // read-sharded ranks: the accumulators of all ranks line up (one plan) — sum them, then finish per node
+    if (accumulate && h->allreduce && h->shared_plan && &dp == &h->full) {
+        int rc_x;
+        if (by_states) {
+            rc_x = h->allreduce(h->allreduce_user, h->d_saccS.p, dp.sacc_total, WEPP_DTYPE_F64, (void*)h->stream);
+            if (!rc_x) rc_x = h->allreduce(h->allreduce_user, h->d_saccC.p, dp.sacc_total, WEPP_DTYPE_I32, (void*)h->stream);
+        } else {
+            rc_x = h->allreduce(h->allreduce_user, h->d_accS.p, pl.acc_total, WEPP_DTYPE_F64, (void*)h->stream);
+            if (!rc_x) rc_x = h->allreduce(h->allreduce_user, h->d_accC.p, pl.acc_total, WEPP_DTYPE_I32, (void*)h->stream);
+        }
+        if (rc_x) return fail(WEPP_E_STATE, "the all-reduce hook failed");
+        CU(cudaEventRecord(h->ev[4], h->stream));
+        h->exchange_timed = true;
+    }
     h->div_count_valid = false;
     if (accumulate && node_tiles) {
         const bool by_state_acc = by_states;
@@ -1211,6 +1232,23 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
         const int blocks = (int)std::min<int64_t>((n_reads + 255) / 256, (int64_t)h->n_sms * 8);
         read_keys_kernel<<<blocks, 256, 0, st>>>(kp);
         CU(cudaGetLastError());
+    }
+    // Read-sharded ranks (wepp_set_allreduce): the cell histogram and the true read counts are summed over the ranks,
+    // so that every rank derives the SAME window lists, buckets and (from them) distinct states — the per-(bucket,
+    // state) accumulators of a placement then line up across ranks and are what the ranks exchange.  The rank's own
+    // histogram is kept for its bucket sizes.
+    h->shared_plan = false;
+    if (h->allreduce && device_keys) {
+        CU(h->d_table_local.ensure((size_t)n_cells));
+        CU(cudaMemcpyAsync(h->d_table_local.p, h->d_table.p, (size_t)n_cells * 4, cudaMemcpyDeviceToDevice, st));
+        if (h->allreduce(h->allreduce_user, h->d_table.p, n_cells, WEPP_DTYPE_I32, (void*)st) != 0 ||
+            h->allreduce(h->allreduce_user, h->d_true_counts.p, NBINS, WEPP_DTYPE_I64, (void*)st) != 0)
+            return fail(WEPP_E_STATE, "the all-reduce hook failed");
+        h->shared_plan = true;
+    } else if (h->allreduce) {
+        return fail(WEPP_E_INVALID, "read-sharded ranks need the device keying path (stripe geometry too fine for the cell table)");
+    }
+    if (n_reads > 0 || h->shared_plan) {
         if (device_keys) {
             CU(h->d_cell_pairs.ensure(CELL_PAIR_CAP));
             cells_compact_kernel<<<(unsigned)std::min<int64_t>((n_cells + 255) / 256, (int64_t)h->n_sms * 8), 256, 0, st>>>(
@@ -1224,6 +1262,8 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
     CU(cudaStreamSynchronize(st));   // also: the caller's buffers are consumed from here on
     lap("keying kernel + histogram out");
     if (st_status[0] != RP_OK) return fail(WEPP_E_INVALID, read_plan_error(st_status[0]));
+    if (h->shared_plan && st_status[1] != 0)
+        return fail(WEPP_E_INVALID, "read-sharded ranks need every read window inside the cell table's span");
     h->n_reads = n_reads;
     h->n_read_muts = nm;
 
@@ -1302,11 +1342,6 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
             }
             a0 = a1;
         }
-        std::vector<int64_t> first;
-        std::string err = finish_read_plan(h->es, h->opt_k, bucket_count, pl, first);
-        if (!err.empty()) return fail(WEPP_E_INVALID, err);
-        lap("descriptors (host)");
-        std::vector<unsigned long long> cursor(first.begin(), first.end());
         CU(h->d_bucket_of_cell.ensure((size_t)n_cells));   // only the occupied cells are ever read
         CU(upload(h->d_cell_assign, assign, st));
         if (!assign.empty()) {
@@ -1314,6 +1349,24 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
                                                                                         h->d_bucket_of_cell.p);
             CU(cudaGetLastError());
         }
+        if (h->shared_plan) {   // the structure came from the summed histogram; the bucket sizes are this rank's own
+            std::vector<int32_t> local(bucket_count.size(), 0);
+            CU(h->d_bucket_count.ensure(bucket_count.size()));
+            CU(cudaMemsetAsync(h->d_bucket_count.p, 0, bucket_count.size() * 4, st));
+            if (!assign.empty()) {
+                cells_local_count_kernel<<<(unsigned)((assign.size() + 255) / 256), 256, 0, st>>>(
+                    h->d_cell_assign.p, (int)assign.size(), h->d_table_local.p, h->d_bucket_count.p);
+                CU(cudaGetLastError());
+            }
+            CU(cudaMemcpyAsync(local.data(), h->d_bucket_count.p, local.size() * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            for (size_t b = 0; b < local.size(); ++b) bucket_count[b] = local[b];
+        }
+        std::vector<int64_t> first;
+        std::string err = finish_read_plan(h->es, h->opt_k, bucket_count, pl, first);
+        if (!err.empty()) return fail(WEPP_E_INVALID, err);
+        lap("descriptors (host)");
+        std::vector<unsigned long long> cursor(first.begin(), first.end());
         CU(upload(h->d_cursor, cursor, st));
         CU(h->full.perm.ensure(n));
         const int blocks = (int)std::min<int64_t>((n_reads + 255) / 256, (int64_t)h->n_sms * 8);
@@ -1333,6 +1386,16 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
     if (rc) return rc;
     lap("descriptors up + Euler lists");
     h->has_reads = true;
+    return WEPP_OK;
+}
+
+int wepp_set_allreduce(wepp_handle* h, wepp_allreduce_fn fn, void* user) {
+    if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
+    h->allreduce = fn;
+    h->allreduce_user = user;
+    h->has_reads = false;   // the plan has to be derived again, with or without the other ranks
+    h->has_results = false;
+    h->shared_plan = false;
     return WEPP_OK;
 }
 
@@ -1682,6 +1745,13 @@ int wepp_get_stats(wepp_handle* h, wepp_stats* out) {
         float ms_scan = 0, ms_node = 0;
         CU(cudaEventElapsedTime(&ms_scan, h->ev[0], h->ev[1]));
         CU(cudaEventElapsedTime(&ms_node, h->ev[1], h->ev[2]));
+        h->stats.ms_exchange = 0.f;
+        if (h->exchange_timed) {   // read-sharded ranks: the accumulator all-reduce sits between placement and node kernels
+            float ms_x = 0;
+            CU(cudaEventElapsedTime(&ms_x, h->ev[1], h->ev[4]));
+            h->stats.ms_exchange = ms_x;
+            ms_node -= ms_x;
+        }
         h->stats.ms_scan_kernel = ms_scan;
         h->stats.ms_node_kernels = ms_node;
         h->stats.ms_place_total = ms_scan + ms_node;

@@ -68,6 +68,26 @@ class Placer:
         m = None if mapped is None else _c(mapped, np.uint8)
         check(self.lib.wepp_set_mapped(self.h, ptr(m)))
 
+    def set_allreduce(self, fn) -> None:
+        """Read-sharded ranks (wepp_set_allreduce, include/wepp_b200.h): fn(dev_ptr: int, count: int, dtype: int,
+        cuda_stream: int) -> 0 sums the device array in place over the ranks (dtype: 0 int32, 1 int64, 2 float64).
+        None = single-rank behaviour.  Call before set_reads."""
+        if fn is None:
+            self._allreduce_cb = None
+            check(self.lib.wepp_set_allreduce(self.h, None, None))
+            return
+        proto = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p)
+
+        def tramp(_user, dev_ptr, count, dtype, stream):
+            try:
+                return int(fn(int(dev_ptr or 0), int(count), int(dtype), int(stream or 0)) or 0)
+            except Exception:   # never let an exception cross the C frame
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._allreduce_cb = proto(tramp)   # keep the thunk alive as long as the handle uses it
+        check(self.lib.wepp_set_allreduce(self.h, C.cast(self._allreduce_cb, C.c_void_p), None))
+
     # -- compute -----------------------------------------------------------------------------
     def set_stream(self, cuda_stream: int) -> None:
         """Run all later work on the caller's CUDA stream (e.g. torch.cuda.current_stream().cuda_stream)."""
