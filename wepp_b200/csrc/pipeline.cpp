@@ -319,13 +319,12 @@ std::string dump_barcode(Pipeline& p, const std::vector<int32_t>& haps) {
     // every non-N read mutation (after masking): de-duplicated as (position, allele) before the strings are made
     {
         const size_t g = ref.size();
-        std::vector<uint8_t> seen((g + 2) * 4, 0);
+        std::vector<uint8_t> seen((g + 2) * 16, 0);   // one slot per 4-bit code: a foreign .pb may carry IUPAC codes
         const ArenaHost& a = p.arena;
         for (size_t k = 0; k < a.rm_pos.size(); ++k) {
             const uint8_t nuc = a.rm_nuc[k];
             if (nuc == 15) continue;
-            const int b = nuc == 1 ? 0 : nuc == 2 ? 1 : nuc == 4 ? 2 : 3;
-            uint8_t& s = seen[(size_t)a.rm_pos[k] * 4 + (size_t)b];
+            uint8_t& s = seen[(size_t)a.rm_pos[k] * 16 + (size_t)(nuc & 15)];
             if (s) continue;
             s = 1;
             mutations.insert(mut_string(nuc_id(ref[(size_t)a.rm_pos[k] - 1]), a.rm_pos[k], nuc));

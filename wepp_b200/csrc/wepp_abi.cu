@@ -255,6 +255,7 @@ struct wepp_handle {
     int32_t peer_rank = -1, peer_world = 0;
     int64_t peer_true_counts[NBINS] = {};
     bool peer_merged = false;   // d_score_merged / d_div_count hold the merged results of the last place
+    bool peer_stale = false;    // the reads changed since wepp_peer_open: the summed true read counts are out of date
     // read-sharded ranks that agree on one plan and exchange the per-(bucket, state) accumulators: wepp_set_allreduce
     wepp_allreduce_fn allreduce = nullptr;
     void* allreduce_user = nullptr;
@@ -1147,6 +1148,16 @@ int wepp_set_arena(wepp_handle* h, int32_t n_nodes, const int32_t* parent, const
     h->sub.states_ready = false;
     h->full.lists_built = false;
     h->sub.lists_built = false;
+    if (h->peer_world > 0) {   // another tree may reallocate the exported per-node buffers: the peers' mappings must go
+        for (int g = 0; g < MAX_PEERS; ++g)
+            for (int b = 0; b < 4; ++b) {
+                if (h->peer_ptr[g][b] && g != h->peer_rank) cudaIpcCloseMemHandle(h->peer_ptr[g][b]);
+                h->peer_ptr[g][b] = nullptr;
+            }
+        h->peer_rank = -1;
+        h->peer_world = 0;
+        h->peer_merged = false;
+    }
     h->tree_on_device = false;
     h->st_cache.clear();
     h->st_cache_pos.clear();
@@ -1168,6 +1179,7 @@ int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const 
     h->has_reads = false;
     h->has_results = false;
     h->host_reads = false;
+    if (h->peer_world > 0) h->peer_stale = true;   // the ranks' true read counts were summed at wepp_peer_open
     cudaStream_t st = h->stream;
     const size_t n = (size_t)n_reads;
     // WEPP_TIMING=2: phase times on stderr (development aid; adds synchronisations)
@@ -1643,6 +1655,7 @@ int wepp_peer_open(wepp_handle* h, int32_t rank, int32_t world, const void* blob
     for (int j = 0; j < NBINS; ++j) h->peer_true_counts[j] = 0;
     h->peer_rank = rank;
     h->peer_world = world;
+    h->peer_stale = false;
     for (int g = 0; g < world; ++g) {
         if (pb[g].n_nodes != h->n_nodes) {
             peer_release(h);
@@ -1671,6 +1684,9 @@ int wepp_peer_open(wepp_handle* h, int32_t rank, int32_t world, const void* blob
 int wepp_peer_merge(wepp_handle* h) {
     if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
     if (h->peer_world < 1) return fail(WEPP_E_STATE, "wepp_peer_open must be called first");
+    if (h->peer_stale)
+        return fail(WEPP_E_STATE, "the reads changed since wepp_peer_open (the ranks' true read counts are summed there): "
+                                  "wepp_peer_export / wepp_peer_open again after wepp_set_reads");
     if (!h->has_results) return fail(WEPP_E_STATE, "no per-node results yet (call wepp_place)");
     CU(cudaSetDevice(h->device));
     PeerMergeParams p = {};
@@ -2272,10 +2288,10 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
             return fail(WEPP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));         \
         }                                                                                          \
     } while (0)
-    const int CAND_CAP = 1 << 20;
+    int cand_cap = 1 << 20;   // nodes within SCORE_EPSILON of the top score that fit the buffers (grown on demand)
     FCU(d_cur.ensure((size_t)n)); FCU(d_orig.ensure((size_t)n)); FCU(d_contrib.ensure((size_t)n));
     FCU(d_pmapped.ensure((size_t)n)); FCU(d_removed.ensure((size_t)std::max<int64_t>(R, 1)));
-    FCU(d_nodes.ensure(CAND_CAP)); FCU(d_fulls.ensure(CAND_CAP)); FCU(d_max.ensure(1)); FCU(d_count.ensure(1));
+    FCU(d_nodes.ensure((size_t)cand_cap)); FCU(d_fulls.ensure((size_t)cand_cap)); FCU(d_max.ensure(1)); FCU(d_count.ensure(1));
     FCU(d_list.ensure((size_t)std::max<int64_t>(R, 1)));
     FCU(cudaMemcpyAsync(d_cur.p, h->d_score.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
     FCU(cudaMemcpyAsync(d_orig.p, h->d_score.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
@@ -2324,15 +2340,18 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
         double top;
         std::memcpy(&top, &top_bits, 8);
         if (!(top >= PEAK_SCORE_EPSILON)) break;   // no available peaks (:401-404) / current is empty
-        FCU(cudaMemsetAsync(d_count.p, 0, sizeof(int), st));
-        peak_collect_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_cur.p, h->d_divergence.p, d_pmapped.p, n, top, d_count.p,
-                                                             d_nodes.p, d_fulls.p, CAND_CAP);
         int n_cand = 0;
-        FCU(cudaMemcpyAsync(&n_cand, d_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        FCU(cudaStreamSynchronize(st));
-        if (n_cand > CAND_CAP) {
-            release();
-            return fail(WEPP_E_CAPACITY, "more than 2^20 nodes tie for the top score");
+        for (;;) {
+            FCU(cudaMemsetAsync(d_count.p, 0, sizeof(int), st));
+            peak_collect_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_cur.p, h->d_divergence.p, d_pmapped.p, n, top, d_count.p,
+                                                                 d_nodes.p, d_fulls.p, cand_cap);
+            FCU(cudaMemcpyAsync(&n_cand, d_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            FCU(cudaStreamSynchronize(st));
+            if (n_cand <= cand_cap) break;
+            // more nodes tie for the top score than the buffers hold (one uninformative read alone can put millions of
+            // nodes at the same score; the reference walks its sorted list and never fails here): grow and collect again
+            cand_cap = n_cand;
+            FCU(d_nodes.ensure((size_t)cand_cap)); FCU(d_fulls.ensure((size_t)cand_cap));
         }
         cand_nodes.resize((size_t)n_cand);
         cand_full.resize((size_t)n_cand);

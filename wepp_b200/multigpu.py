@@ -79,15 +79,24 @@ class PeerMerge:
     def __init__(self, placer, rank: int, world: int, device: int, group=None):
         import torch
         import torch.distributed as dist
-        self.placer, self.group = placer, group
-        blobs = [None] * world
-        dist.all_gather_object(blobs, placer.peer_export(), group=group)
-        placer.peer_open(rank, world, b"".join(blobs))
+        self.placer, self.group, self.rank, self.world = placer, group, rank, world
+        self._open()
         self.token = torch.zeros(1, dtype=torch.int32, device=f"cuda:{device}")
+
+    def _open(self) -> None:
+        """Publish this rank's buffers and true read counts, map the peers'.  The summed true read counts belong to
+        the read sets resident at this moment: after a set_reads the library refuses to merge until this ran again."""
+        import torch.distributed as dist
+        blobs = [None] * self.world
+        dist.all_gather_object(blobs, self.placer.peer_export(), group=self.group)
+        self.placer.peer_open(self.rank, self.world, b"".join(blobs))
+        self._generation = getattr(self.placer, "reads_generation", 0)
 
     def merge(self) -> None:
         """Enqueue: barrier, merge kernel, barrier — all on the current (= the placer's) stream."""
         import torch.distributed as dist
+        if getattr(self.placer, "reads_generation", 0) != self._generation:   # every rank changed its reads: exchange again
+            self._open()
         dist.all_reduce(self.token, group=self.group)   # every rank's placement + scans are done
         self.placer.peer_merge()
         dist.all_reduce(self.token, group=self.group)   # every rank is done reading: the next place may overwrite

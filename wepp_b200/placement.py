@@ -63,6 +63,7 @@ class Placer:
              _c(reads.rm_off, np.int64), _c(reads.rm_pos, np.int32), _c(reads.rm_nuc, np.uint8))
         check(self.lib.wepp_set_reads(self.h, r[0].shape[0], *[ptr(x) for x in r]))
         self.n_reads = int(r[0].shape[0])
+        self.reads_generation = getattr(self, "reads_generation", 0) + 1
 
     def set_mapped(self, mapped) -> None:
         m = None if mapped is None else _c(mapped, np.uint8)
