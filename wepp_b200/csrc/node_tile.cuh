@@ -21,7 +21,7 @@ namespace wepp {
 
 constexpr int NT_TILE = 256;                   // nodes per block
 constexpr int NT_THREADS = 512;
-constexpr int NT_SEG = 64;                     // rows per scan segment
+constexpr int NT_SEG = 16;                     // rows per scan segment (a thread takes a column piece through registers)
 constexpr int NT_NSEG = NT_TILE / NT_SEG;
 constexpr int NT_SEG_WORDS = NT_SEG * NBINS + 4;   // + 4 words: the segments' columns fall into different banks, rows stay 16-byte aligned
 constexpr int NT_SMEM_CNT = NT_NSEG * NT_SEG_WORDS * 4;
@@ -72,6 +72,56 @@ __global__ void tile_ptr_kernel(const Entry* __restrict__ lists, const ListDesc*
     }
 }
 
+constexpr uint32_t NT_REC_POINT = 0x200u, NT_REC_SKIP = 0x400u;
+
+// entries per (tile, bucket), tile-major: the input of the scan that gives rec_off
+__global__ void tile_count_kernel(const int32_t* __restrict__ tile_ptr, const BucketDesc* __restrict__ buckets, int n_tiles,
+                                  int n_lists, int n_buckets, uint32_t* __restrict__ count) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > (int64_t)n_tiles * n_buckets) return;
+    if (k == (int64_t)n_tiles * n_buckets) {
+        count[k] = 0u;
+        return;
+    }
+    const int t = (int)(k / n_buckets), b = (int)(k % n_buckets);
+    const int l = buckets[b].list;
+    count[k] = (uint32_t)(tile_ptr[(size_t)(t + 1) * n_lists + l] - tile_ptr[(size_t)t * n_lists + l]);
+}
+
+// one thread per (bucket, entry): the entry's record at its place in the tile-major order
+template <bool BY_STATE>
+__global__ void tile_records_kernel(const uint32_t* __restrict__ ent_x, const int32_t* __restrict__ prev_boundary,
+                                    const ListDesc* __restrict__ list_desc, const BucketDesc* __restrict__ buckets,
+                                    const int32_t* __restrict__ tile_ptr, const uint32_t* __restrict__ rec_off,
+                                    const int32_t* __restrict__ sid, const int32_t* __restrict__ state_first,
+                                    const int64_t* __restrict__ sacc_off, int n_lists, int n_buckets,
+                                    uint32_t* __restrict__ rec_x, uint32_t* __restrict__ rec_cur, uint32_t* __restrict__ rec_prv) {
+    const int b = blockIdx.y;
+    const BucketDesc bd = buckets[b];
+    const ListDesc ld = list_desc[bd.list];
+    const uint32_t base = BY_STATE ? (uint32_t)sacc_off[b] : (uint32_t)bd.acc_off;
+    const int32_t first = BY_STATE ? state_first[bd.list] : 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ld.n; i += gridDim.x * blockDim.x) {
+        const uint32_t x = ent_x[ld.off + i];
+        const int idx = (int)(x & IDX_MASK), t = idx / NT_TILE;
+        const uint32_t slot = rec_off[(size_t)t * n_buckets + b] + (uint32_t)(i - tile_ptr[(size_t)t * n_lists + bd.list]);
+        const int pbi = prev_boundary[ld.off + i];
+        uint32_t cur = 0xFFFFFFFFu, prv = 0xFFFFFFFFu;
+        if (BY_STATE) {
+            const int32_t sc = sid[ld.off + i], sp = pbi >= 0 ? sid[ld.off + pbi] : -1;
+            if (sc >= 0) cur = base + (uint32_t)(sc - first);
+            if (sp >= 0) prv = base + (uint32_t)(sp - first);
+        } else {
+            cur = base + (uint32_t)i;
+            if (pbi >= 0) prv = base + (uint32_t)pbi;
+        }
+        rec_x[slot] = (uint32_t)(idx - t * NT_TILE) | ((x & ENT_POINT) ? NT_REC_POINT : 0u) | ((x & ENT_SKIP) ? NT_REC_SKIP : 0u) |
+                      ((uint32_t)bd.bin << 12);
+        rec_cur[slot] = cur;
+        rec_prv[slot] = prv;
+    }
+}
+
 struct NodeTileParams {
     const ListDesc* list_desc;
     const BucketDesc* buckets;
@@ -88,6 +138,13 @@ struct NodeTileParams {
     const int32_t* state_first;
     const int64_t* sacc_off;
     const SAccPacked* sacc;
+    // tile-major entry records (optional; nullptr: the per-bucket tables above are walked): rec_off[tile][bucket] = first
+    // record of the bucket's entries inside the tile; per record x = row | flags | bin << 12 and the indices of the
+    // entry's own and its predecessor's accumulator (0xFFFFFFFF: none, value 0)
+    const uint32_t* rec_off;
+    const uint32_t* rec_x;
+    const uint32_t* rec_cur;
+    const uint32_t* rec_prv;
     const uint8_t* mapped;
     double* score;
     int32_t* counts;               // [n_nodes][NBINS] or nullptr
@@ -177,6 +234,93 @@ __global__ void __launch_bounds__(NT_THREADS, 2) node_tile_kernel(const NodeTile
             }
         }
         U128 carry = {0ull, 0ull};   // this thread's share of the score at the tile's first node
+        if (p.rec_x != nullptr) {
+            // ---- tile-major records (tile_records_kernel): the tile's entries of all buckets lie back to back, each with
+            //      the indices of its own and its predecessor's accumulator: coalesced loads, one look-up level ----------
+            auto value_abs = [&](uint32_t idx, double& sv, int32_t& cv) {
+                sv = 0.0;
+                cv = 0;
+                if (idx == 0xFFFFFFFFu) return;
+                if (BY_STATE) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(p.sacc + idx));
+                    sv = __hiloint2double((int)v.y, (int)v.x);
+                    cv = (int32_t)v.z;
+                } else {
+                    sv = __ldg(p.accS + idx);
+                    cv = __ldg(p.accC + idx);
+                }
+            };
+            if (sub == 0) {   // the buckets' values at the tile's first node
+                for (int b = threadIdx.x; b < p.n_buckets; b += NT_THREADS) {
+                    const BucketDesc bd = p.buckets[b];
+                    const int enc = __ldg(p.tile_enc + (size_t)tile * p.n_lists + bd.list);
+                    int32_t key = enc;
+                    uint32_t acc_off = (uint32_t)bd.acc_off;
+                    int32_t first = 0;
+                    if (BY_STATE) {
+                        acc_off = (uint32_t)p.sacc_off[b];
+                        first = p.state_first[bd.list];
+                        if (enc >= 0) key = __ldg(p.sid + p.list_desc[bd.list].off + enc);
+                    }
+                    double sv;
+                    int32_t cv;
+                    value_at(acc_off, first, key, sv, cv);
+                    if (sv != 0.0) {
+                        unsigned long long lo;
+                        long long hi;
+                        dbl_to_fix(sv, lo, hi);
+                        carry = add128(carry, U128{lo, (unsigned long long)hi});
+                    }
+                    if (with_counts && cv != 0) atomicAdd(&cnt[nt_off(0, bd.bin)], cv);
+                }
+            }
+            const uint32_t r0 = __ldg(p.rec_off + (size_t)tile * p.n_buckets), r1 = __ldg(p.rec_off + (size_t)(tile + 1) * p.n_buckets);
+            for (uint32_t k0 = r0 + threadIdx.x; k0 < r1; k0 += NT_U * NT_THREADS) {
+                uint32_t x[NT_U], ic[NT_U], ip[NT_U];
+#pragma unroll
+                for (int u = 0; u < NT_U; ++u) {
+                    const uint32_t k = k0 + u * NT_THREADS;
+                    x[u] = NT_REC_SKIP;
+                    ic[u] = ip[u] = 0xFFFFFFFFu;
+                    if (k < r1) {
+                        x[u] = __ldg(p.rec_x + k);
+                        ic[u] = __ldg(p.rec_cur + k);
+                        ip[u] = __ldg(p.rec_prv + k);
+                    }
+                }
+                double cur[NT_U], prv[NT_U];
+                int32_t ccur[NT_U], cprv[NT_U];
+#pragma unroll
+                for (int u = 0; u < NT_U; ++u) {
+                    value_abs((x[u] & NT_REC_SKIP) ? 0xFFFFFFFFu : ic[u], cur[u], ccur[u]);
+                    value_abs((x[u] & NT_REC_SKIP) ? 0xFFFFFFFFu : ip[u], prv[u], cprv[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < NT_U; ++u) {
+                    if ((x[u] & NT_REC_SKIP) || (cur[u] == prv[u] && ccur[u] == cprv[u])) continue;
+                    const int row = (int)(x[u] & 0x1FFu);
+                    const int bn = (int)((x[u] >> 12) & 63u);
+                    const bool point = (x[u] & NT_REC_POINT) != 0u;
+                    const bool back = point && row + 1 < rows, spill = point && row + 1 == rows;
+                    if (cur[u] != prv[u]) {
+                        unsigned long long alo, blo;
+                        long long ahi, bhi;
+                        dbl_to_fix(cur[u], alo, ahi);
+                        dbl_to_fix(prv[u], blo, bhi);
+                        const unsigned long long lo = alo - blo;
+                        const long long hi = ahi - bhi - (alo < blo ? 1 : 0);
+                        nt_add128(limb, row, lo, (unsigned long long)hi);
+                        if (back) nt_add128(limb, row + 1, 0ull - lo, (unsigned long long)(~hi + (lo == 0ull ? 1 : 0)));
+                        if (spill) nt_add128<1>(spill_limb, 0, 0ull - lo, (unsigned long long)(~hi + (lo == 0ull ? 1 : 0)));
+                    }
+                    if (with_counts && ccur[u] != cprv[u]) {
+                        atomicAdd(&cnt[nt_off(row, bn)], ccur[u] - cprv[u]);
+                        if (back) atomicAdd(&cnt[nt_off(row + 1, bn)], cprv[u] - ccur[u]);
+                        if (spill) atomicAdd(&spill_cnt[bn], cprv[u] - ccur[u]);
+                    }
+                }
+            }
+        } else
         for (int b0 = 0; b0 < p.n_buckets; b0 += NT_BATCH) {
             if (b0 > 0) __syncthreads();
             // ---- NT_BPT buckets per thread: their entries inside the tile, and (first tile of the block) their
@@ -363,22 +507,29 @@ __global__ void __launch_bounds__(NT_THREADS, 2) node_tile_kernel(const NodeTile
         }
         if (!with_counts) continue;
         // ---- counts: scan down the rows, column by column: segment sums, then segment prefixes + rescan in place ----
-        const int seg = threadIdx.x / NBINS, col = threadIdx.x % NBINS;
-        if (seg < NT_NSEG) {
+        for (int pr = threadIdx.x; pr < NT_NSEG * NBINS; pr += NT_THREADS) {
+            const int seg = pr / NBINS, col = pr % NBINS;
             const int* c = cnt + seg * NT_SEG_WORDS + col;
+            int v[NT_SEG];   // independent loads, then the adds
+#pragma unroll
+            for (int i = 0; i < NT_SEG; ++i) v[i] = c[i * NBINS];
             int sum = 0;
-#pragma unroll 8
-            for (int i = 0; i < NT_SEG; ++i) sum += c[i * NBINS];
+#pragma unroll
+            for (int i = 0; i < NT_SEG; ++i) sum += v[i];
             segsum[seg * NBINS + col] = sum;
         }
         __syncthreads();
-        if (seg < NT_NSEG) {
+        for (int pr = threadIdx.x; pr < NT_NSEG * NBINS; pr += NT_THREADS) {
+            const int seg = pr / NBINS, col = pr % NBINS;
+            int* c = cnt + seg * NT_SEG_WORDS + col;
+            int v[NT_SEG];
+#pragma unroll
+            for (int i = 0; i < NT_SEG; ++i) v[i] = c[i * NBINS];
             int run = 0;
             for (int sg = 0; sg < seg; ++sg) run += segsum[sg * NBINS + col];
-            int* c = cnt + seg * NT_SEG_WORDS + col;
-#pragma unroll 8
+#pragma unroll
             for (int i = 0; i < NT_SEG; ++i) {
-                run += c[i * NBINS];
+                run += v[i];
                 c[i * NBINS] = run;
                 if (seg * NT_SEG + i == rows - 1) carry_cnt[col] = run + spill_cnt[col];   // before mapped rows are blanked
             }

@@ -189,6 +189,11 @@ struct wepp_handle {
         std::vector<std::pair<int32_t, int32_t>> list_ranges;
         DevBuf<int32_t> tile_ptr, tile_enc;   // [n_tiles + 1][n_lists]: node_tile.cuh
         DevBuf<uint32_t> ent_x;               // per list entry: idx | flags
+        // tile-major entry records of the node tile kernel (full plan): valid for rec_buckets / rec_mode
+        DevBuf<uint32_t> rec_off, rec_x, rec_cur, rec_prv;
+        bool rec_ready = false;
+        int rec_mode = -1;                    // 1: accumulators per (bucket, state); 0: per (bucket, entry)
+        std::vector<BucketDesc> rec_buckets;
         bool tile_ptr_ready = false;
         // distinct window-restricted haplotypes of the lists (state_place.cuh; built on demand, no mask)
         bool states_ready = false, states_usable = false;
@@ -221,7 +226,7 @@ struct wepp_handle {
         int64_t gscratch_words = 0;
         void release() {
             perm.release(); lists.release(); buckets.release(); tiles.release(); entries.release();
-            prev_boundary.release(); chunk_start.release(); tile_ptr.release(); tile_enc.release(); ent_x.release();
+            prev_boundary.release(); chunk_start.release(); tile_ptr.release(); tile_enc.release(); ent_x.release(); rec_off.release(); rec_x.release(); rec_cur.release(); rec_prv.release();
             sid.release(); state_first.release(); state_eoff.release(); sacc_off.release(); state_ent.release();
             state_list.release(); lpos_base.release(); post_off.release(); post.release(); order.release();
             rec.release(); mrec.release(); groups.release(); units.release(); base.release(); whist.release(); list_goff.release();
@@ -346,6 +351,7 @@ int upload_plan(wepp_handle* h, wepp_handle::DevPlan& dp, bool host_perm) {
     dp.lists_built = true;
     dp.final_for_mask = false;
     dp.tile_ptr_ready = false;
+    dp.rec_ready = false;
     dp.delta_groups_ready = false;   // the window groups (delta_place.cuh) belong to the read set
     }
     // the states (state_place.cuh) are a function of the tree and of the lists' stripe ranges only: they stay
@@ -427,6 +433,7 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     if (dp.states_ready) return WEPP_OK;
     dp.states_ready = true;
     dp.states_usable = false;
+    dp.rec_ready = false;
     const ReadPlan& pl = dp.plan;
     dp.state_ranges.clear();
     for (const ListDesc& l : pl.lists) dp.state_ranges.emplace_back(l.qs, l.qe);
@@ -938,6 +945,45 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
             ++launches;
         }
         np.sacc = h->d_sacc_packed.p;
+        // tile-major entry records for the full plan (kept while lists, buckets, states and the accumulator kind stay)
+        const bool rec_env = !(getenv("WEPP_TILE_RECORDS") && atoi(getenv("WEPP_TILE_RECORDS")) == 0);
+        if (rec_env && &dp == &h->full && (double)n_node_tiles * (double)pl.buckets.size() < 1.0e9) {
+            const int mode = by_state_acc ? 1 : 0;
+            bool same = dp.rec_ready && dp.rec_mode == mode && dp.rec_buckets.size() == pl.buckets.size();
+            for (size_t b = 0; same && b < pl.buckets.size(); ++b)
+                same = dp.rec_buckets[b].list == pl.buckets[b].list && dp.rec_buckets[b].bin == pl.buckets[b].bin &&
+                       dp.rec_buckets[b].acc_off == pl.buckets[b].acc_off;
+            if (!same) {
+                const size_t n_tb = (size_t)n_node_tiles * pl.buckets.size() + 1;
+                TmpBuf<uint32_t> tcount(h->stream);
+                CU(tcount.ensure(n_tb));
+                CU(dp.rec_off.ensure(n_tb));
+                CU(dp.rec_x.ensure((size_t)pl.acc_total)); CU(dp.rec_cur.ensure((size_t)pl.acc_total)); CU(dp.rec_prv.ensure((size_t)pl.acc_total));
+                tile_count_kernel<<<(unsigned)((n_tb + 255) / 256), 256, 0, h->stream>>>(dp.tile_ptr.p, dp.buckets.p, n_node_tiles,
+                                                                                         (int)pl.lists.size(), (int)pl.buckets.size(), tcount.p);
+                CU(cudaGetLastError());
+                size_t tmp = 0;
+                CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, tcount.p, dp.rec_off.p, (int)n_tb, h->stream));
+                CU(h->d_cub_tmp.ensure(tmp));
+                CU(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, tcount.p, dp.rec_off.p, (int)n_tb, h->stream));
+                int max_n = 0;
+                for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
+                dim3 rgrid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
+                if (mode == 1)
+                    tile_records_kernel<true><<<rgrid, 256, 0, h->stream>>>(dp.ent_x.p, dp.prev_boundary.p, dp.lists.p, dp.buckets.p, dp.tile_ptr.p,
+                                                                           dp.rec_off.p, dp.sid.p, dp.state_first.p, dp.sacc_off.p,
+                                                                           (int)pl.lists.size(), (int)pl.buckets.size(), dp.rec_x.p, dp.rec_cur.p, dp.rec_prv.p);
+                else
+                    tile_records_kernel<false><<<rgrid, 256, 0, h->stream>>>(dp.ent_x.p, dp.prev_boundary.p, dp.lists.p, dp.buckets.p, dp.tile_ptr.p,
+                                                                            dp.rec_off.p, nullptr, nullptr, nullptr,
+                                                                            (int)pl.lists.size(), (int)pl.buckets.size(), dp.rec_x.p, dp.rec_cur.p, dp.rec_prv.p);
+                CU(cudaGetLastError());
+                dp.rec_ready = true;
+                dp.rec_mode = mode;
+                dp.rec_buckets = pl.buckets;
+            }
+            np.rec_off = dp.rec_off.p; np.rec_x = dp.rec_x.p; np.rec_cur = dp.rec_cur.p; np.rec_prv = dp.rec_prv.p;
+        }
         np.mapped = h->has_mask ? h->d_mapped.p : nullptr;
         np.score = score_out ? score_out : h->d_score.p;
         np.counts = with_counts ? h->d_counts.p : nullptr;
