@@ -872,15 +872,6 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         delta_finalize_kernel<<<fgrid, 256, 0, h->stream>>>(dp.groups.p, dp.bucket_goff.p, dp.state_first.p, dp.buckets.p, dp.base.p,
                                                            dp.Gw.p, dp.Gc.p, dp.sacc_off.p, h->d_saccS.p, h->d_saccC.p);
         CU(cudaGetLastError());
-        if (!node_tiles) {
-            int max_n = 0;
-            for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
-            dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
-            state_scatter_kernel<<<grid, 256, 0, h->stream>>>(dp.lists.p, dp.buckets.p, dp.sid.p, dp.state_first.p, dp.sacc_off.p,
-                                                              h->d_saccS.p, h->d_saccC.p, h->d_accS.p, h->d_accC.p);
-            CU(cudaGetLastError());
-            ++launches;
-        }
         launches += 2;
     } else if (by_states) {
         StatePlaceParams sp = {};
@@ -894,15 +885,6 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         else if (k == 4) rc = launch_state_place<4>(h, sp, pp.n_tiles, pl.max_width);
         else rc = launch_state_place<2>(h, sp, pp.n_tiles, pl.max_width);
         if (rc) return rc;
-        if (!node_tiles) {
-            int max_n = 0;
-            for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
-            dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
-            state_scatter_kernel<<<grid, 256, 0, h->stream>>>(dp.lists.p, dp.buckets.p, dp.sid.p, dp.state_first.p, dp.sacc_off.p,
-                                                              h->d_saccS.p, h->d_saccC.p, h->d_accS.p, h->d_accC.p);
-            CU(cudaGetLastError());
-            ++launches;
-        }
         ++launches;
     } else if (pp.n_tiles > 0) {
         const int k = pl.reads_per_tile / 32;
@@ -929,6 +911,16 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         h->exchange_timed = true;
     }
     h->div_count_valid = false;
+    if (accumulate && by_states && !node_tiles) {
+        // the difference-array node path reads per-(bucket, entry) accumulators: spread the (merged) per-(bucket, state) ones
+        int max_n = 0;
+        for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
+        dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
+        state_scatter_kernel<<<grid, 256, 0, h->stream>>>(dp.lists.p, dp.buckets.p, dp.sid.p, dp.state_first.p, dp.sacc_off.p,
+                                                          h->d_saccS.p, h->d_saccC.p, h->d_accS.p, h->d_accC.p);
+        CU(cudaGetLastError());
+        ++launches;
+    }
     if (accumulate && node_tiles) {
         const bool by_state_acc = by_states;
         NodeTileParams np = {};
