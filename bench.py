@@ -631,7 +631,22 @@ def parity_block(p, arena, reads, dev):
             orc["score_zero_pattern_equal"] = bool(np.array_equal(sc == 0, o["score"] == 0))
             p.set_reads(reads)
         out["oracle_sample"] = orc
-        flags = [v for k, d in out.items() if isinstance(d, dict) for kk, v in d.items() if kk.endswith("_equal")]
+        # the distinct states are told apart by two 64-bit hashes + size: audit walk on a fresh handle (WEPP_STATE_VERIFY
+        # makes wepp_place fail if any evaluated list entry differs from the entries stored for its state)
+        from wepp_b200.placement import Placer
+        os.environ["WEPP_STATE_VERIFY"] = "1"
+        try:
+            q = Placer(dev)
+            q.set_arena(arena)
+            q.set_reads(reads)
+            q.place(0, 0)
+            out["states_verified_entry_by_entry"] = {"states": int(q.stats()["n_states"]), "equal": True}
+            q.close()
+        except Exception as e:
+            out["states_verified_entry_by_entry"] = {"equal": False, "error": repr(e)[:200]}
+        finally:
+            os.environ.pop("WEPP_STATE_VERIFY", None)
+        flags = [v for k, d in out.items() if isinstance(d, dict) for kk, v in d.items() if kk.endswith("_equal") or kk == "equal"]
         rels = [d["score_max_rel_diff"] for d in out.values() if isinstance(d, dict) and "score_max_rel_diff" in d]
         out["all_green"] = bool(all(flags) and all(x <= 1e-9 for x in rels))
     finally:

@@ -453,3 +453,14 @@ def test_allreduce_hook_single_rank_is_identity():
     with pytest.raises(Exception):
         p.place(0, 0)                                # the plan has to be derived again
     p.close()
+
+
+@pytest.mark.parametrize("name", ["tiny1", "star", "small"])
+def test_state_verify_mode(name, monkeypatch, capfd):
+    """WEPP_STATE_VERIFY=1: the distinct states are told apart by two 64-bit hashes + size (probabilistically exact);
+    the audit walk compares every evaluated list entry's actual state with the entries stored for its state."""
+    monkeypatch.setenv("WEPP_STATE_VERIFY", "1")
+    arena, reads = _rescore_case(name)
+    _check_state_path(arena, reads)
+    if name != "tiny1":   # (tiny trees may overflow the states' position cap and never build states)
+        assert "every entry equals its state's representative" in capfd.readouterr().err

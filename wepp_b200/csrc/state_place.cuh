@@ -63,7 +63,7 @@ struct StateWalkParams {
     const Entry* lists;
     const ListDesc* list_desc;
     int32_t n_lists;
-    int32_t pass;                 // -1: chunk nets ; 0: hashes ; 1: representatives' entries
+    int32_t pass;                 // -1: chunk nets ; 0: hashes ; 1: representatives' entries ; 2: verify (WEPP_STATE_VERIFY)
     // pass 0 out (per list entry)
     uint64_t* key;                // (list << 51 | hash >> 13), SW_NOT_EVAL for entries that are not evaluated
     uint64_t* h2;                 // second hash (size in the low byte)
@@ -76,6 +76,9 @@ struct StateWalkParams {
     const int32_t* state_ucnt;    // [S]
     const int32_t* state_first;   // [n_lists + 1] first state of each list
     Entry* state_ent;
+    // pass 2 in: the state index of every entry; out: entries whose state differs from their state's stored entries
+    const int32_t* sid;
+    unsigned long long* mismatches;
 };
 
 // five signed bytes packed as b0..b3 in z and b4 in the low byte of w
@@ -183,6 +186,29 @@ __global__ void state_walk_kernel(const StateWalkParams p) {
                         }
                     }
                 }
+            }
+            else if (p.pass == 2) {
+                // The states were identified by two 64-bit hashes (+ size): here every evaluated entry's actual state is
+                // compared, position by position, with the entries stored for the state it was assigned to.
+                const int s = p.sid[ld.off + i];
+                bool ok = s >= 0;
+                if (ok) {
+                    const int64_t e0 = p.state_eoff[s], e1 = p.state_eoff[s + 1];
+                    if (n_act == 0) {
+                        ok = e1 - e0 == 1 && p.state_ent[e0].z == 0u && (p.state_ent[e0].w & 0xFFu) == 0u;
+                    } else {
+                        ok = e1 - e0 == n_act;
+                        for (int a = 0; ok && a < n_act; ++a) {   // stored sorted by position: find each active position
+                            bool found = false;
+                            for (int64_t k = e0; k < e1; ++k) {
+                                const Entry se = p.state_ent[k];
+                                if ((se.w >> 16) == pos[a]) found = sw_pack(se.z, se.w) == tab[a];
+                            }
+                            ok = found;
+                        }
+                    }
+                }
+                if (!ok) atomicAdd(p.mismatches, 1ull);
             }
         } else if (p.pass == 0) {
             p.key[ld.off + i] = SW_NOT_EVAL;

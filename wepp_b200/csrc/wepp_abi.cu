@@ -532,6 +532,24 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     }
     CU(upload(dp.sacc_off, sacc, st));
     lap("walk: representatives");
+    if (getenv("WEPP_STATE_VERIFY") && atoi(getenv("WEPP_STATE_VERIFY")) != 0) {
+        // the states were told apart by two 64-bit hashes + size: compare every evaluated entry's actual state with the
+        // entries stored for the state it was assigned to (a third walk; a development / audit switch)
+        TmpBuf<unsigned long long> bad_states(st);
+        CU(bad_states.ensure(1));
+        CU(cudaMemsetAsync(bad_states.p, 0, 8, st));
+        wp.pass = 2;
+        wp.sid = dp.sid.p;
+        wp.mismatches = bad_states.p;
+        state_walk_kernel<<<walk_blocks, 128, 0, st>>>(wp);
+        CU(cudaGetLastError());
+        unsigned long long n_bad = 0;
+        CU(cudaMemcpyAsync(&n_bad, bad_states.p, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (n_bad) return fail(WEPP_E_STATE, "state verification: " + std::to_string(n_bad) + " list entries differ from the state they were hashed to");
+        fprintf(stderr, "[wepp] state verification: %lld list entries, %d states, every entry equals its state's representative\n",
+                (long long)E, n_states);
+    }
     dp.h_state_first = first;
     dp.max_list_states = 0;
     for (int l = 0; l < n_lists; ++l) dp.max_list_states = std::max(dp.max_list_states, first[(size_t)l + 1] - first[(size_t)l]);
