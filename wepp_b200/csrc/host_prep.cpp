@@ -3,6 +3,9 @@
 
 #include <cstdlib>
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cstring>
 #include <numeric>
 #include <thread>
@@ -61,87 +64,191 @@ std::string build_euler_stripes(int32_t n_nodes, const int32_t* parent, const in
             if (sub_end[v] > sub_end[parent[v]]) return "node numbering is not a preorder of the tree";
     }
 
-    // nearest-ancestor event per position, maintained along the DFS
-    std::vector<int64_t> last_ev((size_t)genome_size + 1, -1);
-    std::vector<int64_t> prev_ev((size_t)n_mut, -1);
-    {
-        std::vector<int32_t> stack;
-        for (int32_t v = 0; v < n_nodes; ++v) {
-            while (!stack.empty() && sub_end[stack.back()] <= v) {
-                int32_t u = stack.back();
-                stack.pop_back();
-                for (int64_t k = mut_off[u + 1] - 1; k >= mut_off[u]; --k) last_ev[mut_pos[k]] = prev_ev[k];
-            }
-            if (mut_off[v + 1] < mut_off[v]) return "mut_off must be non-decreasing";
-            for (int64_t k = mut_off[v]; k < mut_off[v + 1]; ++k) {
-                int32_t p = mut_pos[k];
-                if (p < 1 || p > genome_size) return "mutation position outside [1, genome_size]";
-                if (mut_nuc[k] < 1 || mut_nuc[k] > 15 || mut_ref[k] < 1 || mut_ref[k] > 15)
-                    return "mutation nucleotide code outside 1..15";
-                if (last_ev[p] >= mut_off[v]) return "a node has two mutations at the same position";
-                prev_ev[k] = last_ev[p];
-                last_ev[p] = k;
-            }
-            stack.push_back(v);
+    auto _t0 = std::chrono::steady_clock::now(); auto _lap=[&](const char* w){ if(getenv("WEPP_TIMING")){auto t=std::chrono::steady_clock::now(); fprintf(stderr,"[flatten] %-20s %.1f ms\n", w, std::chrono::duration<double,std::milli>(t-_t0).count()); _t0=t;} };
+    // ---- events grouped by genome position, node order inside a position: a parallel stable counting sort -----------
+    // The nearest ancestor event of an event — the "state before it" — only involves events at the SAME position, so
+    // positions are independent: one sequential DFS over the tree becomes a stack walk per position, and the host
+    // threads take stripes of positions.  Every event is copied next to its position's other events together with what
+    // the walk needs of its node (index, subtree end, alleles): the walks then read memory front to back.
+    struct PosEvent {
+        int64_t k;          // event index (emission rank)
+        int32_t v, v_end;   // node, subtree end
+        uint8_t nuc, ref;
+    };
+    if (n_mut >= (1ll << 33)) return "too many mutation events";
+    const int nt_all = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+    const int nt_sort = n_mut < (1 << 16) ? 1 : nt_all;
+    std::vector<std::string> t_error((size_t)nt_sort);
+    std::vector<std::vector<int64_t>> t_count((size_t)nt_sort, std::vector<int64_t>((size_t)genome_size + 2, 0));
+    auto node_range = [&](int t) { return std::make_pair((int32_t)((int64_t)n_nodes * t / nt_sort), (int32_t)((int64_t)n_nodes * (t + 1) / nt_sort)); };
+    auto run_threads = [&](int nt, auto&& fn) {
+        if (nt == 1) {
+            fn(0);
+            return;
         }
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(fn, t);
+        for (auto& x : th) x.join();
+    };
+    run_threads(nt_sort, [&](int t) {   // validation + per-thread histogram
+        const auto [v0, v1] = node_range(t);
+        std::vector<int64_t>& cnt = t_count[(size_t)t];
+        for (int32_t v = v0; v < v1; ++v) {
+            if (mut_off[v + 1] < mut_off[v]) { t_error[(size_t)t] = "mut_off must be non-decreasing"; return; }
+            for (int64_t k = mut_off[v]; k < mut_off[v + 1]; ++k) {
+                const int32_t p = mut_pos[k];
+                if (p < 1 || p > genome_size) { t_error[(size_t)t] = "mutation position outside [1, genome_size]"; return; }
+                if (mut_nuc[k] < 1 || mut_nuc[k] > 15 || mut_ref[k] < 1 || mut_ref[k] > 15) {
+                    t_error[(size_t)t] = "mutation nucleotide code outside 1..15";
+                    return;
+                }
+                ++cnt[(size_t)p];
+            }
+        }
+    });
+    for (const std::string& e : t_error)
+        if (!e.empty()) return e;
+    _lap("validate");
+    std::vector<int64_t> pos_off((size_t)genome_size + 2, 0);
+    {
+        int64_t run = 0;
+        for (int32_t p = 0; p <= genome_size; ++p) {   // thread t's events at p start after those of the threads before it
+            pos_off[(size_t)p] = run;
+            for (int t = 0; t < nt_sort; ++t) {
+                const int64_t c = t_count[(size_t)t][(size_t)p];
+                t_count[(size_t)t][(size_t)p] = run;
+                run += c;
+            }
+        }
+        pos_off[(size_t)genome_size + 1] = run;
     }
-
-    // entries (enter + exit), then counting sort by (stripe, idx)
+    std::vector<PosEvent> ev_at((size_t)n_mut);
+    run_threads(nt_sort, [&](int t) {
+        const auto [v0, v1] = node_range(t);
+        std::vector<int64_t>& cur = t_count[(size_t)t];
+        for (int32_t v = v0; v < v1; ++v)
+            for (int64_t k = mut_off[v]; k < mut_off[v + 1]; ++k)
+                ev_at[(size_t)cur[(size_t)mut_pos[k]]++] = PosEvent{k, v, sub_end[v], mut_nuc[k], mut_ref[k]};
+    });
+    _lap("by position");
     const int32_t q = stripe_width;
     const int32_t n_stripes = genome_size / q + 1;
-    std::vector<Entry> raw;
-    raw.reserve((size_t)n_mut * 2);
-    int64_t n_events = 0;
-    for (int32_t v = 0; v < n_nodes; ++v) {
-        for (int64_t k = mut_off[v]; k < mut_off[v + 1]; ++k) {
-            int d[5];
-            bool any = false;
-            const int64_t pk = prev_ev[k];
-            for (int c = 0; c < 5; ++c) {
-                int after = mismatch_after(c, mut_nuc[k], mut_ref[k]);
-                int before = pk < 0 ? mismatch_seed(c) : mismatch_after(c, mut_nuc[pk], mut_ref[pk]);
-                d[c] = after - before;
-                any |= d[c] != 0;
-            }
-            if (!any) continue;  // event changes nothing for any read: drop
-            ++n_events;
-            if (sub_end[v] == v + 1) {
-                // leaf: one POINT entry — node v's own score is the enclosing state plus this delta;
-                // the running prefix is not changed, so no EXIT entry is needed
-                raw.push_back(Entry{((uint32_t)v << 1) | 1u, (uint32_t)mut_pos[k], pack4(d), (uint32_t)(uint8_t)(int8_t)d[4]});
-                continue;
-            }
-            raw.push_back(Entry{(uint32_t)v << 1, (uint32_t)mut_pos[k], pack4(d), (uint32_t)(uint8_t)(int8_t)d[4]});
-            if (sub_end[v] < n_nodes) {
-                int nd[5];
-                for (int c = 0; c < 5; ++c) nd[c] = -d[c];
-                raw.push_back(Entry{(uint32_t)sub_end[v] << 1, (uint32_t)mut_pos[k], pack4(nd), (uint32_t)(uint8_t)(int8_t)nd[4]});
+    struct Keyed {
+        uint64_t order;   // key (idx << 1 | point) << 34 | emission rank (2 * event + exit): the master order within a stripe
+        Entry e;
+    };
+    std::vector<std::vector<Entry>> stripe_entries((size_t)n_stripes);
+    std::vector<int64_t> stripe_events((size_t)n_stripes, 0);
+    std::vector<std::string> stripe_error((size_t)n_stripes);
+    auto do_stripe = [&](int32_t s, std::vector<Keyed>& keyed, std::vector<int64_t>& stack) {
+        keyed.clear();
+        const int32_t p_lo = std::max(1, s * q), p_hi = std::min(genome_size, s * q + q - 1);
+        for (int32_t p = p_lo; p <= p_hi; ++p) {
+            const int64_t a0 = pos_off[(size_t)p], a1 = pos_off[(size_t)p + 1];
+            stack.clear();
+            for (int64_t j = a0; j < a1; ++j) {   // events at p in node (= preorder) order
+                const PosEvent& ev = ev_at[(size_t)j];
+                const int64_t k = ev.k;
+                const int32_t v = ev.v;
+                while (!stack.empty() && ev_at[(size_t)stack.back()].v_end <= v) stack.pop_back();
+                if (!stack.empty() && ev_at[(size_t)stack.back()].v == v) {
+                    stripe_error[(size_t)s] = "a node has two mutations at the same position";
+                    return;
+                }
+                const PosEvent* pe = stack.empty() ? nullptr : &ev_at[(size_t)stack.back()];
+                stack.push_back(j);
+                int d[5];
+                bool any = false;
+                for (int c = 0; c < 5; ++c) {
+                    const int after = mismatch_after(c, ev.nuc, ev.ref);
+                    const int before = pe == nullptr ? mismatch_seed(c) : mismatch_after(c, pe->nuc, pe->ref);
+                    d[c] = after - before;
+                    any |= d[c] != 0;
+                }
+                if (!any) continue;  // event changes nothing for any read: drop
+                ++stripe_events[(size_t)s];
+                if (ev.v_end == v + 1) {
+                    // leaf: one POINT entry — node v's own score is the enclosing state plus this delta;
+                    // the running prefix is not changed, so no EXIT entry is needed
+                    const uint32_t key = ((uint32_t)v << 1) | 1u;
+                    keyed.push_back(Keyed{((uint64_t)key << 34) | (uint64_t)(2 * k),
+                                          Entry{key, (uint32_t)p, pack4(d), (uint32_t)(uint8_t)(int8_t)d[4]}});
+                    continue;
+                }
+                const uint32_t key = (uint32_t)v << 1;
+                keyed.push_back(Keyed{((uint64_t)key << 34) | (uint64_t)(2 * k), Entry{key, (uint32_t)p, pack4(d), (uint32_t)(uint8_t)(int8_t)d[4]}});
+                if (ev.v_end < n_nodes) {
+                    int nd[5];
+                    for (int c = 0; c < 5; ++c) nd[c] = -d[c];
+                    const uint32_t xkey = (uint32_t)ev.v_end << 1;
+                    keyed.push_back(Keyed{((uint64_t)xkey << 34) | (uint64_t)(2 * k + 1),
+                                          Entry{xkey, (uint32_t)p, pack4(nd), (uint32_t)(uint8_t)(int8_t)nd[4]}});
+                }
             }
         }
-    }
-    // pass 1: stable counting sort by key = (idx << 1 | point): at one preorder index the
-    // boundary entries (exits of subtrees ending here, the node's own enters) precede its point entries
-    std::vector<Entry> by_idx(raw.size());
+        // master order: by key; at one key in emission order (node, event, enter before exit) — what a stable sort by key
+        // of the sequential emission gives: exits of subtrees ending at a node, its own enters, then its point entries
+        std::sort(keyed.begin(), keyed.end(), [](const Keyed& x, const Keyed& y) { return x.order < y.order; });
+        std::vector<Entry>& dst = stripe_entries[(size_t)s];
+        dst.resize(keyed.size());
+        for (size_t i = 0; i < keyed.size(); ++i) dst[i] = keyed[i].e;
+    };
     {
-        std::vector<int64_t> cnt((size_t)2 * n_nodes + 1, 0);
-        for (const Entry& e : raw) ++cnt[e.x + 1];
-        for (int64_t v = 0; v < (int64_t)2 * n_nodes; ++v) cnt[v + 1] += cnt[v];
-        for (const Entry& e : raw) by_idx[cnt[e.x]++] = e;
+        int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+        if (n_mut < (1 << 16)) nt = 1;
+        std::atomic<int32_t> next{0};
+        auto worker = [&]() {
+            std::vector<Keyed> keyed;
+            std::vector<int64_t> stack;
+            for (;;) {
+                const int32_t s0 = next.fetch_add(8);
+                if (s0 >= n_stripes) break;
+                for (int32_t s = s0; s < std::min(n_stripes, s0 + 8); ++s) do_stripe(s, keyed, stack);
+            }
+        };
+        if (nt == 1) {
+            worker();
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; ++t) th.emplace_back(worker);
+            for (auto& x : th) x.join();
+        }
     }
-    raw.clear();
-    raw.shrink_to_fit();
-    // pass 2: stable counting sort by stripe
+    _lap("stripes");
+    for (const std::string& e : stripe_error)
+        if (!e.empty()) return e;
     out.stripe_width = q;
     out.n_stripes = n_stripes;
-    out.n_events = n_events;
+    out.n_events = 0;
     out.stripe_off.assign((size_t)n_stripes + 1, 0);
-    for (const Entry& e : by_idx) ++out.stripe_off[e.y / q + 1];
-    for (int32_t s = 0; s < n_stripes; ++s) out.stripe_off[s + 1] += out.stripe_off[s];
-    out.entries.resize(by_idx.size());
-    {
-        std::vector<int64_t> cur(out.stripe_off.begin(), out.stripe_off.end() - 1);
-        for (const Entry& e : by_idx) out.entries[cur[e.y / q]++] = e;
+    for (int32_t s = 0; s < n_stripes; ++s) {
+        out.n_events += stripe_events[(size_t)s];
+        out.stripe_off[(size_t)s + 1] = out.stripe_off[(size_t)s] + (int64_t)stripe_entries[(size_t)s].size();
     }
+    out.entries.resize((size_t)out.stripe_off[(size_t)n_stripes]);
+    {
+        int nt = (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+        if (out.entries.size() < (1u << 16)) nt = 1;
+        std::atomic<int32_t> next{0};
+        auto copier = [&]() {
+            for (;;) {
+                const int32_t s0 = next.fetch_add(16);
+                if (s0 >= n_stripes) break;
+                for (int32_t s = s0; s < std::min(n_stripes, s0 + 16); ++s) {
+                    const std::vector<Entry>& src = stripe_entries[(size_t)s];
+                    if (!src.empty()) std::memcpy(out.entries.data() + out.stripe_off[(size_t)s], src.data(), src.size() * sizeof(Entry));
+                }
+            }
+        };
+        if (nt == 1) {
+            copier();
+        } else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; ++t) th.emplace_back(copier);
+            for (auto& x : th) x.join();
+        }
+    }
+    _lap("copy");
     return "";
 }
 
