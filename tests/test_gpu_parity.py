@@ -312,21 +312,16 @@ def test_state_place_matches_oracle(name, q, k, monkeypatch):
     _check_state_path(arena, reads, q, k, path=(0, 1) if name.startswith("tiny") or name == "c4" else 1)   # tiny / wide windows may exceed the states' position cap
 
 
-@pytest.mark.parametrize("cand,tab,spill", [(None, None, None), (0, None, None), (3, None, 0), (None, 0, None), (None, 2, 0), (5, 1, 4)])
+@pytest.mark.parametrize("cand", [None, 0, 3])
 @pytest.mark.parametrize("name,q,k", [("tiny0", 8, 8), ("tiny1", 8, 4), ("tiny2", 16, 2), ("tiny3", 4, 0), ("tiny4", 32, 8),
                                       ("tiny5", 1, 2), ("star", 32, 8), ("star", 16, 0), ("small", 32, 0), ("small", 16, 4)])
-def test_delta_place_matches_oracle(name, q, k, cand, tab, spill, monkeypatch):
+def test_delta_place_matches_oracle(name, q, k, cand, monkeypatch):
     """delta_place.cuh: sparse corrections per read over the states.  WEPP_DELTA_PLACE=2 forces the path on read sets
     with a window per read (the tiny cases: all-N reads and reads with dozens of mutations take the byte-scratch
-    route); WEPP_DELTA_CAND / WEPP_DELTA_TQ shrink the queues of multi-hit states in shared memory (the rest spills to
-    global memory), WEPP_DELTA_SPILL the spill areas (the read is handed to the slow path mid-way)."""
+    route); WEPP_DELTA_CAND shrinks the candidate queue so that the posting re-walk runs too."""
     monkeypatch.setenv("WEPP_DELTA_PLACE", "2")
     if cand is not None:
         monkeypatch.setenv("WEPP_DELTA_CAND", str(cand))
-    if tab is not None:
-        monkeypatch.setenv("WEPP_DELTA_TQ", str(tab))
-    if spill is not None:
-        monkeypatch.setenv("WEPP_DELTA_SPILL", str(spill))
     arena, reads = _rescore_case(name)
     _check_state_path(arena, reads, q, k, path=(0, 2) if name.startswith("tiny") else 2)
 

@@ -212,29 +212,25 @@ struct wepp_handle {
         DevBuf<int32_t> state_list, lpos_base;
         DevBuf<uint32_t> post_off;
         DevBuf<uint2> post;
-        DevBuf<uint32_t> postm;
-        DevBuf<int32_t> state_nodes;
         int32_t n_groups = 0, n_units = 0;
         int64_t delta_touch_est = 0;
         DevBuf<uint32_t> order;
         DevBuf<uint4> rec;
-        DevBuf<uint4> mrec;
+        DevBuf<uint2> mrec;
         DevBuf<DeltaGroup> groups;
         DevBuf<DeltaUnit> units;
         DevBuf<uint8_t> base;
         DevBuf<int32_t> whist, list_goff, list_gids, bucket_goff, Gc;
         DevBuf<double> Gw;
-        DevBuf<DeltaW> W;
-        int64_t w_cells = 0;
-        DevBuf<uint32_t> gscratch, gspill;
+        DevBuf<uint32_t> gscratch;
         int64_t gscratch_words = 0;
         void release() {
             perm.release(); lists.release(); buckets.release(); tiles.release(); entries.release();
             prev_boundary.release(); chunk_start.release(); tile_ptr.release(); tile_enc.release(); ent_x.release(); rec_off.release(); rec_x.release(); rec_cur.release(); rec_prv.release();
             sid.release(); state_first.release(); state_eoff.release(); sacc_off.release(); state_ent.release();
-            state_list.release(); lpos_base.release(); post_off.release(); post.release(); postm.release(); state_nodes.release(); order.release();
+            state_list.release(); lpos_base.release(); post_off.release(); post.release(); order.release();
             rec.release(); mrec.release(); groups.release(); units.release(); base.release(); whist.release(); list_goff.release();
-            list_gids.release(); bucket_goff.release(); Gc.release(); Gw.release(); W.release(); gscratch.release(); gspill.release();
+            list_gids.release(); bucket_goff.release(); Gc.release(); Gw.release(); gscratch.release();
         }
     };
     DevPlan full, sub;
@@ -451,8 +447,7 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     Laps lap("build_states", st);
     TmpBuf<uint64_t> key(st), key2(st), h2(st);
     TmpBuf<uint32_t> val(st), val2(st);
-    TmpBuf<int32_t> overflow(st), flag(st), incl(st), rep_state(st), state_rep(st);
-    DevBuf<int32_t>& state_ucnt = dp.state_nodes;   // countable nodes per state: kept for delta_place_kernel
+    TmpBuf<int32_t> overflow(st), flag(st), incl(st), rep_state(st), state_ucnt(st), state_rep(st);
     DevBuf<int32_t>& state_list = dp.state_list;
     TmpBuf<int64_t> state_len(st);
     dp.delta_usable = false;
@@ -570,19 +565,17 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
         if (fits) {
             TmpBuf<uint32_t> slot_count(st);
             TmpBuf<uint64_t> pkey(st), pkey2(st), pval(st);
-            TmpBuf<uint32_t> pmask(st);
             TmpBuf<int32_t> bad(st);
             const size_t TE = (size_t)std::max<int64_t>(total_ent, 1);
             CU(upload(dp.lpos_base, lpos, st));
             CU(slot_count.ensure((size_t)slots + 1)); CU(bad.ensure(1));
-            CU(pkey.ensure(TE)); CU(pkey2.ensure(TE)); CU(pval.ensure(TE)); CU(pmask.ensure(TE));
+            CU(pkey.ensure(TE)); CU(pkey2.ensure(TE)); CU(pval.ensure(TE));
             CU(dp.post_off.ensure((size_t)slots + 1));
-            CU(dp.post.ensure(TE)); CU(dp.postm.ensure(TE));
+            CU(dp.post.ensure(TE));
             CU(cudaMemsetAsync(slot_count.p, 0, ((size_t)slots + 1) * 4, st));
             CU(cudaMemsetAsync(bad.p, 0, 4, st));
             post_pairs_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(dp.state_ent.p, dp.state_eoff.p, state_list.p, dp.state_first.p,
-                                                                          dp.lpos_base.p, dp.lists.p, n_states, slot_count.p, pkey.p, pval.p,
-                                                                          pmask.p, bad.p);
+                                                                          dp.lpos_base.p, n_states, slot_count.p, pkey.p, pval.p, bad.p);
             CU(cudaGetLastError());
             CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, slot_count.p, dp.post_off.p, (int)(slots + 1), st));
             CU(h->d_cub_tmp.ensure(tmp));
@@ -595,18 +588,13 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
             CU(h->d_cub_tmp.ensure(tmp));
             CU(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp.p, tmp, pkey.p, pkey2.p, pval.p, reinterpret_cast<uint64_t*>(dp.post.p),
                                                (int)total_ent, 0, 16 + slot_bits, st));
-            // the mask words take the same (stable) permutation
-            CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, pkey.p, pkey2.p, pmask.p, dp.postm.p, (int)total_ent, 0, 16 + slot_bits, st));
-            CU(h->d_cub_tmp.ensure(tmp));
-            CU(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp.p, tmp, pkey.p, pkey2.p, pmask.p, dp.postm.p, (int)total_ent, 0, 16 + slot_bits, st));
             int32_t h_bad = 0;
             CU(cudaMemcpyAsync(&h_bad, bad.p, 4, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
-            // shared memory of delta_place_kernel: the warps' fixed areas + the widest list's base scores
+            // shared memory of delta_place_kernel: the widest list's base scores + at least 4 warps' nibble scratch
             const int64_t s_max = dp.max_list_states;
-            const int64_t need = DP_FIXED + ((s_max + 15) & ~15ll) + dp_scratch_stride((int)s_max);   // at least one warp's nibble scratch
-            // (checked against one of DP_CTAS shares of the SM's shared memory: the launch never asks for more)
-            dp.delta_usable = h_bad == 0 && need <= ((int64_t)h->smem_optin + 1024) / DP_CTAS - 1024;
+            const int64_t need = DP_FIXED + ((s_max + 15) & ~15ll) + 4 * (((((s_max + 7) / 8 * 4) + 15) & ~15ll) + DP_CAND_MIN * 4);
+            dp.delta_usable = h_bad == 0 && need <= (int64_t)h->smem_optin;
             if (getenv("WEPP_TIMING") && atoi(getenv("WEPP_TIMING")) != 0)
                 fprintf(stderr, "[wepp timing] postings: %lld slots, %lld entries, tables %s, widest list %lld states, shared memory %lld of %lld -> %s\n",
                         (long long)slots, (long long)total_ent, h_bad ? "NOT of the allele form" : "ok", (long long)s_max, (long long)need,
@@ -678,7 +666,7 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
     std::vector<DeltaGroup> groups((size_t)n_groups);
     std::vector<DeltaUnit> units;
     std::vector<int32_t> bucket_goff((size_t)n_buckets + 1, 0), list_goff((size_t)n_lists + 1, 0), list_gids((size_t)n_groups);
-    int64_t base_total = 0, first = 0, w_cells = 0;
+    int64_t base_total = 0, first = 0;
     for (int g = 0; g < n_groups; ++g) {
         DeltaGroup& dg = groups[(size_t)g];
         dg.bucket = (int32_t)(hk[(size_t)g] >> 24);
@@ -686,10 +674,8 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
         dg.a_rel = (int32_t)((hk[(size_t)g] >> 12) & 0xFFFu);
         dg.b_rel = (int32_t)(hk[(size_t)g] & 0xFFFu);
         dg.m0 = 0;
-        dg.clip = std::min(dg.a_rel, 16) | (std::max(0, std::min(pl.lists[(size_t)dg.list].width - 1 - dg.b_rel, 16)) << 8);
+        dg.pad = 0;
         dg.base_off = base_total;
-        dg.w_off = w_cells;
-        w_cells += (int64_t)(dg.b_rel - dg.a_rel + 1) * 15;
         const int64_t s_n = dp.h_state_first[(size_t)dg.list + 1] - dp.h_state_first[(size_t)dg.list];
         base_total += (s_n + 15) & ~15ll;
         ++bucket_goff[(size_t)dg.bucket + 1];
@@ -702,7 +688,7 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
         }
         first += hc[(size_t)g];
     }
-    if (base_total > (8ll << 30) || w_cells > (1ll << 27)) return WEPP_OK;   // (2 GiB of W cells)
+    if (base_total > (8ll << 30)) return WEPP_OK;
     for (int b = 0; b < n_buckets; ++b) bucket_goff[(size_t)b + 1] += bucket_goff[(size_t)b];
     for (int l = 0; l < n_lists; ++l) list_goff[(size_t)l + 1] += list_goff[(size_t)l];
     {
@@ -719,8 +705,6 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
     CU(dp.whist.ensure((size_t)n_groups * DP_BINS));
     CU(dp.Gw.ensure((size_t)n_groups * DP_BINS));
     CU(dp.Gc.ensure((size_t)n_groups * DP_BINS));
-    CU(dp.W.ensure((size_t)std::max<int64_t>(w_cells, 1)));
-    dp.w_cells = w_cells;
     CU(cudaMemsetAsync(dp.whist.p, 0, (size_t)n_groups * DP_BINS * 4, st));
     CU(cudaMemsetAsync(dp.base.p, 0, (size_t)std::max<int64_t>(base_total, 16), st));
     WindowBaseParams wb = {};
@@ -731,10 +715,9 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
     CU(cudaGetLastError());
     window_m0_kernel<<<(n_groups + 255) / 256, 256, 0, st>>>(dp.whist.p, n_groups, dp.groups.p);
     CU(cudaGetLastError());
-    // byte scratch in global memory for the reads that take the slow path: one area per warp of the persistent grid
+    // byte scratch in global memory for the reads with many mutations: one area per warp of the persistent grid
     const int64_t words = ((int64_t)dp.max_list_states + 3) / 4 + 4;
-    CU(dp.gspill.ensure((size_t)h->n_sms * DP_CTAS * DP_WARPS * 2 * DP_SPILL));
-    const size_t need = (size_t)h->n_sms * DP_CTAS * DP_WARPS * (size_t)words;
+    const size_t need = (size_t)h->n_sms * DP_WARPS * (size_t)words;
     if (need > dp.gscratch.cap) {
         CU(dp.gscratch.ensure(need));
         CU(cudaMemsetAsync(dp.gscratch.p, 0, dp.gscratch.cap * 4, st));   // the kernel leaves it zero
@@ -886,58 +869,26 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     if (by_delta) {
         CU(cudaMemsetAsync(dp.Gw.p, 0, (size_t)dp.n_groups * DP_BINS * sizeof(double), h->stream));
         CU(cudaMemsetAsync(dp.Gc.p, 0, (size_t)dp.n_groups * DP_BINS * sizeof(int32_t), h->stream));
-        CU(cudaMemsetAsync(dp.W.p, 0, (size_t)dp.w_cells * sizeof(DeltaW), h->stream));
         DeltaPlaceParams dq = {};
         dq.units = dp.units.p; dq.n_units = dp.n_units; dq.unit_counter = h->d_tile_counter.p;
         dq.groups = dp.groups.p; dq.base = dp.base.p; dq.whist = dp.whist.p; dq.post = dp.post.p;
         dq.state_first = dp.state_first.p; dq.sacc_off = dp.sacc_off.p; dq.rec = dp.rec.p; dq.mrec = dp.mrec.p;
         dq.max_pars = h->d_maxpars.p; dq.mult = h->d_mult.p; dq.saccS = h->d_saccS.p; dq.saccC = h->d_saccC.p;
         dq.Gw = dp.Gw.p; dq.Gc = dp.Gc.p; dq.gscratch = dp.gscratch.p; dq.gscratch_words = dp.gscratch_words;
-        dq.postm = dp.postm.p;
-        dq.state_nodes = dp.state_nodes.p;
-        dq.W = dp.W.p;
-        dq.gspill = dp.gspill.p;
-        dq.spill_cap = DP_SPILL;
-        if (getenv("WEPP_DELTA_SPILL")) dq.spill_cap = std::max(0, std::min(DP_SPILL, atoi(getenv("WEPP_DELTA_SPILL"))));
-        // shared memory: the warps' fixed areas + the widest list's base scores + a nibble scratch per warp, as far as
-        // it fits (fewer warps work on the lists it does not fit for); as many CTAs per SM as that allows
+        // shared memory: fixed areas + the widest list's base scores + 16 warps' nibble scratch, as far as it fits
         const int64_t s_max = dp.max_list_states;
-        const int smem = (int)std::min<int64_t>(((int64_t)h->smem_optin + 1024) / DP_CTAS - 1024,
-                                                DP_FIXED + ((s_max + 15) & ~15ll) + (int64_t)DP_WARPS * dp_scratch_stride((int)s_max));
+        // (one CTA per SM: all of it — what the scratch areas leave is the warps' candidate queues)
+        const int smem = (int)h->smem_optin;
         dq.smem_bytes = smem;
-        dq.cand_cap = DP_CAND;
-        dq.tq_cap = DP_TQ;
-        if (getenv("WEPP_DELTA_CAND")) dq.cand_cap = std::max(0, std::min(DP_CAND, atoi(getenv("WEPP_DELTA_CAND"))));
-        if (getenv("WEPP_DELTA_TQ")) dq.tq_cap = std::max(0, std::min(DP_TQ, atoi(getenv("WEPP_DELTA_TQ"))));
-        const bool dp_stats = getenv("WEPP_DELTA_STATS") && atoi(getenv("WEPP_DELTA_STATS")) != 0;
-        TmpBuf<unsigned long long> dstats(h->stream);
-        if (dp_stats) {
-            CU(dstats.ensure(DP_STATS));
-            CU(cudaMemsetAsync(dstats.p, 0, DP_STATS * 8, h->stream));
-            dq.stats = dstats.p;
-        }
-        auto kern = dp_stats ? delta_place_kernel<true> : delta_place_kernel<false>;
-        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        int per_sm = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DP_WARPS * 32, (size_t)smem));
-        per_sm = std::max(1, std::min(per_sm, (int)DP_CTAS));
-        const int grid_dp = std::max(1, std::min(dp.n_units, h->n_sms * per_sm));
-        kern<<<grid_dp, DP_WARPS * 32, smem, h->stream>>>(dq);
+        dq.cand_cap = 1 << 20;
+        if (getenv("WEPP_DELTA_CAND")) dq.cand_cap = std::max(0, atoi(getenv("WEPP_DELTA_CAND")));
+        CU(cudaFuncSetAttribute(delta_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const int grid_dp = std::max(1, std::min(dp.n_units, h->n_sms));
+        delta_place_kernel<<<grid_dp, DP_WARPS * 32, smem, h->stream>>>(dq);
         CU(cudaGetLastError());
-        if (dp_stats) {
-            unsigned long long hs[DP_STATS];
-            CU(cudaMemcpyAsync(hs, dstats.p, sizeof(hs), cudaMemcpyDeviceToHost, h->stream));
-            CU(cudaStreamSynchronize(h->stream));
-            fprintf(stderr, "[wepp delta stats] reads %lld, hits %llu, possibly multi-hit %llu (distinct states settled %llu, touched queue "
-                            "overflowed for %llu reads), base looked up %llu, tracked %llu, truly multi-hit at or below m0 %llu, slow-path reads "
-                            "%llu; %d CTAs per SM, %d bytes of shared memory, %lld W cells\n",
-                    (long long)pl.n_reads, hs[DP_ST_HITS], hs[DP_ST_MULTI], hs[DP_ST_TAB_ENTRIES], hs[DP_ST_TQ_OVER], hs[DP_ST_CLIPPED],
-                    hs[DP_ST_TRACKED], hs[DP_ST_CAND], hs[DP_ST_SLOW_READS], per_sm, smem, (long long)dp.w_cells);
-        }
         dim3 fgrid((unsigned)std::min<int64_t>((s_max + 255) / 256, 1024), (unsigned)pl.buckets.size());
         delta_finalize_kernel<<<fgrid, 256, 0, h->stream>>>(dp.groups.p, dp.bucket_goff.p, dp.state_first.p, dp.buckets.p, dp.base.p,
-                                                           dp.Gw.p, dp.Gc.p, dp.W.p, dp.state_ent.p, dp.state_eoff.p, dp.sacc_off.p,
-                                                           h->d_saccS.p, h->d_saccC.p);
+                                                           dp.Gw.p, dp.Gc.p, dp.sacc_off.p, h->d_saccS.p, h->d_saccC.p);
         CU(cudaGetLastError());
         launches += 2;
     } else if (by_states) {
