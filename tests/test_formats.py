@@ -122,6 +122,89 @@ def test_mat_loader_gzip_by_file_name(tmp_path):
         wio.load_mat(str(tmp_path / "bad.pb.gz"))
 
 
+def test_mat_sidecar_round_trip_and_invalidation(tmp_path, monkeypatch):
+    """The flattened-tree sidecar (host_io.cpp): the second load of a file reads "<file>.wepp_flat" and gives the same
+    tree (condensed nodes, metadata, masked mutations and all); a changed source, a truncated or foreign sidecar and
+    WEPP_SIDECAR=0 all fall back to parsing; WEPP_SIDECAR_DIR moves it."""
+    monkeypatch.delenv("WEPP_SIDECAR", raising=False)
+    monkeypatch.delenv("WEPP_SIDECAR_DIR", raising=False)
+    pb = _random_mat(21, n_leaves=60)
+    src = tmp_path / "tree.pb.gz"
+    with gzip.open(src, "wb") as f:
+        f.write(pb)
+    side = tmp_path / "tree.pb.gz.wepp_flat"
+    for uncondense in (False, True):
+        want = formats.load_mat(pb, uncondense)
+        _compare_mat(wio.load_mat(str(src), uncondense), want)       # parses (and writes the sidecar the first time)
+        assert side.exists()
+        _compare_mat(wio.load_mat(str(src), uncondense), want)       # reads the sidecar
+    good = side.read_bytes()
+    # the sidecar really is what is read: a sidecar of ANOTHER tree under this source's key must show through
+    pb2 = _random_mat(22, n_leaves=33)
+    src2 = tmp_path / "other.pb"
+    src2.write_bytes(pb2)
+    wio.load_mat(str(src2))
+    other = (tmp_path / "other.pb.wepp_flat").read_bytes()
+    import struct
+    hdr = struct.calcsize("<8sQQq")
+    side.write_bytes(good[:hdr] + other[hdr:])
+    _compare_mat(wio.load_mat(str(src)), formats.load_mat(pb2, True))
+    # ... and a stale one must not: change the source
+    side.write_bytes(good)
+    pb3 = _random_mat(23, n_leaves=60)
+    with gzip.open(src, "wb") as f:
+        f.write(pb3)
+    _compare_mat(wio.load_mat(str(src)), formats.load_mat(pb3, True))
+    assert side.read_bytes() != good                                   # rewritten for the new source
+    # truncated / garbage sidecars are ignored
+    fresh = side.read_bytes()
+    for bad in (fresh[: len(fresh) // 2], b"not a sidecar", fresh[:-8], fresh + b"12345678"):
+        side.write_bytes(bad)
+        _compare_mat(wio.load_mat(str(src)), formats.load_mat(pb3, True))
+    # WEPP_SIDECAR=0: neither read nor written
+    side.unlink()
+    monkeypatch.setenv("WEPP_SIDECAR", "0")
+    _compare_mat(wio.load_mat(str(src)), formats.load_mat(pb3, True))
+    assert not side.exists()
+    monkeypatch.delenv("WEPP_SIDECAR")
+    # WEPP_SIDECAR_DIR
+    d = tmp_path / "cache"
+    d.mkdir()
+    monkeypatch.setenv("WEPP_SIDECAR_DIR", str(d))
+    _compare_mat(wio.load_mat(str(src)), formats.load_mat(pb3, True))
+    assert (d / "tree.pb.gz.wepp_flat").exists() and not side.exists()
+    # a directory that cannot be written to is not an error
+    monkeypatch.setenv("WEPP_SIDECAR_DIR", str(tmp_path / "does" / "not" / "exist"))
+    _compare_mat(wio.load_mat(str(src)), formats.load_mat(pb3, True))
+
+
+@pytest.mark.parametrize("threads", ["1", "3", "16"])
+def test_mat_loader_threads_and_unusual_newick(threads, monkeypatch):
+    """The token scan and the per-node mutation fill run on WEPP_THREADS host threads (the reference's
+    tbb::parallel_for, mutation_annotated_tree.cpp:556-596): any thread count gives the same tree — here on trees large
+    enough to be cut into ranges; Newick tokens of the unusual shape ('(' after a name or after ')') take the
+    one-thread token machine and still agree with the oracle's."""
+    monkeypatch.setenv("WEPP_THREADS", threads)
+    monkeypatch.setenv("WEPP_SIDECAR", "0")
+    pb = _random_mat(31, n_leaves=9000, meta=True, condensed=True)
+    _compare_mat(wio.parse_mat(pb, True), formats.load_mat(pb, True))
+    for nw in ("((A:0.1,B:0.2):0.3,(C,D)x:0.5)root;", "(A(B,C),D);", "((A,B)(C,D),E);", "((A:1,B):2,C:3):4;"):
+        data = formats.ParsimonyData()
+        data.newick = nw
+        try:
+            parent, ids, _, _ = formats.parse_newick(nw)
+        except Exception:
+            parent = None                        # the token machine runs out of branch lengths: malformed for both
+        for _ in range(len(parent) if parent else 8):
+            data.node_mutations.add()
+        if parent is None:
+            with pytest.raises(WeppError):
+                wio.parse_mat(data.SerializeToString(), False)
+            continue
+        got = wio.parse_mat(data.SerializeToString(), False)
+        assert got.parent.tolist() == parent and got.ids == ids, nw
+
+
 def test_mat_loader_rejects_bad_newick_and_truncated_files():
     data = formats.ParsimonyData()
     data.newick = "((A,B),C;"
