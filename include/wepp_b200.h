@@ -197,6 +197,40 @@ int wepp_device_buffer(wepp_handle* h, int32_t which, void** dev_ptr, int64_t* n
 typedef int (*wepp_allreduce_fn)(void* user, void* dev_ptr, int64_t count, int32_t dtype, void* cuda_stream);
 int wepp_set_allreduce(wepp_handle* h, wepp_allreduce_fn fn, void* user);
 
+/* ---- Several GPUs of one box from ONE process (the product driver's multi-GPU mode, WEPP_GPUS) -----------
+ * Replaces the chunk merge of the reference's TBB read decomposition (src/WEPP/initial_filter.cpp:152,
+ * :199-211) across devices: a group owns one handle and one host thread per rank, deals the reads round-robin
+ * (rank r holds the caller's reads r, r + G, ...), replicates the tree and serves the exchanges of
+ * wepp_set_allreduce itself — peer_allreduce_kernel reads and writes the other ranks' buffers over NVLink peer
+ * memory (rank r sums slice r of every buffer in rank order and stores it to every rank: bit-identical results
+ * on all ranks), ordered by CUDA events between the ranks' streams.  No collective library is involved.
+ * `devices` may be NULL (ranks on devices 0..n-1) and may name a device more than once (ranks sharing a GPU:
+ * how the single-GPU test box covers this path).
+ *   wepp_group_set_arena / set_reads / place   = wepp_set_arena / wepp_set_reads (dealt) / wepp_place(h, 0, 0) on
+ *     every rank at once; afterwards every rank holds the merged per-node results (wepp_get_node_results on
+ *     wepp_group_handle(g, 0)), wepp_group_get_read_results gathers the per-read ones in the caller's order.
+ *   wepp_group_filter_peaks = wepp_filter_peaks with the reads sharded: the cartesian_map exchanges the
+ *     per-(bucket, state) accumulators, every step of the peak loop the number of reads removed and the removed
+ *     reads' per-node weights; the ranks take the same decisions on identical merged scores.
+ *   wepp_group_run calls fn(rank, handle, user) on the ranks' threads concurrently (anything else that must run
+ *     in step); wepp_group_take removes a rank's handle from the group (hook cleared, caller owns it).  */
+typedef struct wepp_group wepp_group;
+typedef int (*wepp_group_fn)(int32_t rank, wepp_handle* h, void* user);
+int  wepp_group_create(int32_t n_ranks, const int32_t* devices, wepp_group** out);
+void wepp_group_destroy(wepp_group* g);
+int32_t wepp_group_size(const wepp_group* g);
+wepp_handle* wepp_group_handle(wepp_group* g, int32_t rank);
+wepp_handle* wepp_group_take(wepp_group* g, int32_t rank);
+int  wepp_group_run(wepp_group* g, wepp_group_fn fn, void* user);
+int  wepp_group_set_arena(wepp_group* g, int32_t n_nodes, const int32_t* parent, const int64_t* mut_off,
+                          const int32_t* mut_pos, const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size);
+int  wepp_group_set_reads(wepp_group* g, int64_t n_reads, const int32_t* start, const int32_t* end,
+                          const int32_t* degree, const int64_t* rm_off, const int32_t* rm_pos, const uint8_t* rm_nuc);
+int  wepp_group_place(wepp_group* g);
+int  wepp_group_get_read_results(wepp_group* g, int32_t* max_parsimony, int32_t* multiplicity);
+int  wepp_group_filter_peaks(wepp_group* g, const int32_t* leaf_count, const int32_t* id_rank, int32_t* out_nodes,
+                             int32_t capacity, int32_t* n_peaks, int32_t* n_out);
+
 /* Introspection for benchmarks: numbers describing the last wepp_place.  */
 typedef struct wepp_stats {
     int64_t n_nodes, n_events, n_euler_entries;     /* tree */

@@ -83,6 +83,20 @@ def test_detect_peaks_matches_reference_binary(case, tmp_path):
     compare_workspaces(a, b, ws)
 
 
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0,0"])
+def test_detect_peaks_read_sharded_matches_reference_binary(devices, tmp_path):
+    """WEPP_DEVICES: the initial filter of `build/wepp detectPeaks` read-sharded over several ranks of one process
+    (wepp_group; here the ranks share device 0 so that the single-GPU box covers the path — on a multi-GPU box
+    WEPP_GPUS=N puts a rank on each device, tests/test_multigpu_peer.py).  Every output file as the reference's."""
+    a, b = str(tmp_path / "ref"), str(tmp_path / "ours")
+    ws = wd.make_workspace(a, **CASES["selective"])
+    shutil.copytree(a, b)
+    _run(REF, ws, a)
+    r = _run(OURS, ws, b, env={"WEPP_DEVICES": devices})
+    assert f"peak selection on {len(devices.split(','))} GPUs" in r.stdout
+    compare_workspaces(a, b, ws)
+
+
 def test_detect_peaks_without_lineages_and_few_survivors(tmp_path):
     """clade-idx -1 (the documented "no lineages" value, parsed as uint32 and wrapped) and a stand-in that keeps
     one haplotype in seven, so that the neighbour rounds of the post filter do real work."""

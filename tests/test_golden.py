@@ -111,6 +111,32 @@ def test_cuda_peak_loop_matches_reference_filter(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("ranks", [2, 3])
+@pytest.mark.parametrize("name", NAMES)
+def test_cuda_group_peak_loop_matches_reference_filter(name, ranks):
+    """wepp_group_filter_peaks: the reads dealt over `ranks` ranks of one process (here all on device 0 — the ranks
+    exchange through the same peer-memory kernel and event ordering as on separate GPUs; tests/test_multigpu_peer.py
+    runs it on distinct devices): same peaks and neighbours as the reference's filter(), merged cartesian_map state
+    identical on every rank."""
+    from wepp_b200.multigpu import Group
+    g, tree, reads, masked = load(name)
+    arena, mreads, info = build_arena(tree, reads, masked)
+    _, rank = hap_ids(info["source"])
+    grp = Group([0] * ranks)
+    grp.set_arena(arena)
+    grp.set_reads(mreads)
+    pk, nb = grp.filter_peaks(info["leaf_count"], rank)
+    assert np.array_equal(np.sort(np.concatenate([pk, nb])), np.sort(g["filter_selected"]))
+    sc0, ct0 = grp.node_results(0)
+    assert np.array_equal(ct0, g["cm_counts"])
+    np.testing.assert_allclose(sc0, g["cm_score"], rtol=1e-9, atol=1e-15)
+    for r in range(1, ranks):
+        sc, ct = grp.node_results(r)
+        assert np.array_equal(ct, ct0) and np.array_equal(sc, sc0)   # bit-identical, not merely close
+    grp.close()
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", NAMES)
 def test_cuda_matches_reference_fixtures(name):
     from wepp_b200.placement import Placer, WeppFilter

@@ -464,3 +464,42 @@ def test_state_verify_mode(name, monkeypatch, capfd):
     _check_state_path(arena, reads)
     if name != "tiny1":   # (tiny trees may overflow the states' position cap and never build states)
         assert "every entry equals its state's representative" in capfd.readouterr().err
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ranks", [1, 2, 4])
+@pytest.mark.parametrize("name,q", [("small", 16), ("star", 32), ("tiny1", 8)])
+def test_group_place_matches_oracle(name, q, ranks):
+    """wepp_group_*: reads dealt round-robin over the ranks of one process, one plan agreed through the group's own
+    peer-memory all-reduce (cell histogram, true counts, per-(bucket, state) accumulators): per-read results gathered
+    in the caller's order and the merged per-node results equal the oracle's over the whole read set — on every rank."""
+    from wepp_b200.multigpu import Group
+    arena, reads = _rescore_case(name)
+    o = oracle.cartesian_map(arena, reads, None, n_threads=4)
+    grp = Group([0] * ranks)
+    grp.set_arena(arena)
+    for _ in range(2):   # a second read set through the same group: events and barriers are reusable
+        grp.set_reads(reads)
+        grp.place()
+        mp, mu = grp.read_results()
+        assert np.array_equal(mp, o["max_parsimony"]) and np.array_equal(mu, o["multiplicity"])
+        for r in range(ranks):
+            sc, ct = grp.node_results(r)
+            assert np.array_equal(ct, o["counts"]), r
+            np.testing.assert_allclose(sc, o["score"], rtol=1e-9, atol=1e-15)
+    grp.close()
+
+
+@pytest.mark.gpu
+def test_group_reports_a_failing_rank():
+    """a rank that fails outside an exchange must not leave the others waiting at the barrier"""
+    from wepp_b200._lib import WeppError
+    from wepp_b200.multigpu import Group
+    arena, reads = _rescore_case("small")
+    grp = Group([0, 0])
+    with pytest.raises(WeppError):
+        grp.set_reads(reads)          # no arena yet: every rank fails
+    grp.set_arena(arena)
+    grp.set_reads(reads)
+    grp.place()
+    grp.close()

@@ -58,6 +58,17 @@ SIGNATURES = {
     "wepp_peer_open": (C.c_int, [VP, C.c_int32, C.c_int32, VP]),
     "wepp_peer_merge": (C.c_int, [VP]),
     "wepp_peer_close": (C.c_int, [VP]),
+    "wepp_group_create": (C.c_int, [C.c_int32, VP, C.POINTER(VP)]),
+    "wepp_group_destroy": (None, [VP]),
+    "wepp_group_size": (C.c_int32, [VP]),
+    "wepp_group_handle": (VP, [VP, C.c_int32]),
+    "wepp_group_take": (VP, [VP, C.c_int32]),
+    "wepp_group_run": (C.c_int, [VP, VP, VP]),
+    "wepp_group_set_arena": (C.c_int, [VP, C.c_int32, VP, VP, VP, VP, VP, C.c_int32]),
+    "wepp_group_set_reads": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, VP]),
+    "wepp_group_place": (C.c_int, [VP]),
+    "wepp_group_get_read_results": (C.c_int, [VP, VP, VP]),
+    "wepp_group_filter_peaks": (C.c_int, [VP, VP, VP, VP, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "wepp_cli_main": (C.c_int, [C.c_int, C.POINTER(C.c_char_p)]),
     "wepp_device_buffer": (C.c_int, [VP, C.c_int32, C.POINTER(VP), C.POINTER(C.c_int64)]),
     "wepp_get_stats": (C.c_int, [VP, C.POINTER(WeppStats)]),

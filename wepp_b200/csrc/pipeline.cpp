@@ -241,26 +241,69 @@ std::string pipeline_load(Pipeline& p) {
 std::string pipeline_initial_filter(Pipeline& p, std::vector<int32_t>& running) {
     const ArenaHost& a = p.arena;
     const int32_t n = (int32_t)a.parent.size();
-    int device = 0;
-    if (const char* e = std::getenv("WEPP_DEVICE")) device = std::atoi(e);
-    if (wepp_create(device, &p.h) != WEPP_OK) return std::string("no usable B200 device: ") + wepp_last_error();
-    if (wepp_set_arena(p.h, n, a.parent.data(), a.mut_off.data(), a.mut_pos.data(), a.mut_ref.data(), a.mut_nuc.data(), a.genome_size) != WEPP_OK)
-        return wepp_last_error();
-    if (wepp_set_reads(p.h, p.reads.n_reads(), p.reads.start.data(), p.reads.end.data(), p.reads.degree.data(), a.rm_off.data(),
-                       a.rm_pos.data(), a.rm_nuc.data()) != WEPP_OK)
-        return wepp_last_error();
-    Timer t;
+    // WEPP_DEVICES="0,1,2,3" (or WEPP_GPUS=4 for devices 0..3; WEPP_DEVICE for a single one): the initial filter —
+    // cartesian_map and the peak loop — runs read-sharded on all of them (wepp_group, include/wepp_b200.h); the stages
+    // after it work on candidate sets and stay on the first device
+    std::vector<int32_t> devices;
+    if (const char* e = std::getenv("WEPP_DEVICES")) {
+        for (const char* c = e; *c;) {
+            char* end = nullptr;
+            const long d = std::strtol(c, &end, 10);
+            if (end == c) break;
+            devices.push_back((int32_t)d);
+            c = *end == ',' ? end + 1 : end;
+        }
+    } else if (const char* e = std::getenv("WEPP_GPUS")) {
+        for (int d = 0; d < std::atoi(e); ++d) devices.push_back(d);
+    }
+    if (devices.empty()) devices.push_back(std::getenv("WEPP_DEVICE") ? std::atoi(std::getenv("WEPP_DEVICE")) : 0);
     std::vector<int32_t> out((size_t)n);
     int32_t n_peaks = 0, n_out = 0;
-    if (wepp_filter_peaks(p.h, a.leaf_count.data(), p.id_rank.data(), out.data(), n, &n_peaks, &n_out) != WEPP_OK) return wepp_last_error();
-    std::cout << "--- cartesian mapping + peak selection on the GPU took " << t.seconds() << " seconds " << std::endl;
+    Timer t;
+    // haplotype::full_score with score = orig_score (recover_haplotype_state, haplotype.hpp:51-55,183-185)
+    auto summary = [&](wepp_handle* h) {
+        std::vector<double> score((size_t)n), dd((size_t)n);
+        if (wepp_get_node_summary(h, score.data(), dd.data()) != WEPP_OK) return false;
+        p.full_score.resize((size_t)n);
+        for (int32_t v = 0; v < n; ++v) p.full_score[(size_t)v] = score[(size_t)v] * std::sqrt(dd[(size_t)v]);
+        return true;
+    };
+    if (devices.size() == 1) {
+        if (wepp_create(devices[0], &p.h) != WEPP_OK) return std::string("no usable B200 device: ") + wepp_last_error();
+        if (wepp_set_arena(p.h, n, a.parent.data(), a.mut_off.data(), a.mut_pos.data(), a.mut_ref.data(), a.mut_nuc.data(), a.genome_size) != WEPP_OK)
+            return wepp_last_error();
+        if (wepp_set_reads(p.h, p.reads.n_reads(), p.reads.start.data(), p.reads.end.data(), p.reads.degree.data(), a.rm_off.data(),
+                           a.rm_pos.data(), a.rm_nuc.data()) != WEPP_OK)
+            return wepp_last_error();
+        t = Timer();
+        if (wepp_filter_peaks(p.h, a.leaf_count.data(), p.id_rank.data(), out.data(), n, &n_peaks, &n_out) != WEPP_OK) return wepp_last_error();
+        std::cout << "--- cartesian mapping + peak selection on the GPU took " << t.seconds() << " seconds " << std::endl;
+        if (!summary(p.h)) return wepp_last_error();
+    } else {
+        wepp_group* g = nullptr;
+        if (wepp_group_create((int32_t)devices.size(), devices.data(), &g) != WEPP_OK) return std::string("no usable group of B200 devices: ") + wepp_last_error();
+        struct Guard {
+            wepp_group* g;
+            ~Guard() { wepp_group_destroy(g); }
+        } guard{g};
+        if (wepp_group_set_arena(g, n, a.parent.data(), a.mut_off.data(), a.mut_pos.data(), a.mut_ref.data(), a.mut_nuc.data(), a.genome_size) != WEPP_OK)
+            return wepp_last_error();
+        if (wepp_group_set_reads(g, p.reads.n_reads(), p.reads.start.data(), p.reads.end.data(), p.reads.degree.data(), a.rm_off.data(),
+                                 a.rm_pos.data(), a.rm_nuc.data()) != WEPP_OK)
+            return wepp_last_error();
+        t = Timer();
+        if (wepp_group_filter_peaks(g, a.leaf_count.data(), p.id_rank.data(), out.data(), n, &n_peaks, &n_out) != WEPP_OK) return wepp_last_error();
+        std::cout << "--- cartesian mapping + peak selection on " << devices.size() << " GPUs took " << t.seconds() << " seconds " << std::endl;
+        if (!summary(wepp_group_handle(g, 0))) return wepp_last_error();
+        // the first rank's handle lives on for the later stages (rescoring over candidate sets, the writers), which see
+        // the whole read set again; the other ranks go with the group
+        p.h = wepp_group_take(g, 0);
+        if (wepp_set_reads(p.h, p.reads.n_reads(), p.reads.start.data(), p.reads.end.data(), p.reads.degree.data(), a.rm_off.data(),
+                           a.rm_pos.data(), a.rm_nuc.data()) != WEPP_OK)
+            return wepp_last_error();
+    }
     out.resize((size_t)n_out);
     running = std::move(out);
-    // haplotype::full_score with score = orig_score (recover_haplotype_state, haplotype.hpp:51-55,183-185)
-    std::vector<double> score((size_t)n), dd((size_t)n);
-    if (wepp_get_node_summary(p.h, score.data(), dd.data()) != WEPP_OK) return wepp_last_error();
-    p.full_score.resize((size_t)n);
-    for (int32_t v = 0; v < n; ++v) p.full_score[(size_t)v] = score[(size_t)v] * std::sqrt(dd[(size_t)v]);
     return "";
 }
 

@@ -46,7 +46,7 @@ namespace {
     do {                                                                                                \
         cudaError_t _e = (call);                                                                        \
         if (_e != cudaSuccess)                                                                          \
-            return fail(WEPP_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));               \
+            return fail(WEPP_E_CUDA, std::string(#call) + " (wepp_abi.cu:" + std::to_string(__LINE__) + "): " + cudaGetErrorString(_e)); \
     } while (0)
 
 // Grow-only device buffer.
@@ -389,6 +389,18 @@ int ensure_host_reads(wepp_handle* h) {
     return WEPP_OK;
 }
 
+// The dynamic shared memory a kernel may be launched with is per-device state shared by every host thread (the ranks
+// of a wepp_group launch the same kernels at the same time), so it is not set to what the launch at hand needs —
+// another thread's smaller value could land between this thread's call and its launch — but once and for all to the
+// device's opt-in maximum (less the kernel's static shared memory).
+template <typename Kern>
+cudaError_t allow_max_smem(Kern kernel, const wepp_handle* h) {
+    cudaFuncAttributes fa;
+    const cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(h->smem_optin - fa.sharedSizeBytes));
+}
+
 int finalize_plan(wepp_handle* h, wepp_handle::DevPlan& dp) {
     if (dp.final_for_mask || dp.plan.lists.empty()) return WEPP_OK;
     int max_n = 0;
@@ -412,7 +424,7 @@ int launch_place(wepp_handle* h, const PlaceParams& pp, int width) {
     const size_t smem = (size_t)SMEM_CODES + (((size_t)width * 32 * K + 15) & ~(size_t)15);
     if (smem > h->smem_optin || width > MAX_WINDOW)
         return fail(WEPP_E_INVALID, "read window too wide for shared memory (" + std::to_string(width) + " bases)");
-    CU(cudaFuncSetAttribute(place_kernel<K, ACC, EPP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(allow_max_smem(place_kernel<K, ACC, EPP>, h));
     int per_sm = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_kernel<K, ACC, EPP>, PLACE_WARPS * 32, smem));
     per_sm = std::max(per_sm, 1);
@@ -738,7 +750,7 @@ int launch_state_place(wepp_handle* h, const StatePlaceParams& p, int n_tiles, i
     const size_t smem = (size_t)RtLayout<K>::CODES + 2 * TBL_HALF + (((size_t)width * 32 * K + 15) & ~(size_t)15);
     if (smem > h->smem_optin || width > MAX_WINDOW)
         return fail(WEPP_E_INVALID, "read window too wide for shared memory (" + std::to_string(width) + " bases)");
-    CU(cudaFuncSetAttribute(state_place_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(allow_max_smem(state_place_kernel<K>, h));
     state_place_kernel<K><<<n_tiles, PLACE_WARPS * 32, smem, h->stream>>>(p);
     CU(cudaGetLastError());
     return WEPP_OK;
@@ -882,7 +894,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         dq.smem_bytes = smem;
         dq.cand_cap = 1 << 20;
         if (getenv("WEPP_DELTA_CAND")) dq.cand_cap = std::max(0, atoi(getenv("WEPP_DELTA_CAND")));
-        CU(cudaFuncSetAttribute(delta_place_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(allow_max_smem(delta_place_kernel, h));
         const int grid_dp = std::max(1, std::min(dp.n_units, h->n_sms));
         delta_place_kernel<<<grid_dp, DP_WARPS * 32, smem, h->stream>>>(dq);
         CU(cudaGetLastError());
@@ -1944,10 +1956,10 @@ int launch_rescore_tiles(wepp_handle* h, const RescoreTileParams& p, int n_tiles
     if (smem > h->smem_optin || width > MAX_WINDOW)
         return fail(WEPP_E_INVALID, "read window too wide for shared memory (" + std::to_string(width) + " bases)");
     if (mode == 0) {
-        CU(cudaFuncSetAttribute(rescore_tile_kernel<K, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(allow_max_smem(rescore_tile_kernel<K, 0>, h));
         rescore_tile_kernel<K, 0><<<n_tiles, PLACE_WARPS * 32, smem, h->stream>>>(p);
     } else {
-        CU(cudaFuncSetAttribute(rescore_tile_kernel<K, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(allow_max_smem(rescore_tile_kernel<K, 1>, h));
         rescore_tile_kernel<K, 1><<<n_tiles, PLACE_WARPS * 32, smem, h->stream>>>(p);
     }
     CU(cudaGetLastError());
@@ -2336,6 +2348,7 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
         d_removed.release(); d_stnuc.release(); d_nodes.release(); d_stpos.release(); d_marks.release();
         d_list.release(); d_stoff.release(); d_max.release(); d_count.release();
     };
+    (void)0;
 #define FCU(call)                                                                                  \
     do {                                                                                           \
         cudaError_t _e = (call);                                                                   \
@@ -2359,10 +2372,32 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
         return rc;
     }
 
+    // read-sharded ranks (wepp_set_allreduce with one plan: wepp_group_filter_peaks, or a caller's own ranks in step):
+    // the cartesian_map above merged the accumulators, so score / counts / divergence are those of the whole read set
+    // on every rank, bit for bit; every step below exchanges the number of reads removed and their per-node weights
+    const bool sharded = h->allreduce && h->shared_plan;
+    DevBuf<long long> d_xchg;
+    auto sum_over_ranks = [&](int64_t& v) -> int {
+        if (!sharded) return WEPP_OK;
+        long long x = v;
+        CU(d_xchg.ensure(1));
+        CU(cudaMemcpyAsync(d_xchg.p, &x, 8, cudaMemcpyHostToDevice, st));
+        if (h->allreduce(h->allreduce_user, d_xchg.p, 1, WEPP_DTYPE_I64, (void*)st) != 0) return fail(WEPP_E_STATE, "the all-reduce hook failed");
+        CU(cudaMemcpyAsync(&x, d_xchg.p, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        v = x;
+        return WEPP_OK;
+    };
+    int64_t R_all = R;
+    if ((rc = sum_over_ranks(R_all)) != 0) {
+        release();
+        return rc;
+    }
+
     PeakHost ph(h);
     std::vector<uint8_t> mapped((size_t)n, 0);
     std::set<int32_t> peaks;
-    int64_t remaining = R;
+    int64_t remaining = R_all;
     auto cmp_tie = [&](int32_t l, int32_t r) {   // score_comparator's tie-breaks (arena.hpp:24-29)
         if (leaf_count[l] != leaf_count[r]) return leaf_count[l] > leaf_count[r];
         return id_rank[l] > id_rank[r];
@@ -2468,28 +2503,41 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
         FCU(cudaMemcpyAsync(&n_rem, d_count.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         FCU(cudaStreamSynchronize(st));
         lap(2);
-        n_removed_total += n_rem;
-        if (n_rem > 0) {
-            removed_now.resize((size_t)n_rem);
-            FCU(cudaMemcpyAsync(removed_now.data(), d_list.p, (size_t)n_rem * 8, cudaMemcpyDeviceToHost, st));
-            FCU(cudaStreamSynchronize(st));
-            std::sort(removed_now.begin(), removed_now.end());
-            std::string err = build_read_plan(h->es, h->genome, h->n_reads, h->r_start.data(), h->r_end.data(),
-                                              h->r_degree.data(), h->r_off.data(), h->r_pos.data(), h->r_nuc.data(),
-                                              h->opt_k, removed_now.data(), n_rem, h->sub.plan);
-            if (!err.empty()) {
-                release();
-                return fail(WEPP_E_INVALID, err);
+        int64_t n_rem_all = n_rem;
+        if ((rc = sum_over_ranks(n_rem_all)) != 0) {
+            release();
+            return rc;
+        }
+        n_removed_total += n_rem_all;
+        if (n_rem_all > 0) {
+            if (n_rem > 0) {
+                removed_now.resize((size_t)n_rem);
+                FCU(cudaMemcpyAsync(removed_now.data(), d_list.p, (size_t)n_rem * 8, cudaMemcpyDeviceToHost, st));
+                FCU(cudaStreamSynchronize(st));
+                std::sort(removed_now.begin(), removed_now.end());
+                std::string err = build_read_plan(h->es, h->genome, h->n_reads, h->r_start.data(), h->r_end.data(),
+                                                  h->r_degree.data(), h->r_off.data(), h->r_pos.data(), h->r_nuc.data(),
+                                                  h->opt_k, removed_now.data(), n_rem, h->sub.plan);
+                if (!err.empty()) {
+                    release();
+                    return fail(WEPP_E_INVALID, err);
+                }
+                lap(3);
+                rc = upload_plan(h, h->sub, true);
+                if (!rc) rc = run_place(h, h->sub, true, 0, 0, /*with_counts*/ false, d_contrib.p);
+                if (rc) {
+                    release();
+                    return rc;
+                }
+            } else {
+                FCU(cudaMemsetAsync(d_contrib.p, 0, (size_t)n * 8, st));   // none of this rank's reads: it still takes part
             }
-            lap(3);
-            rc = upload_plan(h, h->sub, true);
-            if (!rc) rc = run_place(h, h->sub, true, 0, 0, /*with_counts*/ false, d_contrib.p);
-            if (rc) {
+            if (sharded && h->allreduce(h->allreduce_user, d_contrib.p, n, WEPP_DTYPE_F64, (void*)st) != 0) {
                 release();
-                return rc;
+                return fail(WEPP_E_STATE, "the all-reduce hook failed");
             }
             subtract_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_cur.p, d_contrib.p, n);
-            remaining -= n_rem;
+            remaining -= n_rem_all;
             lap(4);
         }
         if (consideration.empty()) break;   // nothing selectable: the reference would spin on the same head
@@ -2548,3 +2596,5 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
     h->has_results = true;
     return WEPP_OK;
 }
+
+#include "peer_group.cuh"

@@ -8,6 +8,8 @@ any device, so the same code runs over NCCL (GPU buffers of the library, see ben
 gloo (CPU tests)."""
 from __future__ import annotations
 
+import numpy as np
+
 
 def shard_bounds(n_reads: int, rank: int, world: int) -> tuple[int, int]:
     return n_reads * rank // world, n_reads * (rank + 1) // world
@@ -118,3 +120,82 @@ def gather_read_results(local, n_reads: int, rank: int, world: int, group=None):
     bufs = [torch.empty(m, dtype=local.dtype, device=local.device) for _ in sizes]
     dist.all_gather(bufs, padded, group=group)
     return torch.cat([b[:s] for b, s in zip(bufs, sizes)])
+
+
+class Group:
+    """wepp_group (include/wepp_b200.h): several GPUs of one box driven from THIS process — a handle and a host
+    thread per rank inside the library, reads dealt round-robin, exchanges by the library's own peer-memory kernel
+    (no torch.distributed, no NCCL).  `devices` may repeat a device (ranks sharing one GPU)."""
+
+    def __init__(self, devices):
+        import ctypes as C
+        from . import _lib
+        self.lib = _lib.load()
+        self._check = _lib.check
+        dev = np.ascontiguousarray(devices, np.int32)
+        g = C.c_void_p()
+        self._check(self.lib.wepp_group_create(int(dev.shape[0]), _lib.ptr(dev), C.byref(g)))
+        self.g = g
+        self.n_ranks = int(dev.shape[0])
+        self.n_nodes = 0
+        self.n_reads = 0
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.lib.wepp_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_arena(self, arena):
+        from ._lib import ptr
+        a = (np.ascontiguousarray(arena.parent, np.int32), np.ascontiguousarray(arena.mut_off, np.int64),
+             np.ascontiguousarray(arena.mut_pos, np.int32), np.ascontiguousarray(arena.mut_ref, np.uint8),
+             np.ascontiguousarray(arena.mut_nuc, np.uint8))
+        self._check(self.lib.wepp_group_set_arena(self.g, a[0].shape[0], *[ptr(x) for x in a], int(arena.genome_size)))
+        self.n_nodes = int(a[0].shape[0])
+
+    def set_reads(self, reads):
+        from ._lib import ptr
+        r = (np.ascontiguousarray(reads.start, np.int32), np.ascontiguousarray(reads.end, np.int32),
+             np.ascontiguousarray(reads.degree, np.int32), np.ascontiguousarray(reads.rm_off, np.int64),
+             np.ascontiguousarray(reads.rm_pos, np.int32), np.ascontiguousarray(reads.rm_nuc, np.uint8))
+        self._check(self.lib.wepp_group_set_reads(self.g, r[0].shape[0], *[ptr(x) for x in r]))
+        self.n_reads = int(r[0].shape[0])
+
+    def place(self):
+        self._check(self.lib.wepp_group_place(self.g))
+
+    def read_results(self):
+        from ._lib import ptr
+        mp, mu = np.empty(self.n_reads, np.int32), np.empty(self.n_reads, np.int32)
+        self._check(self.lib.wepp_group_get_read_results(self.g, ptr(mp), ptr(mu)))
+        return mp, mu
+
+    def node_results(self, rank: int = 0):
+        """the merged per-node score and mapped_read_counts as rank `rank` holds them (identical on every rank)"""
+        from ._lib import ptr
+        from .placement import NUM_RANGE_BINS
+        sc = np.empty(self.n_nodes, np.float64)
+        ct = np.empty((self.n_nodes, NUM_RANGE_BINS), np.int32)
+        self._check(self.lib.wepp_get_node_results(self.lib.wepp_group_handle(self.g, int(rank)), ptr(sc), ptr(ct)))
+        return sc, ct
+
+    def node_summary(self, rank: int = 0):
+        from ._lib import ptr
+        sc, dv = np.empty(self.n_nodes, np.float64), np.empty(self.n_nodes, np.float64)
+        self._check(self.lib.wepp_get_node_summary(self.lib.wepp_group_handle(self.g, int(rank)), ptr(sc), ptr(dv)))
+        return sc, dv
+
+    def filter_peaks(self, leaf_count, id_rank):
+        import ctypes as C
+        from ._lib import ptr
+        lc, ir = np.ascontiguousarray(leaf_count, np.int32), np.ascontiguousarray(id_rank, np.int32)
+        out = np.empty(self.n_nodes, np.int32)
+        npk, nout = C.c_int32(0), C.c_int32(0)
+        self._check(self.lib.wepp_group_filter_peaks(self.g, ptr(lc), ptr(ir), ptr(out), out.shape[0], C.byref(npk), C.byref(nout)))
+        return out[: npk.value].copy(), out[npk.value: nout.value].copy()
