@@ -1,2 +1,3 @@
 set -x
-timeout 900 python -m pytest tests/test_cli_gpu.py -x -q -m gpu -k "sharded" 2>&1 | grep -v "^$" | tail -40 | cut -c1-1500
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "delta" 2>&1 | tail -2
+timeout 600 python profiles/dev_paths.py 1.0 2>&1 | tail -3 | head -1

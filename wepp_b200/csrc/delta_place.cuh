@@ -43,7 +43,7 @@
 
 namespace wepp {
 
-constexpr int DP_WARPS = 16;          // warps per CTA (one CTA per SM: the shared memory is the limit)
+constexpr int DP_WARPS = 16;          // warps per CTA (one CTA per SM: the shared memory is the limit; 24 warps at 72 registers measured slower, 5.2 vs 5.0 ms)
 constexpr int DP_BINS = 64;           // score bins: bin = base - red + DP_VOFF
 constexpr int DP_VOFF = SW_MAX_ACTIVE;   // base <= SW_MAX_ACTIVE and red <= 2 * base
 constexpr int DP_CAND_MIN = 64;       // candidate queue entries per warp: at least this many (the rest of the shared memory is split)
@@ -87,10 +87,11 @@ __device__ __forceinline__ uint32_t dp_table_class(uint32_t z, uint32_t w) {
 }
 
 // One thread per state: a (sort key, posting) pair per state entry, at the entry's own index, and the entries per
-// (list, position) slot.  Sorting by key = slot << 16 | allele class << 8 | entries of the state groups the postings by
-// slot and, inside a slot, puts states with the same allele and the same number of mutations next to each other: the
-// 32 states a warp touches together then mostly share one (base score, red), and their nodes move between the
-// histogram bins with one warp sum.  The empty state's placeholder entry sorts to the end (key = all ones).
+// (list, position) slot.  Sorting (stably) by key = slot << 16 | allele class << 8 groups the postings by slot and
+// allele and keeps them in state order inside: the states are numbered in Euler order of their first node
+// (state_place.cuh), so a mutation carried by a clade posts runs of consecutive states — the 32 states a warp touches
+// together then mostly lie next to each other (dp_nibble below).  The empty state's placeholder entry sorts to the
+// end (key = all ones).
 __global__ void post_pairs_kernel(const Entry* __restrict__ state_ent, const int64_t* __restrict__ state_eoff,
                                   const int32_t* __restrict__ state_list, const int32_t* __restrict__ state_first,
                                   const int32_t* __restrict__ lpos_base, int32_t n_states, uint32_t* __restrict__ slot_count,
@@ -101,7 +102,6 @@ __global__ void post_pairs_kernel(const Entry* __restrict__ state_ent, const int
     const uint32_t local = (uint32_t)(s - state_first[l]);
     const int32_t lp = lpos_base[l];
     const int64_t e0 = state_eoff[s], e1 = state_eoff[s + 1];
-    const uint32_t len = (uint32_t)min((int64_t)255, e1 - e0);
     for (int64_t k = e0; k < e1; ++k) {
         const Entry e = state_ent[k];
         pkey[k] = ~0ull;
@@ -114,7 +114,7 @@ __global__ void post_pairs_kernel(const Entry* __restrict__ state_ent, const int
         }
         const uint32_t slot = (uint32_t)lp + (e.w >> 16);
         atomicAdd(slot_count + slot, 1u);
-        pkey[k] = ((uint64_t)slot << 16) | ((uint64_t)xc << 8) | (uint64_t)len;
+        pkey[k] = ((uint64_t)slot << 16) | ((uint64_t)xc << 8);
         pval[k] = (uint64_t)(local | (xc << 24)) | ((uint64_t)e.y << 32);   // uint2 {state | class << 24, nodes}
     }
 }
@@ -257,6 +257,12 @@ struct DeltaPlaceParams {
     int64_t gscratch_words;
 };
 
+// Nibble scratch: state s lives in word (s / 256) * 32 + s % 32, nibble (s / 32) % 8 — 32 consecutive states are 32
+// consecutive words (one per bank), where the plain layout s / 8 would put them in four words, eight lanes fighting
+// over each.
+__device__ __forceinline__ uint32_t dp_nibble_word(uint32_t s) { return ((s >> 8) << 5) | (s & 31u); }
+__device__ __forceinline__ int dp_nibble_shift(uint32_t s) { return (int)((s >> 5) & 7u) * 4; }
+
 // One read by one warp.  FAST: nibble scratch in shared memory + candidate queue; else byte scratch in global memory
 // and the postings are walked again for the weights.  rec / m = the read's record and this lane's mutation record
 // (mutations 0..31; reads with more fetch the rest here).
@@ -306,8 +312,8 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
                     if (act[h]) {
                         int oldred;
                         if (FAST) {
-                            const int sh = (int)(s[h] & 7u) * 4;
-                            oldred = (int)((atomicAdd(scr + (s[h] >> 3), (uint32_t)d[h] << sh) >> sh) & 15u);
+                            const int sh = dp_nibble_shift(s[h]);
+                            oldred = (int)((atomicAdd(scr + dp_nibble_word(s[h]), (uint32_t)d[h] << sh) >> sh) & 15u);
                         } else {
                             const int sh = (int)(s[h] & 3u) * 8;
                             oldred = (int)((atomicAdd(scr + (s[h] >> 2), (uint32_t)d[h] << sh) >> sh) & 255u);
@@ -364,8 +370,8 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
     if (FAST && n_cand <= cand_cap) {
         for (int i = lane; i < n_cand; i += 32) {
             const uint32_t s = cand[i];
-            const int sh = (int)(s & 7u) * 4;
-            const int red = (int)((atomicAnd(scr + (s >> 3), ~(15u << sh)) >> sh) & 15u);   // duplicates see 0
+            const int sh = dp_nibble_shift(s);
+            const int red = (int)((atomicAnd(scr + dp_nibble_word(s), ~(15u << sh)) >> sh) & 15u);   // duplicates see 0
             if (red && n_epp > 0 && (int)base_s[s] + DP_VOFF - red == mV) {
                 atomicAdd(p.saccS + so + s, wgt);
                 atomicAdd(p.saccC + so + s, deg);
@@ -390,8 +396,8 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
                     if (i + 32 < hi) nx = __ldg(&p.post[i + 32].x);
                     int red;
                     if (FAST) {
-                        const int sh = (int)(s & 7u) * 4;
-                        red = (int)((atomicAnd(scr + (s >> 3), ~(15u << sh)) >> sh) & 15u);
+                        const int sh = dp_nibble_shift(s);
+                        red = (int)((atomicAnd(scr + dp_nibble_word(s), ~(15u << sh)) >> sh) & 15u);
                     } else {
                         const int sh = (int)(s & 3u) * 8;
                         red = (int)((atomicAnd(scr + (s >> 2), ~(255u << sh)) >> sh) & 255u);
@@ -432,7 +438,7 @@ __global__ void __launch_bounds__(DP_WARPS * 32, 1) delta_place_kernel(const Del
         const DeltaGroup dg = p.groups[du.group];
         const int s_n = p.state_first[dg.list + 1] - p.state_first[dg.list];
         const int s_pad = (s_n + 15) & ~15;
-        const int stride = ((s_n + 7) / 8 * 4 + 15) & ~15;          // nibble scratch bytes per warp
+        const int stride = (s_n + 255) / 256 * 128;                 // nibble scratch bytes per warp (dp_nibble_word)
         const int aw = min(DP_WARPS, (p.smem_bytes - DP_FIXED - s_pad) / (stride + DP_CAND_MIN * 4));
         // the shared memory the scratch areas leave is the warps' candidate queues
         const int cand_cap = min(p.cand_cap, (p.smem_bytes - DP_FIXED - s_pad - aw * stride) / (aw * 16) * 4);

@@ -279,6 +279,25 @@ __global__ void state_flag_kernel(const uint64_t* __restrict__ key, const uint32
     flag[j] = f;
 }
 
+// States are renumbered in the order of their first evaluated entry (Euler order, list by list): the states first
+// met inside a subtree get consecutive numbers, so the posting list of a mutation carried by a whole clade is a few
+// runs of consecutive states (delta_place.cuh: conflict-free scratch banks, coalesced base scores).
+__global__ void state_first_entry_kernel(const uint64_t* __restrict__ key, const uint32_t* __restrict__ ent, const int32_t* __restrict__ incl,
+                                         int64_t n, uint32_t* __restrict__ first_entry) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || key[j] == SW_NOT_EVAL) return;
+    atomicMin(&first_entry[incl[j] - 1], ent[j]);
+}
+__global__ void state_newid_kernel(const uint32_t* __restrict__ order, int32_t n_states, int32_t* __restrict__ newid) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_states) newid[order[k]] = k;
+}
+__global__ void state_renumber_kernel(const uint64_t* __restrict__ key, const int32_t* __restrict__ newid, int64_t n, int32_t* __restrict__ incl) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n || key[j] == SW_NOT_EVAL) return;
+    incl[j] = newid[incl[j] - 1] + 1;
+}
+
 // state index per entry, countable nodes / representative / size per state
 __global__ void state_assign_kernel(const uint64_t* __restrict__ key, const uint32_t* __restrict__ ent, const int32_t* __restrict__ incl,
                                     const Entry* __restrict__ lists, const uint64_t* __restrict__ h2, int64_t n,

@@ -508,6 +508,22 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
     lap("sort + flags + scan");
     if (n_states <= 0) return WEPP_OK;
     const size_t S = (size_t)n_states;
+    if (!(getenv("WEPP_STATE_ORDER") && atoi(getenv("WEPP_STATE_ORDER")) == 0)) {   // (0: keep the hash order — a development switch)
+        TmpBuf<uint32_t> first_entry(st), first_sorted(st), ids(st), order(st);
+        TmpBuf<int32_t> newid(st);
+        CU(first_entry.ensure(S)); CU(first_sorted.ensure(S)); CU(ids.ensure(S)); CU(order.ensure(S)); CU(newid.ensure(S));
+        CU(cudaMemsetAsync(first_entry.p, 0xFF, S * 4, st));
+        state_first_entry_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(key2.p, val2.p, incl.p, E, first_entry.p);
+        iota_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(ids.p, (int64_t)S);
+        CU(cudaGetLastError());
+        CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, first_entry.p, first_sorted.p, ids.p, order.p, (int)S, 0, 32, st));
+        CU(h->d_cub_tmp.ensure(tmp));
+        CU(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp.p, tmp, first_entry.p, first_sorted.p, ids.p, order.p, (int)S, 0, 32, st));
+        state_newid_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(order.p, n_states, newid.p);
+        state_renumber_kernel<<<(unsigned)((E + 255) / 256), 256, 0, st>>>(key2.p, newid.p, E, incl.p);
+        CU(cudaGetLastError());
+        lap("states in Euler order");
+    }
     CU(state_ucnt.ensure(S)); CU(state_rep.ensure(S)); CU(state_list.ensure(S)); CU(state_len.ensure(S + 1));
     CU(dp.state_eoff.ensure(S + 1)); CU(dp.state_first.ensure((size_t)n_lists + 1)); CU(rep_state.ensure((size_t)E));
     CU(cudaMemsetAsync(state_ucnt.p, 0, S * 4, st));
@@ -605,7 +621,7 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
             CU(cudaStreamSynchronize(st));
             // shared memory of delta_place_kernel: the widest list's base scores + at least 4 warps' nibble scratch
             const int64_t s_max = dp.max_list_states;
-            const int64_t need = DP_FIXED + ((s_max + 15) & ~15ll) + 4 * (((((s_max + 7) / 8 * 4) + 15) & ~15ll) + DP_CAND_MIN * 4);
+            const int64_t need = DP_FIXED + ((s_max + 15) & ~15ll) + 4 * ((s_max + 255) / 256 * 128 + DP_CAND_MIN * 4);
             dp.delta_usable = h_bad == 0 && need <= (int64_t)h->smem_optin;
             if (getenv("WEPP_TIMING") && atoi(getenv("WEPP_TIMING")) != 0)
                 fprintf(stderr, "[wepp timing] postings: %lld slots, %lld entries, tables %s, widest list %lld states, shared memory %lld of %lld -> %s\n",
