@@ -14,6 +14,7 @@
 // Included at the end of wepp_abi.cu (it needs wepp_handle).
 #pragma once
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <thread>
 
@@ -81,6 +82,16 @@ struct wepp_group {
     std::string err;
     // the reads as dealt: rank r holds the caller's reads r, r + G, r + 2G, ...
     int64_t n_reads = 0;
+    // one host thread per rank for the life of the group (a thread spawned per call costs more than an exchange)
+    std::vector<std::thread> workers;
+    std::mutex tm;
+    std::condition_variable task_cv, done_cv;
+    std::function<int(int)> task;
+    uint64_t task_gen = 0;
+    int n_done = 0;
+    bool quit = false;
+    std::vector<int> rc;
+    std::vector<std::string> msg;
 
     bool barrier() {
         std::unique_lock<std::mutex> lk(m);
@@ -143,35 +154,55 @@ int peer_group_allreduce(void* user, void* dev_ptr, int64_t count, int32_t dtype
     return 0;
 }
 
-// fn(rank) on one host thread per rank, concurrently (the exchanges are rendezvous); the first failure is reported
+void group_worker(wepp_group* g, int r) {
+    cudaSetDevice(g->dev[(size_t)r]);
+    uint64_t seen = 0;
+    for (;;) {
+        std::function<int(int)> fn;
+        {
+            std::unique_lock<std::mutex> lk(g->tm);
+            g->task_cv.wait(lk, [&] { return g->quit || g->task_gen != seen; });
+            if (g->quit) return;
+            seen = g->task_gen;
+            fn = g->task;
+        }
+        const int rc = fn(r);
+        if (rc) {
+            g->msg[(size_t)r] = wepp_last_error();
+            g->break_barrier();
+        }
+        std::lock_guard<std::mutex> lk(g->tm);
+        g->rc[(size_t)r] = rc;
+        if (++g->n_done == g->G) g->done_cv.notify_all();
+    }
+}
+
+// fn(rank) on the ranks' threads, concurrently (the exchanges are rendezvous); the first failure is reported
 template <typename F>
 int group_run(wepp_group* g, F fn) {
-    std::vector<int> rc((size_t)g->G, 0);
-    std::vector<std::string> msg((size_t)g->G);
     {
         std::lock_guard<std::mutex> lk(g->m);
         g->broken = false;
         g->waiting = 0;
     }
-    std::vector<std::thread> th;
-    for (int r = 0; r < g->G; ++r)
-        th.emplace_back([&, r]() {
-            cudaSetDevice(g->dev[(size_t)r]);
-            rc[(size_t)r] = fn(r);
-            if (rc[(size_t)r]) {
-                msg[(size_t)r] = wepp_last_error();
-                g->break_barrier();
-            }
-        });
-    for (auto& t : th) t.join();
+    {
+        std::unique_lock<std::mutex> lk(g->tm);
+        g->task = fn;
+        g->n_done = 0;
+        std::fill(g->rc.begin(), g->rc.end(), 0);
+        ++g->task_gen;
+        g->task_cv.notify_all();
+        g->done_cv.wait(lk, [&] { return g->n_done == g->G; });
+        g->task = nullptr;
+    }
     // a rank that failed on its own comes before the ranks that only saw the broken exchange
     int first = -1;
     for (int r = 0; r < g->G; ++r)
-        if (rc[(size_t)r] && (first < 0 || (msg[(size_t)first].find("all-reduce hook") != std::string::npos &&
-                                            msg[(size_t)r].find("all-reduce hook") == std::string::npos)))
+        if (g->rc[(size_t)r] && (first < 0 || (g->msg[(size_t)first].find("all-reduce hook") != std::string::npos &&
+                                               g->msg[(size_t)r].find("all-reduce hook") == std::string::npos)))
             first = r;
     if (first < 0) return WEPP_OK;
-    return fail(rc[(size_t)first], "rank " + std::to_string(first) + ": " + msg[(size_t)first]);
+    return fail(g->rc[(size_t)first], "rank " + std::to_string(first) + ": " + g->msg[(size_t)first]);
 }
 
 }  // namespace
@@ -211,12 +242,21 @@ int wepp_group_create(int32_t n_ranks, const int32_t* devices, wepp_group** out)
         g->refs[(size_t)r] = {g, r};
         if (n_ranks > 1) wepp_set_allreduce(h, peer_group_allreduce, &g->refs[(size_t)r]);
     }
+    g->rc.assign((size_t)n_ranks, 0);
+    g->msg.assign((size_t)n_ranks, std::string());
+    for (int r = 0; r < n_ranks; ++r) g->workers.emplace_back(group_worker, g, r);
     *out = g;
     return WEPP_OK;
 }
 
 void wepp_group_destroy(wepp_group* g) {
     if (!g) return;
+    {
+        std::lock_guard<std::mutex> lk(g->tm);
+        g->quit = true;
+        g->task_cv.notify_all();
+    }
+    for (auto& t : g->workers) t.join();
     for (size_t r = 0; r < g->h.size(); ++r) {
         if (g->h[r]) wepp_destroy(g->h[r]);
         else cudaSetDevice(g->dev[r]);
