@@ -52,13 +52,15 @@ constexpr int DP_UNIT = 256;          // reads per work unit (a group of up to 2
 constexpr int DP_FIXED = 16 + DP_BINS * 4 + DP_WARPS * DP_BINS * 4;   // ctrl, whist, mv
 static_assert(DP_VOFF + SW_MAX_ACTIVE + 1 <= DP_BINS, "score bins");
 constexpr uint32_t DP_X_NONE = 7u;    // allele class of a state entry that equals no read allele (IUPAC union)
+constexpr int DP_MARGIN = 16;         // the core of a list of `width` positions is [DP_MARGIN, width - 1 - DP_MARGIN]: inside every window of the list
+constexpr int DP_LEVELS = 8;          // posting cells per slot: core base score 0..6 and "7 or more"
 
 struct DeltaGroup {     // reads of one bucket with the same window
     int64_t base_off;   // first byte of base_w in the base buffer (S_list bytes, 16-byte aligned)
     int32_t list, bucket;
     int32_t a_rel, b_rel;   // window relative to the list's first position
     int32_t m0;         // smallest occupied bin of the window's histogram
-    int32_t pad;
+    int32_t prune;      // 1: the window holds the list's core (base_w >= core base score: the reads walk a prefix of every slot)
 };
 struct DeltaUnit {
     int32_t group, first, count, pad;   // reads order[first .. first + count)
@@ -87,21 +89,33 @@ __device__ __forceinline__ uint32_t dp_table_class(uint32_t z, uint32_t w) {
 }
 
 // One thread per state: a (sort key, posting) pair per state entry, at the entry's own index, and the entries per
-// (list, position) slot.  Sorting (stably) by key = slot << 16 | allele class << 8 groups the postings by slot and
-// allele and keeps them in state order inside: the states are numbered in Euler order of their first node
-// (state_place.cuh), so a mutation carried by a clade posts runs of consecutive states — the 32 states a warp touches
-// together then mostly lie next to each other (dp_nibble below).  The empty state's placeholder entry sorts to the
-// end (key = all ones).
+// posting cell.  A slot (list, position) has DP_LEVELS cells, by the state's CORE base score cb = its mismatching
+// positions inside the list's core (capped): cb <= base_w(s) for every window w of the list that holds the core, so a
+// read whose mutations can take back at most R mismatches only walks the cells cb <= (window minimum) + R of its slots
+// — the other states cannot end at or below the window's minimum whatever the read hits (delta_mrec_kernel).  Sorting
+// (stably) by cell keeps the postings in state order inside a cell: the states are numbered in Euler order of their
+// first node (state_place.cuh), so a mutation carried by a clade posts runs of consecutive states — the 32 states a
+// warp touches together then mostly lie next to each other (dp_nibble_word below).  The empty state's placeholder
+// entry sorts to the end (key = all ones).
 __global__ void post_pairs_kernel(const Entry* __restrict__ state_ent, const int64_t* __restrict__ state_eoff,
                                   const int32_t* __restrict__ state_list, const int32_t* __restrict__ state_first,
-                                  const int32_t* __restrict__ lpos_base, int32_t n_states, uint32_t* __restrict__ slot_count,
-                                  uint64_t* __restrict__ pkey, uint64_t* __restrict__ pval, int32_t* __restrict__ bad) {
+                                  const int32_t* __restrict__ lpos_base, const ListDesc* __restrict__ list_desc, int32_t n_states,
+                                  uint32_t* __restrict__ cell_count, uint64_t* __restrict__ pkey, uint64_t* __restrict__ pval,
+                                  int32_t* __restrict__ bad) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_states) return;
     const int l = state_list[s];
     const uint32_t local = (uint32_t)(s - state_first[l]);
     const int32_t lp = lpos_base[l];
+    const int width = list_desc[l].width;
     const int64_t e0 = state_eoff[s], e1 = state_eoff[s + 1];
+    uint32_t cb = 0u;
+    for (int64_t k = e0; k < e1; ++k) {
+        const Entry e = state_ent[k];
+        const int q = (int)(e.w >> 16);
+        if ((e.z & 0xFFu) == 1u && q >= DP_MARGIN && q <= width - 1 - DP_MARGIN) ++cb;   // delta[ref] = 1: a mismatch of the state
+    }
+    cb = min(cb, (uint32_t)DP_LEVELS - 1u);
     for (int64_t k = e0; k < e1; ++k) {
         const Entry e = state_ent[k];
         pkey[k] = ~0ull;
@@ -112,9 +126,9 @@ __global__ void post_pairs_kernel(const Entry* __restrict__ state_ent, const int
             *bad = 1;
             continue;
         }
-        const uint32_t slot = (uint32_t)lp + (e.w >> 16);
-        atomicAdd(slot_count + slot, 1u);
-        pkey[k] = ((uint64_t)slot << 16) | ((uint64_t)xc << 8);
+        const uint32_t cell = ((uint32_t)lp + (e.w >> 16)) * DP_LEVELS + cb;
+        atomicAdd(cell_count + cell, 1u);
+        pkey[k] = (uint64_t)cell;
         pval[k] = (uint64_t)(local | (xc << 24)) | ((uint64_t)e.y << 32);   // uint2 {state | class << 24, nodes}
     }
 }
@@ -137,8 +151,8 @@ __global__ void delta_keys_kernel(const TileDesc* __restrict__ tiles, const Buck
         const int64_t rid = perm[td.first + i];
         uint32_t cost = 0;
         for (int64_t k = rm_off[rid]; k < rm_off[rid + 1]; ++k) {
-            const int slot = lp + rm_pos[k] - b0;
-            cost += post_off[slot + 1] - post_off[slot] + 16u;
+            const size_t slot = (size_t)(lp + rm_pos[k] - b0);
+            cost += post_off[(slot + 1) * DP_LEVELS] - post_off[slot * DP_LEVELS] + 16u;
         }
         const uint64_t w = ((uint64_t)td.bucket << 24) | ((uint64_t)(start[rid] - b0) << 12) | (uint64_t)(end[rid] - b0);
         key[td.first + i] = (w << DP_COST_BITS) | (uint64_t)(255u - min(255u, cost >> 6));
@@ -152,28 +166,44 @@ __global__ void delta_window_of_key_kernel(const uint64_t* __restrict__ key, int
 }
 
 // What the placement kernel reads per read, in sorted order: {read index, degree, first mutation, mutations | non-N
-// mutations << 16}; and per read mutation (at its index in the caller's mutation arrays) the posting range it
-// touches: {first posting, postings | allele class << 28}.
-__global__ void delta_records_kernel(const uint64_t* __restrict__ sorted_key, const uint32_t* __restrict__ order, int64_t n,
-                                     const BucketDesc* __restrict__ buckets, const ListDesc* __restrict__ list_desc,
-                                     const int32_t* __restrict__ lpos_base, const uint32_t* __restrict__ post_off,
-                                     const int32_t* __restrict__ degree, const int64_t* __restrict__ rm_off,
-                                     const int32_t* __restrict__ rm_pos, const uint8_t* __restrict__ rm_code,
-                                     uint4* __restrict__ rec, uint2* __restrict__ mrec) {
+// mutations << 16}
+__global__ void delta_records_kernel(const uint32_t* __restrict__ order, int64_t n, const int32_t* __restrict__ degree,
+                                     const int64_t* __restrict__ rm_off, const uint8_t* __restrict__ rm_code, uint4* __restrict__ rec) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t rid = order[i];
-    const int32_t list = buckets[(int32_t)(sorted_key[i] >> (24 + DP_COST_BITS))].list;
-    const int32_t b0 = list_desc[list].b0, lp = lpos_base[list];
     const int64_t a = rm_off[rid], b = rm_off[rid + 1];
     uint32_t non_n = 0;
-    for (int64_t k = a; k < b; ++k) {
-        const uint32_t c = rm_code[k];
-        non_n += c <= 4u;
-        const uint32_t lo = post_off[lp + rm_pos[k] - b0], hi = post_off[lp + rm_pos[k] - b0 + 1];
-        mrec[k] = make_uint2(lo, (hi - lo) | (c << 28));
-    }
+    for (int64_t k = a; k < b; ++k) non_n += rm_code[k] <= 4u;
     rec[i] = make_uint4(rid, (uint32_t)degree[rid], (uint32_t)a, (uint32_t)(b - a) | (non_n << 16));
+}
+
+// ... and per read mutation, at its index in the caller's mutation arrays, the postings it walks: {first posting,
+// postings | allele class << 28} (one block per work unit, once the windows' minima are known).  A read with k
+// allele mutations and n N's takes back at most R = 2 k + n mismatches of a state (2 where the alleles agree, 1 for
+// another allele or an N), so a state must start at or below (window minimum) + R to end at or below the window
+// minimum — and nothing above the window minimum can be the read's minimum.  base_w >= core base score, so the cells
+// of core base score > (window minimum) + R are skipped: typically most of a slot for the reads with one or two
+// mutations.  Windows that do not hold the list's core walk the whole slot.
+__global__ void delta_mrec_kernel(const DeltaUnit* __restrict__ units, const DeltaGroup* __restrict__ groups,
+                                  const ListDesc* __restrict__ list_desc, const int32_t* __restrict__ lpos_base,
+                                  const uint32_t* __restrict__ post_off, const uint4* __restrict__ rec,
+                                  const int32_t* __restrict__ rm_pos, const uint8_t* __restrict__ rm_code, int32_t prune_on,
+                                  uint2* __restrict__ mrec) {
+    const DeltaUnit du = units[blockIdx.x];
+    const DeltaGroup dg = groups[du.group];
+    const int32_t b0 = list_desc[dg.list].b0, lp = lpos_base[dg.list];
+    for (int i = threadIdx.x; i < du.count; i += blockDim.x) {
+        const uint4 r = rec[du.first + i];
+        const int nm = (int)(r.w & 0xFFFFu), non_n = (int)(r.w >> 16);
+        const int t = (dg.m0 - DP_VOFF) + nm + non_n;   // window minimum + R
+        const int levels = (prune_on && dg.prune && t + 1 < DP_LEVELS) ? max(t + 1, 0) : DP_LEVELS;
+        for (uint32_t k = r.z; k < r.z + (uint32_t)nm; ++k) {
+            const size_t cell = (size_t)(lp + rm_pos[k] - b0) * DP_LEVELS;
+            const uint32_t lo = post_off[cell], hi = post_off[cell + levels];
+            mrec[k] = make_uint2(lo, (hi - lo) | ((uint32_t)rm_code[k] << 28));
+        }
+    }
 }
 
 struct WindowBaseParams {
@@ -324,7 +354,9 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
                 // Only the bins at or below the window's own minimum m0 can hold the read's minimum (a touched state
                 // only moves down), so only hits that end there are tracked: the state's nodes leave the tracked bin
                 // they were in (if any) and enter the new one, and the state is remembered — the read's weight goes
-                // to it once the minimum is known.  ~30 such hits per read against ~700 hits.
+                // to it once the minimum is known.  (Measured dead ends: keeping the top bins per lane in registers and
+                // taking queue slots from a ballot instead of these same-address atomics — 5.26 vs 4.87 ms, the
+                // unconditional instructions cost more than the serialised atomics of the ~10 % of hits that get here.)
 #pragma unroll
                 for (int h = 0; h < DP_U; ++h) {
                     if (v_new[h] <= dg.m0) {

@@ -589,33 +589,34 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
             slots += pl.lists[(size_t)l].width;
         }
         lpos[(size_t)n_lists] = (int32_t)slots;
-        const bool fits = slots < (1ll << 30) && total_ent < (1ll << 31);
+        const int64_t cells = slots * DP_LEVELS;
+        const bool fits = cells < (1ll << 30) && total_ent < (1ll << 31);
         if (fits) {
             TmpBuf<uint32_t> slot_count(st);
             TmpBuf<uint64_t> pkey(st), pkey2(st), pval(st);
             TmpBuf<int32_t> bad(st);
             const size_t TE = (size_t)std::max<int64_t>(total_ent, 1);
             CU(upload(dp.lpos_base, lpos, st));
-            CU(slot_count.ensure((size_t)slots + 1)); CU(bad.ensure(1));
+            CU(slot_count.ensure((size_t)cells + 1)); CU(bad.ensure(1));
             CU(pkey.ensure(TE)); CU(pkey2.ensure(TE)); CU(pval.ensure(TE));
-            CU(dp.post_off.ensure((size_t)slots + 1));
+            CU(dp.post_off.ensure((size_t)cells + 1));
             CU(dp.post.ensure(TE));
-            CU(cudaMemsetAsync(slot_count.p, 0, ((size_t)slots + 1) * 4, st));
+            CU(cudaMemsetAsync(slot_count.p, 0, ((size_t)cells + 1) * 4, st));
             CU(cudaMemsetAsync(bad.p, 0, 4, st));
             post_pairs_kernel<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(dp.state_ent.p, dp.state_eoff.p, state_list.p, dp.state_first.p,
-                                                                          dp.lpos_base.p, n_states, slot_count.p, pkey.p, pval.p, bad.p);
+                                                                          dp.lpos_base.p, dp.lists.p, n_states, slot_count.p, pkey.p, pval.p, bad.p);
             CU(cudaGetLastError());
-            CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, slot_count.p, dp.post_off.p, (int)(slots + 1), st));
+            CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, slot_count.p, dp.post_off.p, (int)(cells + 1), st));
             CU(h->d_cub_tmp.ensure(tmp));
-            CU(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, slot_count.p, dp.post_off.p, (int)(slots + 1), st));
+            CU(cub::DeviceScan::ExclusiveSum(h->d_cub_tmp.p, tmp, slot_count.p, dp.post_off.p, (int)(cells + 1), st));
             int slot_bits = 1;
-            while ((1ll << slot_bits) < slots + 1) ++slot_bits;
+            while ((1ll << slot_bits) < cells + 1) ++slot_bits;
             static_assert(sizeof(uint2) == sizeof(uint64_t), "postings are sorted as 64-bit values");
             CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, pkey.p, pkey2.p, pval.p, reinterpret_cast<uint64_t*>(dp.post.p),
-                                               (int)total_ent, 0, 16 + slot_bits, st));
+                                               (int)total_ent, 0, slot_bits, st));
             CU(h->d_cub_tmp.ensure(tmp));
             CU(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp.p, tmp, pkey.p, pkey2.p, pval.p, reinterpret_cast<uint64_t*>(dp.post.p),
-                                               (int)total_ent, 0, 16 + slot_bits, st));
+                                               (int)total_ent, 0, slot_bits, st));
             int32_t h_bad = 0;
             CU(cudaMemcpyAsync(&h_bad, bad.p, 4, cudaMemcpyDeviceToHost, st));
             CU(cudaStreamSynchronize(st));
@@ -670,9 +671,7 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
     if (h->n_read_muts >= (1ll << 32)) return WEPP_OK;   // 32-bit mutation offsets in the read records
     CU(dp.rec.ensure((size_t)R));
     CU(dp.mrec.ensure((size_t)std::max<int64_t>(h->n_read_muts, 1)));
-    delta_records_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(key2.p, dp.order.p, R, dp.buckets.p, dp.lists.p, dp.lpos_base.p,
-                                                                      dp.post_off.p, h->d_rdegree.p, h->d_roff.p, h->d_rpos.p, h->d_rcode.p,
-                                                                      dp.rec.p, dp.mrec.p);
+    delta_records_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(dp.order.p, R, h->d_rdegree.p, h->d_roff.p, h->d_rcode.p, dp.rec.p);
     CU(cudaGetLastError());
     delta_window_of_key_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(key2.p, R, key.p);   // the sort is done with key
     CU(cudaGetLastError());
@@ -702,7 +701,7 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
         dg.a_rel = (int32_t)((hk[(size_t)g] >> 12) & 0xFFFu);
         dg.b_rel = (int32_t)(hk[(size_t)g] & 0xFFFu);
         dg.m0 = 0;
-        dg.pad = 0;
+        dg.prune = dg.a_rel <= DP_MARGIN && dg.b_rel >= pl.lists[(size_t)dg.list].width - 1 - DP_MARGIN;   // the window holds the list's core
         dg.base_off = base_total;
         const int64_t s_n = dp.h_state_first[(size_t)dg.list + 1] - dp.h_state_first[(size_t)dg.list];
         base_total += (s_n + 15) & ~15ll;
@@ -742,6 +741,11 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
     window_base_kernel<<<grid, 256, 0, st>>>(wb);
     CU(cudaGetLastError());
     window_m0_kernel<<<(n_groups + 255) / 256, 256, 0, st>>>(dp.whist.p, n_groups, dp.groups.p);
+    CU(cudaGetLastError());
+    // the postings every read mutation walks: they depend on the windows' minima (WEPP_DELTA_PRUNE=0: whole slots)
+    delta_mrec_kernel<<<(unsigned)units.size(), 128, 0, st>>>(dp.units.p, dp.groups.p, dp.lists.p, dp.lpos_base.p, dp.post_off.p, dp.rec.p,
+                                                              h->d_rpos.p, h->d_rcode.p,
+                                                              !(getenv("WEPP_DELTA_PRUNE") && atoi(getenv("WEPP_DELTA_PRUNE")) == 0), dp.mrec.p);
     CU(cudaGetLastError());
     // byte scratch in global memory for the reads with many mutations: one area per warp of the persistent grid
     const int64_t words = ((int64_t)dp.max_list_states + 3) / 4 + 4;
