@@ -92,9 +92,16 @@ def test_restated_peak_loop_matches_reference_filter(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("env", [{}, {"WEPP_DELTA_PLACE": "2"}, {"WEPP_DELTA_PLACE": "2", "WEPP_PEAK_DELTA": "0"}],
+                         ids=["default", "sparse_subsets", "sparse_map_list_subsets"])
 @pytest.mark.parametrize("name", NAMES)
-def test_cuda_peak_loop_matches_reference_filter(name):
+def test_cuda_peak_loop_matches_reference_filter(name, env, monkeypatch):
+    """WEPP_DELTA_PLACE=2 forces the sparse corrections on these small read sets: the removed reads' per-node weights
+    then come from the whole read set's plan (place_subset_by_delta) instead of a subset plan's window lists
+    (WEPP_PEAK_DELTA=0 keeps those)."""
     from wepp_b200.placement import Placer
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     g, tree, reads, masked = load(name)
     arena, mreads, info = build_arena(tree, reads, masked)
     _, rank = hap_ids(info["source"])
@@ -111,14 +118,17 @@ def test_cuda_peak_loop_matches_reference_filter(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("force", [False, True], ids=["default", "sparse_subsets"])
 @pytest.mark.parametrize("ranks", [2, 3])
 @pytest.mark.parametrize("name", NAMES)
-def test_cuda_group_peak_loop_matches_reference_filter(name, ranks):
+def test_cuda_group_peak_loop_matches_reference_filter(name, ranks, force, monkeypatch):
     """wepp_group_filter_peaks: the reads dealt over `ranks` ranks of one process (here all on device 0 — the ranks
     exchange through the same peer-memory kernel and event ordering as on separate GPUs; tests/test_multigpu_peer.py
     runs it on distinct devices): same peaks and neighbours as the reference's filter(), merged cartesian_map state
     identical on every rank."""
     from wepp_b200.multigpu import Group
+    if force:
+        monkeypatch.setenv("WEPP_DELTA_PLACE", "2")
     g, tree, reads, masked = load(name)
     arena, mreads, info = build_arena(tree, reads, masked)
     _, rank = hap_ids(info["source"])

@@ -611,4 +611,42 @@ __global__ void state_scatter_kernel(const ListDesc* __restrict__ list_desc, con
     }
 }
 
+// expand_kernel (kernels.cuh) straight from the per-(bucket, state) weight sums, score only: what a list entry holds is
+// its state's sum, the step at an entry is that minus the enclosing boundary entry's.  The per-step node pass of the
+// peak loop (no counts, no per-entry copy of the accumulators).
+__global__ void expand_states_score_kernel(const Entry* __restrict__ lists, const ListDesc* __restrict__ list_desc,
+                                           const BucketDesc* __restrict__ buckets, const int32_t* __restrict__ prev_boundary,
+                                           const int32_t* __restrict__ sid, const int32_t* __restrict__ state_first,
+                                           const int64_t* __restrict__ sacc_off, const double* __restrict__ saccS,
+                                           unsigned long long* __restrict__ diff_lo, unsigned long long* __restrict__ diff_hi) {
+    const BucketDesc bd = buckets[blockIdx.y];
+    const ListDesc ld = list_desc[bd.list];
+    const Entry* e = lists + ld.off;
+    const int32_t* pb = prev_boundary + ld.off;
+    const int32_t* sd = sid + ld.off;
+    const double* s = saccS + sacc_off[blockIdx.y] - state_first[bd.list];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ld.n; i += gridDim.x * blockDim.x) {
+        const uint32_t x = __ldg(&e[i].x);
+        if (x & ENT_SKIP) continue;
+        const int pi = pb[i];
+        const int32_t si = sd[i], sp = pi >= 0 ? sd[pi] : -1;
+        if (si == sp) continue;
+        const double cur = si >= 0 ? s[si] : 0.0, prv = sp >= 0 ? s[sp] : 0.0;
+        if (cur == prv) continue;
+        const uint32_t idx = x & IDX_MASK;
+        unsigned long long alo, blo;
+        long long ahi, bhi;
+        dbl_to_fix(cur, alo, ahi);
+        dbl_to_fix(prv, blo, bhi);
+        const unsigned long long lo = alo - blo;
+        const long long hi = ahi - bhi - (alo < blo ? 1 : 0);
+        atomic_add128(diff_lo + idx, diff_hi + idx, lo, hi);
+        if (x & ENT_POINT) {   // back to the enclosing value right after the leaf
+            const unsigned long long nlo = 0ull - lo;
+            const long long nhi = ~hi + (lo == 0ull ? 1 : 0);
+            atomic_add128(diff_lo + idx + 1, diff_hi + idx + 1, nlo, nhi);
+        }
+    }
+}
+
 }  // namespace wepp

@@ -224,7 +224,15 @@ struct wepp_handle {
         DevBuf<double> Gw;
         DevBuf<uint32_t> gscratch;
         int64_t gscratch_words = 0;
+        // a subset of the resident reads through the same path (the peak loop's remove_read): where each read sits in the
+        // sorted order, the groups' first positions, and the subset's own records / work units
+        std::vector<int64_t> h_group_first;
+        DevBuf<uint32_t> pos_of_read, sub_pos, sub_pos_sorted;
+        bool pos_ready = false;
+        DevBuf<uint4> rec_sub;
+        DevBuf<DeltaUnit> units_sub;
         void release() {
+            pos_of_read.release(); sub_pos.release(); sub_pos_sorted.release(); rec_sub.release(); units_sub.release();
             perm.release(); lists.release(); buckets.release(); tiles.release(); entries.release();
             prev_boundary.release(); chunk_start.release(); tile_ptr.release(); tile_enc.release(); ent_x.release(); rec_off.release(); rec_x.release(); rec_cur.release(); rec_prv.release();
             sid.release(); state_first.release(); state_eoff.release(); sacc_off.release(); state_ent.release();
@@ -694,7 +702,10 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
     std::vector<DeltaUnit> units;
     std::vector<int32_t> bucket_goff((size_t)n_buckets + 1, 0), list_goff((size_t)n_lists + 1, 0), list_gids((size_t)n_groups);
     int64_t base_total = 0, first = 0;
+    dp.h_group_first.assign((size_t)n_groups + 1, 0);
+    dp.pos_ready = false;
     for (int g = 0; g < n_groups; ++g) {
+        dp.h_group_first[(size_t)g] = first;
         DeltaGroup& dg = groups[(size_t)g];
         dg.bucket = (int32_t)(hk[(size_t)g] >> 24);
         dg.list = pl.buckets[(size_t)dg.bucket].list;
@@ -715,6 +726,7 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
         }
         first += hc[(size_t)g];
     }
+    dp.h_group_first[(size_t)n_groups] = first;
     if (base_total > (8ll << 30)) return WEPP_OK;
     for (int b = 0; b < n_buckets; ++b) bucket_goff[(size_t)b + 1] += bucket_goff[(size_t)b];
     for (int l = 0; l < n_lists; ++l) list_goff[(size_t)l + 1] += list_goff[(size_t)l];
@@ -776,8 +788,16 @@ int launch_state_place(wepp_handle* h, const StatePlaceParams& p, int n_tiles, i
     return WEPP_OK;
 }
 
+// (`sub`: only these reads of the FULL plan, through its sparse-correction path — work units over the subset's own
+// records; the states, posting lists and window groups are those of the whole read set.  Per-node weights go to
+// score_out through the difference arrays, nothing else of the handle's results changes.)
+struct DeltaSubset {
+    const DeltaUnit* units;
+    int32_t n_units;
+    const uint4* rec;
+};
 int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t epp_cap, int64_t epp_capacity,
-              bool with_counts = true, double* score_out = nullptr) {
+              bool with_counts = true, double* score_out = nullptr, const DeltaSubset* sub = nullptr) {
     ReadPlan& pl = dp.plan;
     int rc = finalize_plan(h, dp);
     if (rc) return rc;
@@ -801,7 +821,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     // HBM (expand_kernel + scans), as does a tile pointer table over 2 GiB
     const int n_node_tiles = (n + NT_TILE - 1) / NT_TILE;
     const bool tiles_env = !(getenv("WEPP_NODE_TILES") && atoi(getenv("WEPP_NODE_TILES")) == 0);
-    const bool node_tiles = accumulate && tiles_env && !pl.lists.empty() && pl.acc_total < (1ll << 32) &&
+    const bool node_tiles = accumulate && tiles_env && !sub && !pl.lists.empty() && pl.acc_total < (1ll << 32) &&
                             pl.list_entries_total < (1ll << 32) && pl.buckets.size() < (1u << 24) &&
                             (double)pl.lists.size() * (n_node_tiles + 1) * 8.0 <= 2.0 * 1024 * 1024 * 1024;
     Laps lap_place("run_place", h->stream);
@@ -872,7 +892,10 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     // whole read set is placed with nothing mapped and no explicit EPP lists; WEPP_STATE_PLACE=0 keeps place_kernel
     const bool state_env = !(getenv("WEPP_STATE_PLACE") && atoi(getenv("WEPP_STATE_PLACE")) == 0);
     bool by_states = false;
-    if (state_env && accumulate && !want_epp && !h->has_mask && &dp == &h->full && pp.n_tiles > 0) {
+    if (sub) {
+        if (!dp.states_usable || !dp.delta_groups_usable) return fail(WEPP_E_STATE, "subset placement without the read set's window groups");
+        by_states = true;
+    } else if (state_env && accumulate && !want_epp && !h->has_mask && &dp == &h->full && pp.n_tiles > 0) {
         rc = build_states(h, dp);
         if (rc) return rc;
         by_states = dp.states_usable;
@@ -881,15 +904,19 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     // WEPP_DELTA_PLACE=0 keeps state_place_kernel
     const bool delta_env = !(getenv("WEPP_DELTA_PLACE") && atoi(getenv("WEPP_DELTA_PLACE")) == 0);
     bool by_delta = false;
-    if (by_states && delta_env && dp.delta_usable) {
+    if (sub) {
+        by_delta = true;
+    } else if (by_states && delta_env && dp.delta_usable) {
         rc = build_delta_groups(h, dp);
         if (rc) return rc;
         by_delta = dp.delta_groups_usable;
     }
     lap_place("states / window groups");
-    h->stats.place_path = by_delta ? 2 : (by_states ? 1 : 0);
-    h->stats.n_states = by_states ? dp.n_states : 0;
-    h->stats.n_window_groups = by_delta ? dp.n_groups : 0;
+    if (!sub) {
+        h->stats.place_path = by_delta ? 2 : (by_states ? 1 : 0);
+        h->stats.n_states = by_states ? dp.n_states : 0;
+        h->stats.n_window_groups = by_delta ? dp.n_groups : 0;
+    }
     if (accumulate && !by_states) CU(zero_acc());   // place_kernel adds into the per-(bucket, entry) accumulators
     CU(cudaEventRecord(h->ev[0], h->stream));
     if (by_states) {
@@ -902,9 +929,9 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         CU(cudaMemsetAsync(dp.Gw.p, 0, (size_t)dp.n_groups * DP_BINS * sizeof(double), h->stream));
         CU(cudaMemsetAsync(dp.Gc.p, 0, (size_t)dp.n_groups * DP_BINS * sizeof(int32_t), h->stream));
         DeltaPlaceParams dq = {};
-        dq.units = dp.units.p; dq.n_units = dp.n_units; dq.unit_counter = h->d_tile_counter.p;
+        dq.units = sub ? sub->units : dp.units.p; dq.n_units = sub ? sub->n_units : dp.n_units; dq.unit_counter = h->d_tile_counter.p;
         dq.groups = dp.groups.p; dq.base = dp.base.p; dq.whist = dp.whist.p; dq.post = dp.post.p;
-        dq.state_first = dp.state_first.p; dq.sacc_off = dp.sacc_off.p; dq.rec = dp.rec.p; dq.mrec = dp.mrec.p;
+        dq.state_first = dp.state_first.p; dq.sacc_off = dp.sacc_off.p; dq.rec = sub ? sub->rec : dp.rec.p; dq.mrec = dp.mrec.p;
         dq.max_pars = h->d_maxpars.p; dq.mult = h->d_mult.p; dq.saccS = h->d_saccS.p; dq.saccC = h->d_saccC.p;
         dq.Gw = dp.Gw.p; dq.Gc = dp.Gc.p; dq.gscratch = dp.gscratch.p; dq.gscratch_words = dp.gscratch_words;
         // shared memory: fixed areas + the widest list's base scores + 16 warps' nibble scratch, as far as it fits
@@ -915,7 +942,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         dq.cand_cap = 1 << 20;
         if (getenv("WEPP_DELTA_CAND")) dq.cand_cap = std::max(0, atoi(getenv("WEPP_DELTA_CAND")));
         CU(allow_max_smem(delta_place_kernel, h));
-        const int grid_dp = std::max(1, std::min(dp.n_units, h->n_sms));
+        const int grid_dp = std::max(1, std::min((int)dq.n_units, h->n_sms));
         delta_place_kernel<<<grid_dp, DP_WARPS * 32, smem, h->stream>>>(dq);
         CU(cudaGetLastError());
         dim3 fgrid((unsigned)std::min<int64_t>((s_max + 255) / 256, 1024), (unsigned)pl.buckets.size());
@@ -947,7 +974,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
     CU(cudaEventRecord(h->ev[1], h->stream));
     h->exchange_timed = false;
     // read-sharded ranks: the accumulators of all ranks line up (one plan) — sum them, then finish per node
-    if (accumulate && h->allreduce && h->shared_plan && &dp == &h->full) {
+    if (accumulate && h->allreduce && h->shared_plan && &dp == &h->full && !sub) {
         int rc_x;
         if (by_states) {
             rc_x = h->allreduce(h->allreduce_user, h->d_saccS.p, dp.sacc_total, WEPP_DTYPE_F64, (void*)h->stream);
@@ -960,8 +987,8 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         CU(cudaEventRecord(h->ev[4], h->stream));
         h->exchange_timed = true;
     }
-    h->div_count_valid = false;
-    if (accumulate && by_states && !node_tiles) {
+    if (!sub) h->div_count_valid = false;
+    if (accumulate && by_states && !node_tiles && !sub) {
         // the difference-array node path reads per-(bucket, entry) accumulators: spread the (merged) per-(bucket, state) ones
         int max_n = 0;
         for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
@@ -1066,9 +1093,14 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
             int max_n = 0;
             for (const ListDesc& l : pl.lists) max_n = std::max(max_n, l.n);
             dim3 grid((unsigned)std::min<int64_t>((max_n + 255) / 256, 4096), (unsigned)pl.buckets.size());
-            expand_kernel<<<grid, 256, 0, h->stream>>>(dp.entries.p, dp.lists.p, dp.buckets.p, dp.prev_boundary.p,
-                                                       h->d_accS.p, h->d_accC.p, h->d_diff_lo.p, h->d_diff_hi.p,
-                                                       with_counts ? h->d_counts.p : nullptr);
+            if (sub)
+                expand_states_score_kernel<<<grid, 256, 0, h->stream>>>(dp.entries.p, dp.lists.p, dp.buckets.p, dp.prev_boundary.p, dp.sid.p,
+                                                                        dp.state_first.p, dp.sacc_off.p, h->d_saccS.p, h->d_diff_lo.p,
+                                                                        h->d_diff_hi.p);
+            else
+                expand_kernel<<<grid, 256, 0, h->stream>>>(dp.entries.p, dp.lists.p, dp.buckets.p, dp.prev_boundary.p,
+                                                           h->d_accS.p, h->d_accC.p, h->d_diff_lo.p, h->d_diff_hi.p,
+                                                           with_counts ? h->d_counts.p : nullptr);
             CU(cudaGetLastError());
             ++launches;
         }
@@ -1095,6 +1127,7 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         CU(cudaGetLastError());
     }
     CU(cudaEventRecord(h->ev[2], h->stream));
+    if (sub) return WEPP_OK;   // the handle's results and statistics stay those of the last whole placement
     h->stats_pending = true;
     wepp_stats& st = h->stats;
     st.n_nodes = n;
@@ -2330,6 +2363,71 @@ struct PeakHost {
 
 }  // namespace
 
+namespace {
+
+__global__ void inverse_order_kernel(const uint32_t* __restrict__ order, int64_t n, uint32_t* __restrict__ pos_of_read) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pos_of_read[order[i]] = (uint32_t)i;
+}
+__global__ void gather_pos_kernel(const int64_t* __restrict__ read_idx, int n, const uint32_t* __restrict__ pos_of_read, uint32_t* __restrict__ pos) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pos[i] = pos_of_read[read_idx[i]];
+}
+__global__ void gather_rec_kernel(const uint32_t* __restrict__ pos, int n, const uint4* __restrict__ rec, uint4* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = rec[pos[i]];
+}
+
+// remove_read for a batch (initial_filter.cpp:284-342) through the sparse corrections of the whole read set's plan:
+// the per-node weights node_score(max_parsimony, multiplicity, degree) of the reads d_read_idx[0 .. n) — resident reads,
+// caller order — at their minimum-parsimony nodes, into score_out[N].  The reads are looked up in the plan's sorted
+// order, their records gathered, one work unit made per window group present (the host sees only the n sorted
+// positions), and delta_place_kernel / delta_finalize_kernel run over those units; the per-node sums come from the
+// difference arrays (no counts matrix).  Nothing is rebuilt per call — the window lists of a subset plan were.
+int place_subset_by_delta(wepp_handle* h, const int64_t* d_read_idx, int n, double* score_out) {
+    wepp_handle::DevPlan& dp = h->full;
+    cudaStream_t st = h->stream;
+    const int64_t R = dp.plan.n_reads;
+    if (!dp.pos_ready) {
+        CU(dp.pos_of_read.ensure((size_t)R));
+        inverse_order_kernel<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(dp.order.p, R, dp.pos_of_read.p);
+        CU(cudaGetLastError());
+        dp.pos_ready = true;
+    }
+    CU(dp.sub_pos.ensure((size_t)n)); CU(dp.sub_pos_sorted.ensure((size_t)n)); CU(dp.rec_sub.ensure((size_t)n));
+    gather_pos_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_read_idx, n, dp.pos_of_read.p, dp.sub_pos.p);
+    CU(cudaGetLastError());
+    int bits = 1;
+    while ((1ll << bits) < R) ++bits;
+    size_t tmp = 0;
+    CU(cub::DeviceRadixSort::SortKeys(nullptr, tmp, dp.sub_pos.p, dp.sub_pos_sorted.p, n, 0, bits, st));
+    CU(h->d_cub_tmp.ensure(tmp));
+    CU(cub::DeviceRadixSort::SortKeys(h->d_cub_tmp.p, tmp, dp.sub_pos.p, dp.sub_pos_sorted.p, n, 0, bits, st));
+    gather_rec_kernel<<<(n + 255) / 256, 256, 0, st>>>(dp.sub_pos_sorted.p, n, dp.rec.p, dp.rec_sub.p);
+    CU(cudaGetLastError());
+    std::vector<uint32_t> pos((size_t)n);
+    CU(cudaMemcpyAsync(pos.data(), dp.sub_pos_sorted.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    std::vector<DeltaUnit> units;
+    const std::vector<int64_t>& gf = dp.h_group_first;
+    for (int i = 0; i < n;) {
+        const int g = (int)(std::upper_bound(gf.begin(), gf.end(), (int64_t)pos[(size_t)i]) - gf.begin()) - 1;
+        int j = i;
+        while (j < n && (int64_t)pos[(size_t)j] < gf[(size_t)g + 1]) ++j;
+        for (int o = i; o < j;) {   // units of DP_UNIT reads; a remainder of up to 2 * DP_UNIT stays whole
+            const int take = j - o <= 2 * DP_UNIT ? j - o : DP_UNIT;
+            units.push_back(DeltaUnit{g, o, take, 0});
+            o += take;
+        }
+        i = j;
+    }
+    CU(upload(dp.units_sub, units, st));
+    const DeltaSubset sub = {dp.units_sub.p, (int32_t)units.size(), dp.rec_sub.p};
+    return run_place(h, dp, true, 0, 0, /*with_counts*/ false, score_out, &sub);
+}
+
+}  // namespace
+
 extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, const int32_t* id_rank, int32_t* out_nodes,
                                  int32_t capacity, int32_t* n_peaks_out, int32_t* n_out) {
     if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
@@ -2340,6 +2438,7 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
     const int64_t R = h->n_reads;
     cudaStream_t st = h->stream;
 
+    const auto t_enter = std::chrono::steady_clock::now();
     // reset_haplotype_state + cartesian_map (initial_filter.cpp:458-466)
     h->has_mask = false;
     h->full.final_for_mask = false;
@@ -2386,8 +2485,12 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
     FCU(cudaMemcpyAsync(d_orig.p, h->d_score.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
     FCU(cudaMemsetAsync(d_pmapped.p, 0, (size_t)n, st));
     FCU(cudaMemsetAsync(d_removed.p, 0, (size_t)std::max<int64_t>(R, 1), st));
-    // find_correspondents reads the resident reads (caller order); the subset plans below need the host copy
-    if ((rc = ensure_host_reads(h)) != 0) {
+    // find_correspondents reads the resident reads (caller order).  The removed reads' per-node weights come from the
+    // sparse corrections of the whole read set's plan where the cartesian_map above took that path (WEPP_PEAK_DELTA=0:
+    // never), else from a placement of a subset plan over its own window lists, which needs the host copy of the reads
+    const bool subset_by_delta = h->stats.place_path == 2 && h->full.delta_groups_usable &&
+                                 !(getenv("WEPP_PEAK_DELTA") && atoi(getenv("WEPP_PEAK_DELTA")) == 0);
+    if (!subset_by_delta && (rc = ensure_host_reads(h)) != 0) {
         release();
         return rc;
     }
@@ -2439,6 +2542,12 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
         t_phase[k] += std::chrono::duration<double, std::milli>(t - t_mark).count();
         t_mark = t;
     };
+    if (timing) {
+        cudaStreamSynchronize(st);
+        fprintf(stderr, "[wepp timing] initial filter: cartesian_map + set-up of the loop %.1f ms\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enter).count());
+        t_mark = std::chrono::steady_clock::now();
+    }
     while (remaining > 0 && (int)peaks.size() < MAX_PEAKS) {
         ++n_steps;
         lap(5);
@@ -2530,7 +2639,12 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
         }
         n_removed_total += n_rem_all;
         if (n_rem_all > 0) {
-            if (n_rem > 0) {
+            if (n_rem > 0 && subset_by_delta) {
+                if ((rc = place_subset_by_delta(h, d_list.p, n_rem, d_contrib.p)) != 0) {
+                    release();
+                    return rc;
+                }
+            } else if (n_rem > 0) {
                 removed_now.resize((size_t)n_rem);
                 FCU(cudaMemcpyAsync(removed_now.data(), d_list.p, (size_t)n_rem * 8, cudaMemcpyDeviceToHost, st));
                 FCU(cudaStreamSynchronize(st));
