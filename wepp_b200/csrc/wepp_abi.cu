@@ -11,6 +11,8 @@
 #include <unordered_map>
 #include <string>
 #include <thread>
+#include <atomic>
+#include <memory>
 #include <vector>
 
 #include "../../include/wepp_b200.h"
@@ -2288,12 +2290,20 @@ constexpr int MAX_NEIGHBORS_WEPP = 50;      // :23
 // Host view of the arena for the haplotype-to-haplotype work of the peak loop.
 struct PeakHost {
     const wepp_handle* h;
-    std::vector<int64_t> child_off;
-    std::vector<int32_t> child;
+    std::vector<int64_t> own_child_off;
+    std::vector<int32_t> own_child;
+    const std::vector<int64_t>& child_off;   // the children lists: this object's own, or another's (worker threads)
+    const std::vector<int32_t>& child;
     std::unordered_map<int32_t, std::vector<std::pair<int32_t, uint8_t>>> cache;
     std::vector<int64_t> last;
 
-    explicit PeakHost(const wepp_handle* hh) : h(hh) {
+    // a worker's view: shares the children lists, has its own stack cache and scratch
+    PeakHost(const wepp_handle* hh, const PeakHost& share) : h(hh), child_off(share.child_off), child(share.child) {
+        last.assign((size_t)h->genome + 1, -1);
+    }
+    explicit PeakHost(const wepp_handle* hh) : h(hh), child_off(own_child_off), child(own_child) {
+        std::vector<int64_t>& child_off = own_child_off;
+        std::vector<int32_t>& child = own_child;
         const int32_t n = h->n_nodes;
         child_off.assign((size_t)n + 1, 0);
         for (int32_t v = 1; v < n; ++v) ++child_off[h->parent[v] + 1];
@@ -2342,6 +2352,42 @@ struct PeakHost {
         }
         (void)A;
         return m;
+    }
+
+    // The same walk at the largest radius of the neighbour expansion, once: every node of the radius-`radius`
+    // neighbourhood with the smallest radius at which neighbors() reaches it (the largest distance from the pivot over
+    // the tree path between them — the climb stops at the first ancestor beyond the radius and the descent does not
+    // pass a node beyond it).  neighbors(pivot, r, mapped) = the nodes here with need <= r that are not mapped.
+    void neighborhood(int32_t pivot, int radius, std::vector<std::pair<int32_t, int>>& out) {
+        out.clear();
+        std::unordered_map<int32_t, int> chain;   // the pivot's ancestors within reach: need along the climb
+        int32_t curr = pivot;
+        int need = 0;
+        chain.emplace(pivot, 0);
+        while (h->parent[curr] >= 0) {
+            const int d = dist(pivot, h->parent[curr]);
+            if (d > radius) break;
+            need = std::max(need, d);
+            curr = h->parent[curr];
+            chain.emplace(curr, need);
+        }
+        std::vector<std::pair<int32_t, int>> st{{curr, 0}};
+        while (!st.empty()) {
+            const int32_t v = st.back().first;
+            const int above = st.back().second;
+            st.pop_back();
+            int nd;
+            const auto it = chain.find(v);
+            if (it != chain.end()) {
+                nd = it->second;
+            } else {
+                const int d = dist(pivot, v);
+                if (d > radius) continue;
+                nd = std::max(above, d);
+            }
+            out.emplace_back(v, nd);
+            for (int64_t k = child_off[v + 1] - 1; k >= child_off[v]; --k) st.emplace_back(child[k], nd);
+        }
     }
 
     // arena::highest_scoring_neighbors(pivot, include_mapped = false, radius, INT_MAX) (arena.cpp:209-249),
@@ -2693,12 +2739,35 @@ extern "C" int wepp_filter_peaks(wepp_handle* h, const int32_t* leaf_count, cons
         if (std::fabs(full[l] - full[r]) > PEAK_SCORE_EPSILON) return full[l] > full[r];
         return cmp_tie(l, r);
     };
+    // the five radii are nested: one walk per peak at the largest radius, on the host threads (each with its own stack
+    // cache), records the radius each node is first reached at; the rounds below filter it
+    const std::vector<int32_t> peak_list(peaks.begin(), peaks.end());
+    std::vector<std::vector<std::pair<int32_t, int>>> hood(peak_list.size());
+    {
+        const int n_thr = (int)std::max<size_t>(1, std::min<size_t>({(size_t)16, (size_t)std::thread::hardware_concurrency(), peak_list.size()}));
+        std::atomic<size_t> next{0};
+        auto work = [&](PeakHost* me) {
+            for (size_t i = next.fetch_add(1); i < peak_list.size(); i = next.fetch_add(1))
+                me->neighborhood(peak_list[i], MAX_PEAK_PEAK_MUTATION + 4, hood[i]);
+        };
+        if (n_thr <= 1) {
+            work(&ph);
+        } else {
+            std::vector<std::unique_ptr<PeakHost>> views;
+            std::vector<std::thread> pool;
+            for (int t = 0; t < n_thr; ++t) views.emplace_back(new PeakHost(h, ph));
+            for (int t = 0; t < n_thr; ++t) pool.emplace_back(work, views[(size_t)t].get());
+            for (auto& th : pool) th.join();
+        }
+    }
     std::set<int32_t> nbrs;
     for (int k = 0; k < 5; ++k) {
         std::fill(mapped.begin(), mapped.end(), 0);
         std::set<int32_t> curr;
-        for (int32_t pivot : peaks) {
-            ph.neighbors(pivot, MAX_PEAK_PEAK_MUTATION + k, mapped, nb);
+        for (size_t pi = 0; pi < peak_list.size(); ++pi) {
+            nb.clear();
+            for (const auto& vn : hood[pi])
+                if (vn.second <= MAX_PEAK_PEAK_MUTATION + k && !mapped[vn.first]) nb.push_back(vn.first);
             std::set<int32_t, decltype(cmp)> ordered(cmp);
             for (int32_t v : nb) ordered.insert(v);
             int i = 0;
