@@ -1,3 +1,4 @@
 set -x
-timeout 900 python -m pytest tests/test_golden.py tests/test_cli_gpu.py -x -q -m gpu -k "peak_loop or selective or sharded" 2>&1 | tail -3
-WEPP_TIMING=1 timeout 900 python profiles/peaks_run.py 1.0 2>&1 | grep "initial filter\|peak loop\|neighbour\|filter_peaks_s" | cut -c1-330
+cp wepp_b200/libwepp_b200.so /tmp/lib_orig.so
+for U in 512 128; do cp profiles/tmp_libs/lib_unit_$U.so wepp_b200/libwepp_b200.so; echo UNIT $U; timeout 600 python profiles/dev_paths.py 1.0 2>&1 | grep "^delta {" ; done
+cp /tmp/lib_orig.so wepp_b200/libwepp_b200.so

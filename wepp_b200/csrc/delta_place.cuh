@@ -48,7 +48,7 @@ constexpr int DP_BINS = 64;           // score bins: bin = base - red + DP_VOFF
 constexpr int DP_VOFF = SW_MAX_ACTIVE;   // base <= SW_MAX_ACTIVE and red <= 2 * base
 constexpr int DP_CAND_MIN = 64;       // candidate queue entries per warp: at least this many (the rest of the shared memory is split)
 constexpr int DP_FAST_MUTS = 7;       // reads with more mutations use byte scratch in global memory (nibbles hold <= 15)
-constexpr int DP_UNIT = 256;          // reads per work unit (a group of up to 2 * DP_UNIT reads stays whole)
+constexpr int DP_UNIT = 512;          // reads per work unit (a group of up to 2 * DP_UNIT reads stays whole)
 constexpr int DP_FIXED = 16 + DP_BINS * 4 + DP_WARPS * DP_BINS * 4;   // ctrl, whist, mv
 static_assert(DP_VOFF + SW_MAX_ACTIVE + 1 <= DP_BINS, "score bins");
 constexpr uint32_t DP_X_NONE = 7u;    // allele class of a state entry that equals no read allele (IUPAC union)
