@@ -1,4 +1,3 @@
 set -x
-cp wepp_b200/libwepp_b200.so /tmp/lib_orig.so
-for U in 512 128; do cp profiles/tmp_libs/lib_unit_$U.so wepp_b200/libwepp_b200.so; echo UNIT $U; timeout 600 python profiles/dev_paths.py 1.0 2>&1 | grep "^delta {" ; done
-cp /tmp/lib_orig.so wepp_b200/libwepp_b200.so
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_c1_full.py -x -q -m gpu -k "delta or state_place or c1" 2>&1 | tail -3
+timeout 600 python profiles/dev_paths.py 1.0 2>&1 | tail -3

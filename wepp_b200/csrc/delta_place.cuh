@@ -201,7 +201,14 @@ __global__ void delta_mrec_kernel(const DeltaUnit* __restrict__ units, const Del
         for (uint32_t k = r.z; k < r.z + (uint32_t)nm; ++k) {
             const size_t cell = (size_t)(lp + rm_pos[k] - b0) * DP_LEVELS;
             const uint32_t lo = post_off[cell], hi = post_off[cell + levels];
-            mrec[k] = make_uint2(lo, (hi - lo) | ((uint32_t)rm_code[k] << 28));
+            uint2 m = make_uint2(lo, (hi - lo) | ((uint32_t)rm_code[k] << 28));
+            // shortest posting list first (the order of a read's mutations is free): the states of the read's own
+            // lineage carry its rare mutations, so they are low before the long lists of its clade-level mutations
+            // are walked — and a lane that has seen a low score no longer tracks the hits above it
+            uint32_t at = k;
+            if (nm <= 32)
+                for (; at > r.z && (mrec[at - 1].y & 0x0FFFFFFFu) > (m.y & 0x0FFFFFFFu); --at) mrec[at] = mrec[at - 1];
+            mrec[at] = m;
         }
     }
 }
@@ -304,6 +311,7 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
     const unsigned FULL = 0xFFFFFFFFu;
     const int nm = (int)(rec.w & 0xFFFFu), k_non_n = (int)(rec.w >> 16);
     int* n_cand_s = mv + (DP_BINS - 1);   // bins above DP_VOFF + SW_MAX_ACTIVE are never used: the last one counts candidates
+    int lane_min = dg.m0;                 // the lowest score this lane has seen a state end at (tracked bins start at m0)
     for (int j0 = 0; j0 < nm; j0 += 32) {
         uint2 mm = m;
         if (j0 > 0) {
@@ -321,6 +329,7 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
                 nxt[h] = make_uint2(0u, 0u);
                 if (lo + 32 * h + lane < hi) nxt[h] = __ldg(p.post + lo + 32 * h + lane);
             }
+            lane_min = __reduce_min_sync(FULL, lane_min);   // what any lane has seen, once per posting list
             for (uint32_t i0 = lo; i0 < hi; i0 += 32 * DP_U) {
                 uint2 e[DP_U];
                 bool act[DP_U];
@@ -357,9 +366,14 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
                 // to it once the minimum is known.  (Measured dead ends: keeping the top bins per lane in registers and
                 // taking queue slots from a ballot instead of these same-address atomics — 5.26 vs 4.87 ms, the
                 // unconditional instructions cost more than the serialised atomics of the ~10 % of hits that get here.)
+                // A lane that has already seen a lower score skips a hit above it: the bins above the read's minimum
+                // may then be off (an arrival not recorded, its departure later taken from a bin it never entered),
+                // the minimum's bin and everything below it are not — a hit that ends at the final minimum is never
+                // above anything its lane has seen.
 #pragma unroll
                 for (int h = 0; h < DP_U; ++h) {
-                    if (v_new[h] <= dg.m0) {
+                    if (v_new[h] <= lane_min) {
+                        lane_min = v_new[h];
                         if (v_new[h] + d[h] <= dg.m0) atomicSub(&mv[v_new[h] + d[h]], (int)e[h].y);
                         atomicAdd(&mv[v_new[h]], (int)e[h].y);
                         if (FAST) {
