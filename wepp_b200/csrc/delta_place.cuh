@@ -342,13 +342,12 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
                 int d[DP_U], v_new[DP_U];
 #pragma unroll
                 for (int h = 0; h < DP_U; ++h) {
-                    e[h] = nxt[h];
-                    const bool in = i0 + 32 * h + lane < hi;
+                    e[h] = nxt[h];   // (a lane past the end holds x = 0: no allele bit, delta[ref] = 0, so d = 0)
                     nxt[h] = make_uint2(0u, 0u);
                     if (i0 + 32 * (DP_U + h) + lane < hi) nxt[h] = __ldg(p.post + i0 + 32 * (DP_U + h) + lane);
                     s[h] = e[h].x & 0xFFFFFFu;
                     d[h] = __popc(e[h].x & cmask);   // delta[ref] - delta[c]
-                    act[h] = in && d[h] > 0;
+                    act[h] = d[h] > 0;
                 }
 #pragma unroll
                 for (int h = 0; h < DP_U; ++h) {
