@@ -43,7 +43,8 @@
 
 namespace wepp {
 
-constexpr int DP_WARPS = 16;          // warps per CTA (one CTA per SM: the shared memory is the limit; 24 warps at 72 registers measured slower, 5.2 vs 5.0 ms)
+constexpr int DP_WARPS = 8;           // warps per CTA
+constexpr int DP_CTAS = 2;            // CTAs per SM, each with half of the shared memory (see delta_place_kernel)
 constexpr int DP_BINS = 64;           // score bins: bin = base - red + DP_VOFF
 constexpr int DP_VOFF = SW_MAX_ACTIVE;   // base <= SW_MAX_ACTIVE and red <= 2 * base
 constexpr int DP_CAND_MIN = 64;       // candidate queue entries per warp: at least this many (the rest of the shared memory is split)
@@ -463,7 +464,7 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(DP_WARPS * 32, 1) delta_place_kernel(const DeltaPlaceParams p) {
+__global__ void __launch_bounds__(DP_WARPS * 32, DP_CTAS) delta_place_kernel(const DeltaPlaceParams p) {
     extern __shared__ __align__(16) unsigned char smem[];
     int* ctrl = reinterpret_cast<int*>(smem);                       // [0] unit, [1] next read of the unit
     int* whist_s = reinterpret_cast<int*>(smem + 16);
