@@ -146,17 +146,21 @@ __global__ void delta_keys_kernel(const TileDesc* __restrict__ tiles, const Buck
                                   const ListDesc* __restrict__ list_desc, const int64_t* __restrict__ perm,
                                   const int32_t* __restrict__ start, const int32_t* __restrict__ end,
                                   const int64_t* __restrict__ rm_off, const int32_t* __restrict__ rm_pos,
-                                  const uint32_t* __restrict__ post_off, const int32_t* __restrict__ lpos_base,
-                                  uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
+                                  const uint8_t* __restrict__ rm_code, const uint32_t* __restrict__ post_off,
+                                  const int32_t* __restrict__ lpos_base, uint64_t* __restrict__ key, uint32_t* __restrict__ val) {
     const TileDesc td = tiles[blockIdx.x];
     const int32_t list = buckets[td.bucket].list;
     const int32_t b0 = list_desc[list].b0, lp = lpos_base[list];
     for (int i = threadIdx.x; i < td.count; i += blockDim.x) {
         const int64_t rid = perm[td.first + i];
         uint32_t cost = 0;
+        // (the cells the read will walk if its window's minimum is the empty state's, the usual case: delta_mrec_kernel)
+        int levels = 1;
+        for (int64_t k = rm_off[rid]; k < rm_off[rid + 1]; ++k) levels += rm_code[k] <= 4u ? 2 : 1;
+        levels = min(levels, DP_LEVELS);
         for (int64_t k = rm_off[rid]; k < rm_off[rid + 1]; ++k) {
             const size_t slot = (size_t)(lp + rm_pos[k] - b0);
-            cost += post_off[(slot + 1) * DP_LEVELS] - post_off[slot * DP_LEVELS] + 16u;
+            cost += post_off[slot * DP_LEVELS + levels] - post_off[slot * DP_LEVELS] + 16u;
         }
         const uint64_t w = ((uint64_t)td.bucket << 24) | ((uint64_t)(start[rid] - b0) << 12) | (uint64_t)(end[rid] - b0);
         key[td.first + i] = (w << DP_COST_BITS) | (uint64_t)(255u - min(255u, cost >> 6));

@@ -673,7 +673,7 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
     CU(key.ensure((size_t)R)); CU(key2.ensure((size_t)R)); CU(ukey.ensure((size_t)R));
     CU(val.ensure((size_t)R)); CU(dp.order.ensure((size_t)R)); CU(ucount.ensure((size_t)R)); CU(nruns.ensure(1));
     delta_keys_kernel<<<n_tiles, 256, 0, st>>>(dp.tiles.p, dp.buckets.p, dp.lists.p, dp.perm.p, h->d_rstart.p, h->d_rend.p, h->d_roff.p,
-                                               h->d_rpos.p, dp.post_off.p, dp.lpos_base.p, key.p, val.p);
+                                               h->d_rpos.p, h->d_rcode.p, dp.post_off.p, dp.lpos_base.p, key.p, val.p);
     CU(cudaGetLastError());
     int key_bits = 24 + DP_COST_BITS;
     while ((1ll << (key_bits - 24 - DP_COST_BITS)) < n_buckets) ++key_bits;
