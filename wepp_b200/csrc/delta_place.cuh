@@ -43,14 +43,16 @@
 
 namespace wepp {
 
-constexpr int DP_WARPS = 8;           // warps per CTA
-constexpr int DP_CTAS = 2;            // CTAs per SM, each with half of the shared memory (measured: 1 x 16 warps 4.12 ms, 2 x 8 3.60, 3 x 6 4.2, 4 x 4 5.3)
+// CTA shapes (warps per CTA x CTAs per SM, the shared memory split between the CTAs): 8 x 2 where the widest list of
+// the plan fits half of an SM's shared memory (measured 3.60 ms; 16 x 1: 4.12, 6 x 3: 4.2, 4 x 4: 5.3 — a heavy read at
+// the end of a unit idles the other warps of its CTA, and fewer warps wait with smaller CTAs), else 16 x 1
+constexpr int DP_WARPS_SM = 16;       // warps per SM in either shape
 constexpr int DP_BINS = 64;           // score bins: bin = base - red + DP_VOFF
 constexpr int DP_VOFF = SW_MAX_ACTIVE;   // base <= SW_MAX_ACTIVE and red <= 2 * base
 constexpr int DP_CAND_MIN = 64;       // candidate queue entries per warp: at least this many (the rest of the shared memory is split)
 constexpr int DP_FAST_MUTS = 7;       // reads with more mutations use byte scratch in global memory (nibbles hold <= 15)
 constexpr int DP_UNIT = 512;          // reads per work unit (a group of up to 2 * DP_UNIT reads stays whole)
-constexpr int DP_FIXED = 16 + DP_BINS * 4 + DP_WARPS * DP_BINS * 4;   // ctrl, whist, mv
+__host__ __device__ constexpr int dp_fixed(int warps) { return 16 + DP_BINS * 4 + warps * DP_BINS * 4; }   // ctrl, whist, mv
 static_assert(DP_VOFF + SW_MAX_ACTIVE + 1 <= DP_BINS, "score bins");
 constexpr uint32_t DP_X_NONE = 7u;    // allele class of a state entry that equals no read allele (IUPAC union)
 constexpr int DP_MARGIN = 16;         // the core of a list of `width` positions is [DP_MARGIN, width - 1 - DP_MARGIN]: inside every window of the list
@@ -468,7 +470,9 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(DP_WARPS * 32, DP_CTAS) delta_place_kernel(const DeltaPlaceParams p) {
+template <int DP_WARPS>
+__global__ void __launch_bounds__(DP_WARPS * 32, DP_WARPS_SM / DP_WARPS) delta_place_kernel(const DeltaPlaceParams p) {
+    constexpr int DP_FIXED = dp_fixed(DP_WARPS);
     extern __shared__ __align__(16) unsigned char smem[];
     int* ctrl = reinterpret_cast<int*>(smem);                       // [0] unit, [1] next read of the unit
     int* whist_s = reinterpret_cast<int*>(smem + 16);

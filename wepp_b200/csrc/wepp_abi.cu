@@ -451,7 +451,12 @@ int launch_place_k(wepp_handle* h, const PlaceParams& pp, int width) {
 }
 
 // dynamic shared memory of one delta_place_kernel CTA: DP_CTAS of them share an SM (each also costs 1 KiB of system use)
-inline int delta_smem_bytes(const wepp_handle* h) { return (int)((((h->smem_optin + 1024) / DP_CTAS) - 1024) & ~(size_t)15); }
+inline int delta_smem_bytes(const wepp_handle* h, int ctas) { return (int)((((h->smem_optin + 1024) / ctas) - 1024) & ~(size_t)15); }
+// shared memory a CTA of `warps` warps needs for a list of s states: the fixed areas, the base scores, and at least four
+// warps' nibble scratch + candidate queues
+inline int64_t delta_smem_need(int64_t s, int warps) {
+    return dp_fixed(warps) + ((s + 15) & ~15ll) + 4 * ((s + 255) / 256 * 128 + DP_CAND_MIN * 4);
+}
 
 // The distinct restricted haplotypes ("states") of every list of the plan: state_place.cuh.
 int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
@@ -635,8 +640,8 @@ int build_states(wepp_handle* h, wepp_handle::DevPlan& dp) {
             CU(cudaStreamSynchronize(st));
             // shared memory of delta_place_kernel: the widest list's base scores + at least 4 warps' nibble scratch
             const int64_t s_max = dp.max_list_states;
-            const int64_t need = DP_FIXED + ((s_max + 15) & ~15ll) + 4 * ((s_max + 255) / 256 * 128 + DP_CAND_MIN * 4);
-            dp.delta_usable = h_bad == 0 && need <= (int64_t)delta_smem_bytes(h);
+            const int64_t need = delta_smem_need(s_max, DP_WARPS_SM);
+            dp.delta_usable = h_bad == 0 && need <= (int64_t)delta_smem_bytes(h, 1);
             if (getenv("WEPP_TIMING") && atoi(getenv("WEPP_TIMING")) != 0)
                 fprintf(stderr, "[wepp timing] postings: %lld slots, %lld entries, tables %s, widest list %lld states, shared memory %lld of %lld -> %s\n",
                         (long long)slots, (long long)total_ent, h_bad ? "NOT of the allele form" : "ok", (long long)s_max, (long long)need,
@@ -766,7 +771,7 @@ int build_delta_groups(wepp_handle* h, wepp_handle::DevPlan& dp) {
     CU(cudaGetLastError());
     // byte scratch in global memory for the reads with many mutations: one area per warp of the persistent grid
     const int64_t words = ((int64_t)dp.max_list_states + 3) / 4 + 4;
-    const size_t need = (size_t)h->n_sms * DP_CTAS * DP_WARPS * (size_t)words;
+    const size_t need = (size_t)h->n_sms * DP_WARPS_SM * (size_t)words;
     if (need > dp.gscratch.cap) {
         CU(dp.gscratch.ensure(need));
         CU(cudaMemsetAsync(dp.gscratch.p, 0, dp.gscratch.cap * 4, st));   // the kernel leaves it zero
@@ -942,13 +947,23 @@ int run_place(wepp_handle* h, wepp_handle::DevPlan& dp, bool accumulate, int32_t
         // shared memory: fixed areas + the widest list's base scores + 16 warps' nibble scratch, as far as it fits
         const int64_t s_max = dp.max_list_states;
         // (one CTA per SM: all of it — what the scratch areas leave is the warps' candidate queues)
-        const int smem = delta_smem_bytes(h);
+        // two CTAs of 8 warps per SM where the widest list leaves room in half of the shared memory, else one of 16
+        // (WEPP_DELTA_CTAS=1 forces the latter: tests)
+        const bool two = delta_smem_need(s_max, DP_WARPS_SM / 2) <= (int64_t)delta_smem_bytes(h, 2) &&
+                         !(getenv("WEPP_DELTA_CTAS") && atoi(getenv("WEPP_DELTA_CTAS")) == 1);
+        const int ctas = two ? 2 : 1, warps = DP_WARPS_SM / ctas;
+        const int smem = delta_smem_bytes(h, ctas);
         dq.smem_bytes = smem;
         dq.cand_cap = 1 << 20;
         if (getenv("WEPP_DELTA_CAND")) dq.cand_cap = std::max(0, atoi(getenv("WEPP_DELTA_CAND")));
-        CU(allow_max_smem(delta_place_kernel, h));
-        const int grid_dp = std::max(1, std::min((int)dq.n_units, h->n_sms * DP_CTAS));
-        delta_place_kernel<<<grid_dp, DP_WARPS * 32, smem, h->stream>>>(dq);
+        const int grid_dp = std::max(1, std::min((int)dq.n_units, h->n_sms * ctas));
+        if (two) {
+            CU(allow_max_smem(delta_place_kernel<DP_WARPS_SM / 2>, h));
+            delta_place_kernel<DP_WARPS_SM / 2><<<grid_dp, warps * 32, smem, h->stream>>>(dq);
+        } else {
+            CU(allow_max_smem(delta_place_kernel<DP_WARPS_SM>, h));
+            delta_place_kernel<DP_WARPS_SM><<<grid_dp, warps * 32, smem, h->stream>>>(dq);
+        }
         CU(cudaGetLastError());
         dim3 fgrid((unsigned)std::min<int64_t>((s_max + 255) / 256, 1024), (unsigned)pl.buckets.size());
         delta_finalize_kernel<<<fgrid, 256, 0, h->stream>>>(dp.groups.p, dp.bucket_goff.p, dp.state_first.p, dp.buckets.p, dp.base.p,
