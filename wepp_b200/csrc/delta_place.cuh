@@ -24,11 +24,20 @@
 // score) sum G that is expanded once per step; touched states that end at the minimum get it directly.  A touched
 // state can never leave the minimum (red > 0 only lowers it), so there is nothing to subtract.
 //
-//   post_*_kernel          posting lists: per (list, position) the states that mutate it (state, allele class, nodes)
-//   delta_keys_kernel      sort key (bucket, window) per read -> cub sort + run-length encode = window groups
+// What keeps the walk short (all exact, each explained where it is done): only the posting cells whose states can
+// still end at or below the window's minimum are walked (post_pairs_kernel / delta_mrec_kernel); a lane that has seen
+// a lower score stops tracking the hits above it, and a read's shortest posting list comes first (dp_read).
+//
+//   post_pairs_kernel      posting lists: per (list, position, core base score) the states that mutate the position
+//                          {state | allele one-hot | delta[ref], nodes}
+//   delta_keys_kernel      sort key (bucket, window, cost) per read -> cub sort + run-length encode = window groups
 //   window_base_kernel     base_w(s) for every group of a list, and the groups' histograms
-//   delta_place_kernel     persistent CTAs pull work units (<= 128 reads of one group); a warp takes a read
+//   delta_mrec_kernel      per read mutation: the postings it walks (they depend on the window's minimum)
+//   delta_place_kernel     persistent CTAs (8 warps, two per SM) pull work units (a window group, or 512 reads of a
+//                          large one); a warp takes a read
 //   delta_finalize_kernel  per-(bucket, state) accumulators += sum over the bucket's groups of G[group][base(s)]
+// The peak loop places its removed reads through the same kernels over the subset's own work units
+// (wepp_abi.cu: place_subset_by_delta).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
