@@ -429,8 +429,12 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
         p.mult[rec.x] = n_epp;
     }
     if (n_epp > 0 && lane == (mV & 31)) {
-        gw[mV >> 5] += wgt;
-        gc[mV >> 5] += deg;
+        // (selects, not gw[mV >> 5]: a dynamic index would put the two sums into local memory)
+        const bool low = mV < 32;
+        gw[0] += low ? wgt : 0.0;
+        gw[1] += low ? 0.0 : wgt;
+        gc[0] += low ? deg : 0;
+        gc[1] += low ? 0 : deg;
     }
     // touched states at the minimum; scratch back to zero
     if (FAST && n_cand <= cand_cap) {
