@@ -494,10 +494,10 @@ __global__ void __launch_bounds__(NT_THREADS, 2) node_tile_kernel(const NodeTile
             }
             if (lane == 31) warp_tot[warp] = inc;
             __syncthreads();
-            U128 off = {0, 0};
-            for (int w = 0; w < warp; ++w) off = add128(off, warp_tot[w]);
-            const U128 run = add128(off, inc);
-            if ((int)threadIdx.x < rows) {
+            if ((int)threadIdx.x < rows) {   // (only the first NT_TILE threads hold a row: the other warps have nothing to add up)
+                U128 off = {0, 0};
+                for (int w = 0; w < warp; ++w) off = add128(off, warp_tot[w]);
+                const U128 run = add128(off, inc);
                 const double d = ((double)(long long)run.hi * 18446744073709551616.0 + (double)run.lo) * 8.271806125530277e-25;   // 2^-80
                 p.score[c0 + threadIdx.x] = (p.mapped && p.mapped[c0 + threadIdx.x]) ? 0.0 : d;
                 if ((int)threadIdx.x == rows - 1)
@@ -531,8 +531,9 @@ __global__ void __launch_bounds__(NT_THREADS, 2) node_tile_kernel(const NodeTile
             for (int i = 0; i < NT_SEG; ++i) {
                 run += v[i];
                 c[i * NBINS] = run;
-                if (seg * NT_SEG + i == rows - 1) carry_cnt[col] = run + spill_cnt[col];   // before mapped rows are blanked
             }
+            // the tile's last row is the next tile's start (taken before mapped rows are blanked): its segment's thread
+            if (seg == (rows - 1) / NT_SEG) carry_cnt[col] = c[((rows - 1) % NT_SEG) * NBINS] + spill_cnt[col];
         }
         __syncthreads();
         // ---- mapped nodes hold nothing; divergence bin count per node; the tile goes out once -----------------------
