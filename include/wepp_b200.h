@@ -284,7 +284,7 @@ int  wepp_set_arena_from(wepp_handle* h, const wepp_arena* a);
  * The Newick token scan and the per-node mutation fill (the reference's tbb::parallel_for, :556-596) run
  * on WEPP_THREADS host threads (default: all).  wepp_mat_load keeps a flattened-tree sidecar
  * "<path>.wepp_flat" (or in $WEPP_SIDECAR_DIR): the parsed tree as flat arrays, keyed by the source's
- * size, mtime and a 64-bit hash of its bytes, read back on the next load of the same file instead of
+ * size and a 64-bit hash of its bytes, read back on the next load of the same file instead of
  * inflating and parsing it; WEPP_SIDECAR=0 turns it off, an unwritable directory is not an error.  */
 typedef struct wepp_mat wepp_mat;
 int  wepp_mat_load(const char* path, int32_t uncondense, wepp_mat** out);

@@ -626,8 +626,8 @@ void uncondense_leaves(MatTree& t) {
 // A parsed MAT (before uncondense_leaves) written next to the file it came from as "<file>.wepp_flat" — or into
 // $WEPP_SIDECAR_DIR — and read back instead of inflating and parsing the protobuf again: the same tree serves
 // every sample of a run (workflow/rules/filter.smk:21-36 passes one MAT to all of them).  The sidecar names its
-// source by size, modification time and a 64-bit hash of the source's bytes; any mismatch, a short file or another
-// layout version and the source is parsed (and the sidecar rewritten).  WEPP_SIDECAR=0 neither reads nor writes one;
+// source by size and a 64-bit hash of the source's bytes; any mismatch, a short file or another layout version and the
+// source is parsed (and the sidecar rewritten).  WEPP_SIDECAR=0 neither reads nor writes one;
 // a directory that cannot be written to is not an error.
 namespace {
 constexpr char SIDECAR_MAGIC[8] = {'W', 'E', 'P', 'P', 'F', 'L', 'T', '2'};
@@ -755,8 +755,9 @@ bool read_sidecar(const std::string& file, const SidecarHeader& key, MatTree& t)
     if (!slurp(file, bytes).empty() || bytes.size() < sizeof(SidecarHeader)) return false;
     SidecarHeader h;
     std::memcpy(&h, bytes.data(), sizeof(h));
+    // (the source's modification time is recorded but not compared: a copied data directory keeps a valid sidecar)
     if (std::memcmp(h.magic, SIDECAR_MAGIC, 8) != 0 || h.src_size != key.src_size || h.src_hash != key.src_hash ||
-        h.src_mtime_ns != key.src_mtime_ns || h.n_nodes >= (1ull << 31) || h.n_annotations < 0)
+        h.n_nodes >= (1ull << 31) || h.n_annotations < 0)
         return false;
     t = MatTree();
     BlobReader r{bytes.data() + sizeof(h), bytes.data() + bytes.size()};

@@ -290,7 +290,15 @@ int wepp_group_run(wepp_group* g, wepp_group_fn fn, void* user) {
 int wepp_group_set_arena(wepp_group* g, int32_t n_nodes, const int32_t* parent, const int64_t* mut_off, const int32_t* mut_pos,
                          const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size) {
     if (!g) return fail(WEPP_E_INVALID, "group is NULL");
-    return group_run(g, [&](int r) { return wepp_set_arena(g->h[(size_t)r], n_nodes, parent, mut_off, mut_pos, mut_ref, mut_nuc, genome_size); });
+    if (!g->h[0] || !parent || !mut_off) return fail(WEPP_E_INVALID, "NULL argument");
+    // one host flatten for all ranks (it already uses every core); each rank copies and uploads it
+    wepp::EulerStripes es;
+    const std::string err = wepp::build_euler_stripes(n_nodes, parent, mut_off, mut_pos, mut_ref, mut_nuc, genome_size, g->h[0]->opt_q, es);
+    if (!err.empty()) return fail(WEPP_E_INVALID, err);
+    return group_run(g, [&](int r) {
+        return set_arena_with(g->h[(size_t)r], n_nodes, parent, mut_off, mut_pos, mut_ref, mut_nuc, genome_size,
+                              g->h[(size_t)r]->opt_q == g->h[0]->opt_q ? &es : nullptr);
+    });
 }
 
 int wepp_group_set_reads(wepp_group* g, int64_t n_reads, const int32_t* start, const int32_t* end, const int32_t* degree,

@@ -1188,6 +1188,9 @@ static void copy_out(T* dst, const std::vector<T>& v) {
     if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(T));
 }
 
+int set_arena_with(wepp_handle* h, int32_t n_nodes, const int32_t* parent, const int64_t* mut_off, const int32_t* mut_pos,
+                   const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size, const EulerStripes* flattened);
+
 extern "C" {
 
 const char* wepp_last_error(void) { return g_err.c_str(); }
@@ -1262,13 +1265,26 @@ int wepp_set_options(wepp_handle* h, int32_t stripe_width, int32_t reads_per_lan
 
 int wepp_set_arena(wepp_handle* h, int32_t n_nodes, const int32_t* parent, const int64_t* mut_off,
                    const int32_t* mut_pos, const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size) {
+    return set_arena_with(h, n_nodes, parent, mut_off, mut_pos, mut_ref, mut_nuc, genome_size, nullptr);
+}
+
+}  // extern "C"
+
+// wepp_set_arena; `flattened` = the tree's Euler stripes already built for this stripe width (the ranks of a group
+// share one host flatten)
+int set_arena_with(wepp_handle* h, int32_t n_nodes, const int32_t* parent, const int64_t* mut_off, const int32_t* mut_pos,
+                   const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size, const EulerStripes* flattened) {
     if (!h) return fail(WEPP_E_INVALID, "handle is NULL");
     if (!parent || !mut_off) return fail(WEPP_E_INVALID, "parent / mut_off is NULL");
     if (n_nodes >= 1 && mut_off[n_nodes] > 0 && (!mut_pos || !mut_ref || !mut_nuc))
         return fail(WEPP_E_INVALID, "mutation arrays are NULL");
     CU(cudaSetDevice(h->device));
-    std::string err = build_euler_stripes(n_nodes, parent, mut_off, mut_pos, mut_ref, mut_nuc, genome_size, h->opt_q, h->es);
-    if (!err.empty()) return fail(WEPP_E_INVALID, err);
+    if (flattened) {
+        h->es = *flattened;
+    } else {
+        std::string err = build_euler_stripes(n_nodes, parent, mut_off, mut_pos, mut_ref, mut_nuc, genome_size, h->opt_q, h->es);
+        if (!err.empty()) return fail(WEPP_E_INVALID, err);
+    }
     h->n_nodes = n_nodes;
     h->genome = genome_size;
     h->parent.assign(parent, parent + n_nodes);
@@ -1305,6 +1321,8 @@ int wepp_set_arena(wepp_handle* h, int32_t n_nodes, const int32_t* parent, const
     h->st_cache_nuc.clear();
     return WEPP_OK;
 }
+
+extern "C" {
 
 int wepp_set_reads(wepp_handle* h, int64_t n_reads, const int32_t* start, const int32_t* end,
                    const int32_t* degree, const int64_t* rm_off, const int32_t* rm_pos, const uint8_t* rm_nuc) {
