@@ -324,7 +324,9 @@ __device__ __forceinline__ int dp_nibble_shift(uint32_t s) { return (int)((s >> 
 // and the postings are walked again for the weights.  rec / m = the read's record and this lane's mutation record
 // (mutations 0..31; reads with more fetch the rest here).
 constexpr int DP_U = 4;   // chunks of 32 postings per loop iteration (independent dependency chains)
-template <bool FAST>
+// SINGLE (with FAST): a read with at most one mutation — every hit is its state's only one, so there is no earlier
+// reduction to look up and no scratch to keep (nor to zero afterwards); the queue remembers d beside the state.
+template <bool FAST, bool SINGLE = false>
 __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGroup& dg, const uint4 rec, const uint2 m, int lane,
                                         const unsigned char* base_s, uint32_t* scr, int scr_words, int* mv, uint32_t* cand,
                                         int cand_cap, const int* whist_s, int64_t so, double (&gw)[2], int (&gc)[2]) {
@@ -370,7 +372,9 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
                     v_new[h] = DP_BINS;
                     if (act[h]) {
                         int oldred;
-                        if (FAST) {
+                        if (SINGLE) {
+                            oldred = 0;
+                        } else if (FAST) {
                             const int sh = dp_nibble_shift(s[h]);
                             oldred = (int)((atomicAdd(scr + dp_nibble_word(s[h]), (uint32_t)d[h] << sh) >> sh) & 15u);
                         } else {
@@ -398,7 +402,7 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
                         atomicAdd(&mv[v_new[h]], (int)e[h].y);
                         if (FAST) {
                             const int slot = atomicAdd(n_cand_s, 1);
-                            if (slot < cand_cap) cand[slot] = s[h];
+                            if (slot < cand_cap) cand[slot] = SINGLE ? (s[h] | ((uint32_t)d[h] << 24)) : s[h];
                         }
                     }
                 }
@@ -439,15 +443,20 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
     // touched states at the minimum; scratch back to zero
     if (FAST && n_cand <= cand_cap) {
         for (int i = lane; i < n_cand; i += 32) {
-            const uint32_t s = cand[i];
-            const int sh = dp_nibble_shift(s);
-            const int red = (int)((atomicAnd(scr + dp_nibble_word(s), ~(15u << sh)) >> sh) & 15u);   // duplicates see 0
+            const uint32_t cs = cand[i], s = cs & 0xFFFFFFu;
+            int red;
+            if (SINGLE) {
+                red = (int)(cs >> 24);
+            } else {
+                const int sh = dp_nibble_shift(s);
+                red = (int)((atomicAnd(scr + dp_nibble_word(s), ~(15u << sh)) >> sh) & 15u);   // duplicates see 0
+            }
             if (red && n_epp > 0 && (int)base_s[s] + DP_VOFF - red == mV) {
                 atomicAdd(p.saccS + so + s, wgt);
                 atomicAdd(p.saccC + so + s, deg);
             }
         }
-        if (nm > 0) {
+        if (nm > 0 && !SINGLE) {
             __syncwarp();
             uint4* z = reinterpret_cast<uint4*>(scr);
             for (int i = lane; i < scr_words / 4; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -461,11 +470,15 @@ __device__ __forceinline__ void dp_read(const DeltaPlaceParams& p, const DeltaGr
                 const uint32_t lo = __shfl_sync(FULL, mm.x, j), hi = lo + (__shfl_sync(FULL, mm.y, j) & 0x0FFFFFFFu);
                 uint32_t nx = 0u;
                 if (lo + lane < hi) nx = __ldg(&p.post[lo + lane].x);
+                const uint32_t c2 = __shfl_sync(FULL, mm.y, j) >> 28;
+                const uint32_t cmask2 = (1u << 28) | ((c2 >= 1u && c2 <= 4u) ? (1u << (23u + c2)) : 0u);
                 for (uint32_t i = lo + lane; i < hi; i += 32) {
-                    const uint32_t s = nx & 0xFFFFFFu;
+                    const uint32_t x = nx, s = nx & 0xFFFFFFu;
                     if (i + 32 < hi) nx = __ldg(&p.post[i + 32].x);
                     int red;
-                    if (FAST) {
+                    if (SINGLE) {
+                        red = __popc(x & cmask2);
+                    } else if (FAST) {
                         const int sh = dp_nibble_shift(s);
                         red = (int)((atomicAnd(scr + dp_nibble_word(s), ~(15u << sh)) >> sh) & 15u);
                     } else {
@@ -553,7 +566,8 @@ __global__ void __launch_bounds__(DP_WARPS * 32, DP_WARPS_SM / DP_WARPS) delta_p
                 if (i3 < du.count) r3 = __ldg(rec + i3);
                 uint2 m2 = make_uint2(0u, 0u);
                 if (lane < (int)(r2.w & 0xFFFFu)) m2 = __ldg(p.mrec + r2.z + lane);
-                if ((int)(r1.w & 0xFFFFu) <= DP_FAST_MUTS) dp_read<true>(p, dg, r1, m1, lane, base_s, scr, stride / 4, mv, cand, cand_cap, whist_s, so, gw, gc);
+                if ((int)(r1.w & 0xFFFFu) <= 1) dp_read<true, true>(p, dg, r1, m1, lane, base_s, scr, stride / 4, mv, cand, cand_cap, whist_s, so, gw, gc);
+                else if ((int)(r1.w & 0xFFFFu) <= DP_FAST_MUTS) dp_read<true>(p, dg, r1, m1, lane, base_s, scr, stride / 4, mv, cand, cand_cap, whist_s, so, gw, gc);
                 else dp_read<false>(p, dg, r1, m1, lane, base_s, gscr, 0, mv, cand, 0, whist_s, so, gw, gc);
                 i1 = i2; r1 = r2; m1 = m2;
                 i2 = i3; r2 = r3;
