@@ -280,17 +280,24 @@ wepp_handle* wepp_group_take(wepp_group* g, int32_t rank) {
     return h;
 }
 
-int wepp_group_run(wepp_group* g, wepp_group_fn fn, void* user) {
-    if (!g || !fn) return fail(WEPP_E_INVALID, "NULL argument");
-    for (wepp_handle* h : g->h)
+// group-wide calls need every rank: a handle taken out (wepp_group_take) ends the group's collective life
+static int group_whole(const wepp_group* g) {
+    if (!g) return fail(WEPP_E_INVALID, "group is NULL");
+    for (const wepp_handle* h : g->h)
         if (!h) return fail(WEPP_E_STATE, "a handle was taken out of the group");
+    return WEPP_OK;
+}
+
+int wepp_group_run(wepp_group* g, wepp_group_fn fn, void* user) {
+    if (!fn) return fail(WEPP_E_INVALID, "NULL argument");
+    if (int rc = group_whole(g)) return rc;
     return group_run(g, [&](int r) { return fn(r, g->h[(size_t)r], user); });
 }
 
 int wepp_group_set_arena(wepp_group* g, int32_t n_nodes, const int32_t* parent, const int64_t* mut_off, const int32_t* mut_pos,
                          const uint8_t* mut_ref, const uint8_t* mut_nuc, int32_t genome_size) {
-    if (!g) return fail(WEPP_E_INVALID, "group is NULL");
-    if (!g->h[0] || !parent || !mut_off) return fail(WEPP_E_INVALID, "NULL argument");
+    if (int rc = group_whole(g)) return rc;
+    if (!parent || !mut_off) return fail(WEPP_E_INVALID, "NULL argument");
     // one host flatten for all ranks (it already uses every core); each rank copies and uploads it
     wepp::EulerStripes es;
     const std::string err = wepp::build_euler_stripes(n_nodes, parent, mut_off, mut_pos, mut_ref, mut_nuc, genome_size, g->h[0]->opt_q, es);
@@ -303,7 +310,7 @@ int wepp_group_set_arena(wepp_group* g, int32_t n_nodes, const int32_t* parent, 
 
 int wepp_group_set_reads(wepp_group* g, int64_t n_reads, const int32_t* start, const int32_t* end, const int32_t* degree,
                          const int64_t* rm_off, const int32_t* rm_pos, const uint8_t* rm_nuc) {
-    if (!g) return fail(WEPP_E_INVALID, "group is NULL");
+    if (int rc = group_whole(g)) return rc;
     if (n_reads < 0 || (n_reads > 0 && (!start || !end || !degree || !rm_off))) return fail(WEPP_E_INVALID, "NULL argument");
     g->n_reads = n_reads;
     const int G = g->G;
@@ -325,7 +332,7 @@ int wepp_group_set_reads(wepp_group* g, int64_t n_reads, const int32_t* start, c
 }
 
 int wepp_group_place(wepp_group* g) {
-    if (!g) return fail(WEPP_E_INVALID, "group is NULL");
+    if (int rc = group_whole(g)) return rc;
     return group_run(g, [&](int r) {
         const int rc = wepp_place(g->h[(size_t)r], 0, 0);
         return rc ? rc : wepp_sync(g->h[(size_t)r]);
@@ -333,7 +340,7 @@ int wepp_group_place(wepp_group* g) {
 }
 
 int wepp_group_get_read_results(wepp_group* g, int32_t* max_parsimony, int32_t* multiplicity) {
-    if (!g) return fail(WEPP_E_INVALID, "group is NULL");
+    if (int rc = group_whole(g)) return rc;
     const int G = g->G;
     const int64_t n = g->n_reads;
     return group_run(g, [&](int r) {
@@ -351,10 +358,11 @@ int wepp_group_get_read_results(wepp_group* g, int32_t* max_parsimony, int32_t* 
 
 int wepp_group_filter_peaks(wepp_group* g, const int32_t* leaf_count, const int32_t* id_rank, int32_t* out_nodes, int32_t capacity,
                             int32_t* n_peaks_out, int32_t* n_out) {
-    if (!g || !n_out) return fail(WEPP_E_INVALID, "NULL argument");
+    if (!n_out) return fail(WEPP_E_INVALID, "NULL argument");
+    if (int rc = group_whole(g)) return rc;
     std::vector<std::vector<int32_t>> outs((size_t)g->G);
     std::vector<int32_t> np((size_t)g->G, 0), no((size_t)g->G, 0);
-    const int32_t n = g->h[0] ? g->h[0]->n_nodes : 0;
+    const int32_t n = g->h[0]->n_nodes;
     int rc = group_run(g, [&](int r) {
         outs[(size_t)r].resize((size_t)std::max(n, 1));
         return wepp_filter_peaks(g->h[(size_t)r], leaf_count, id_rank, outs[(size_t)r].data(), n, &np[(size_t)r], &no[(size_t)r]);
