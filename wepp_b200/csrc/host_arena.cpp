@@ -2,7 +2,6 @@
 #include "host_arena.h"
 
 #include <algorithm>
-#include <deque>
 
 namespace wepp {
 
@@ -72,32 +71,49 @@ std::string build_arena(int32_t n_mat, const int32_t* parent, const int64_t* mut
     };
 
     // ---- condensed tree, BFS (util.cpp:79-133): keep a node iff it mutates a covered site; other
-    //      nodes fold into the nearest kept ancestor; children in BFS pop order -------------------
-    std::vector<int32_t> c_src, c_parent;                 // condensed nodes in creation order
-    std::vector<std::vector<int32_t>> c_children, c_map;  // children / folded MAT nodes
+    //      nodes fold into the nearest kept ancestor; children in BFS pop order.  Flat arrays throughout
+    //      (a vector per node costs seconds at 8 M nodes): the BFS order of the MAT, the condensed node every
+    //      MAT node lands in, then children and folded nodes as CSR filled in pop order -----------------
+    std::vector<int32_t> bfs((size_t)n_mat), land((size_t)n_mat, 0);   // land[v]: condensed id of v, or of the kept ancestor it folds into
+    std::vector<int32_t> c_src, c_parent;                              // condensed nodes in creation (= pop) order
+    c_src.reserve((size_t)n_mat);
+    c_parent.reserve((size_t)n_mat);
     c_src.push_back(0);
     c_parent.push_back(-1);
-    c_children.emplace_back();
-    c_map.push_back({0});
-    std::deque<std::pair<int32_t, int32_t>> q;  // (MAT node, condensed parent)
-    for (int32_t k = child_off[0]; k < child_off[1]; ++k) q.emplace_back(child[k], 0);
-    while (!q.empty()) {
-        const auto [v, np] = q.front();
-        q.pop_front();
-        int32_t tgt = np;
-        if (has_covered(v)) {
-            tgt = (int32_t)c_src.size();
-            c_src.push_back(v);
-            c_parent.push_back(np);
-            c_children.emplace_back();
-            c_map.push_back({v});
-            c_children[np].push_back(tgt);
-        } else {
-            c_map[np].push_back(v);
+    {
+        int32_t head = 0, tail = 0;
+        bfs[tail++] = 0;
+        while (head < tail) {
+            const int32_t v = bfs[head++];
+            if (v != 0) {
+                const int32_t np = land[parent[v]];
+                if (has_covered(v)) {
+                    land[v] = (int32_t)c_src.size();
+                    c_src.push_back(v);
+                    c_parent.push_back(np);
+                } else {
+                    land[v] = np;
+                }
+            }
+            for (int32_t k = child_off[v]; k < child_off[v + 1]; ++k) bfs[tail++] = child[k];
         }
-        for (int32_t k = child_off[v]; k < child_off[v + 1]; ++k) q.emplace_back(child[k], tgt);
     }
     const int32_t nc = (int32_t)c_src.size();
+    std::vector<int32_t> cc_off((size_t)nc + 1, 0), cc((size_t)std::max(nc - 1, 0));   // condensed children
+    for (int32_t c = 1; c < nc; ++c) ++cc_off[c_parent[c] + 1];
+    for (int32_t c = 0; c < nc; ++c) cc_off[c + 1] += cc_off[c];
+    {
+        std::vector<int32_t> cur(cc_off.begin(), cc_off.end() - 1);
+        for (int32_t c = 1; c < nc; ++c) cc[cur[c_parent[c]]++] = c;   // creation order = pop order
+    }
+    std::vector<int64_t> cm_off((size_t)nc + 1, 0);                   // MAT nodes folded into each condensed node
+    std::vector<int32_t> cm((size_t)n_mat);
+    for (int32_t v = 0; v < n_mat; ++v) ++cm_off[land[v] + 1];
+    for (int32_t c = 0; c < nc; ++c) cm_off[c + 1] += cm_off[c];
+    {
+        std::vector<int64_t> cur(cm_off.begin(), cm_off.end() - 1);
+        for (int32_t i = 0; i < n_mat; ++i) cm[cur[land[bfs[i]]]++] = bfs[i];   // itself first (popped before what folds into it), then pop order
+    }
 
     // ---- leaves under every MAT node (get_num_leaves, util.cpp:298-315) -------------------------
     std::vector<int32_t> leaves((size_t)n_mat, 0);
@@ -111,11 +127,14 @@ std::string build_arena(int32_t n_mat, const int32_t* parent, const int64_t* mut
     out.source.reserve(nc);
     out.leaf_count.reserve(nc);
     out.is_leaf.reserve(nc);
+    out.mut_off.reserve((size_t)nc + 1);
+    out.map_off.reserve((size_t)nc + 1);
+    out.map_nodes.reserve((size_t)n_mat);
     out.mut_off.push_back(0);
     out.map_off.push_back(0);
     std::vector<int32_t> arena_of((size_t)nc, -1);
-    std::vector<std::pair<int32_t, size_t>> stack;  // (condensed node, next child)
-    stack.emplace_back(0, 0);
+    std::vector<std::pair<int32_t, int32_t>> stack;  // (condensed node, next child slot)
+    std::vector<std::pair<int32_t, int64_t>> ms;
     auto emit = [&](int32_t c) {
         const int32_t idx = (int32_t)out.parent.size();
         arena_of[c] = idx;
@@ -125,26 +144,31 @@ std::string build_arena(int32_t n_mat, const int32_t* parent, const int64_t* mut
         out.leaf_count.push_back(leaves[v]);
         out.is_leaf.push_back(child_off[v + 1] == child_off[v]);
         // muts: the covered mutations, sorted by position (arena.cpp:45-46)
-        std::vector<std::pair<int32_t, int64_t>> ms;
+        ms.clear();
+        bool sorted = true;
         for (int64_t k = mut_off[v]; k < mut_off[v + 1]; ++k)
-            if (mut_pos[k] >= 1 && mut_pos[k] <= g && out.covered[mut_pos[k]]) ms.emplace_back(mut_pos[k], k);
-        std::stable_sort(ms.begin(), ms.end(), [](auto& a, auto& b) { return a.first < b.first; });
+            if (mut_pos[k] >= 1 && mut_pos[k] <= g && out.covered[mut_pos[k]]) {
+                sorted = sorted && (ms.empty() || ms.back().first <= mut_pos[k]);
+                ms.emplace_back(mut_pos[k], k);
+            }
+        if (!sorted) std::stable_sort(ms.begin(), ms.end(), [](auto& a, auto& b) { return a.first < b.first; });
         for (auto& m : ms) {
             out.mut_pos.push_back(m.first);
             out.mut_ref.push_back(mut_ref[m.second]);
             out.mut_nuc.push_back(mut_nuc[m.second]);
         }
         out.mut_off.push_back((int64_t)out.mut_pos.size());
-        for (int32_t u : c_map[c]) out.map_nodes.push_back(u);
+        out.map_nodes.insert(out.map_nodes.end(), cm.begin() + cm_off[c], cm.begin() + cm_off[c + 1]);
         out.map_off.push_back((int64_t)out.map_nodes.size());
     };
     emit(0);
+    stack.emplace_back(0, cc_off[0]);
     while (!stack.empty()) {
         auto& [c, k] = stack.back();
-        if (k < c_children[c].size()) {
-            const int32_t ch = c_children[c][k++];
+        if (k < cc_off[c + 1]) {
+            const int32_t ch = cc[k++];
             emit(ch);
-            stack.emplace_back(ch, 0);
+            stack.emplace_back(ch, cc_off[ch]);
         } else {
             stack.pop_back();
         }
