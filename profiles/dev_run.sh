@@ -1,2 +1,2 @@
 set -x
-timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_golden.py -x -q -m gpu -k "group" 2>&1 | tail -2
+timeout 600 python -m pytest tests/test_cli_gpu.py -x -q -m gpu -k "nomask" 2>&1 | tail -2

@@ -79,7 +79,8 @@ def test_detect_peaks_matches_reference_binary(case, tmp_path):
     ws = wd.make_workspace(a, **CASES[case])
     shutil.copytree(a, b)
     _run(REF, ws, a)
-    _run(OURS, ws, b)
+    # (one case also cuts the id sort of the load stage into runs, as an 8 M-node tree does by itself)
+    _run(OURS, ws, b, env={"WEPP_SORT_RUN": "64"} if case == "nomask_plain_pb" else {})
     compare_workspaces(a, b, ws)
 
 

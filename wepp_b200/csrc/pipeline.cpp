@@ -224,7 +224,22 @@ std::string pipeline_load(Pipeline& p) {
     // rank of haplotype::id in std::string order (score_comparator's last tie-break, arena.hpp:27-29)
     std::vector<int32_t> order((size_t)n);
     for (int32_t v = 0; v < n; ++v) order[(size_t)v] = v;
-    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) { return p.hap_id(a) < p.hap_id(b); });
+    {   // (ids are unique, so the order does not depend on how the sort is cut up: sorted runs on the host threads, merged pairwise)
+        auto less = [&](int32_t a, int32_t b) { return p.hap_id(a) < p.hap_id(b); };
+        int runs = 1;
+        const size_t min_run = std::getenv("WEPP_SORT_RUN") ? (size_t)std::max(1, std::atoi(std::getenv("WEPP_SORT_RUN"))) : 65536;   // (tests shrink it)
+        while (runs * 2 <= std::min(p.n_threads, 64) && (size_t)n / (size_t)(runs * 2) >= min_run) runs *= 2;
+        auto cut = [&](int r) { return order.begin() + (ptrdiff_t)((int64_t)n * r / runs); };
+        std::vector<std::thread> pool;
+        for (int r = 0; r < runs; ++r) pool.emplace_back([&, r]() { std::sort(cut(r), cut(r + 1), less); });
+        for (auto& t : pool) t.join();
+        for (int w = 1; w < runs; w *= 2) {
+            pool.clear();
+            for (int r = 0; r + w < runs; r += 2 * w)
+                pool.emplace_back([&, r, w]() { std::inplace_merge(cut(r), cut(r + w), cut(std::min(r + 2 * w, runs)), less); });
+            for (auto& t : pool) t.join();
+        }
+    }
     p.id_rank.assign((size_t)n, 0);
     for (int32_t k = 0; k < n; ++k) p.id_rank[(size_t)order[(size_t)k]] = k;
     p.child_off.assign((size_t)n + 1, 0);
