@@ -1,2 +1,3 @@
 set -x
-timeout 600 python -m pytest tests/test_cli_gpu.py -x -q -m gpu -k "nomask" 2>&1 | tail -2
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" 2>&1 | tail -1
+timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tiny0 and delta" 2>&1 | tail -1
