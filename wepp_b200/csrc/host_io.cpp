@@ -581,36 +581,104 @@ std::string parse_mat(const std::string& bytes, MatTree& t) {
 // tbb::concurrent_unordered_map, so the order in which condensed nodes are expanded — and with it the
 // node_<k> ids handed to condensed nodes that carry mutations, and the order of the new siblings — is
 // unspecified there; here it is the file order.
+namespace {
+// identifier -> node index for uncondense_leaves: the reference's all_nodes map restricted to what this pass does with
+// it (look a name up, rename the node).  Open addressing over node indices, the keys are the strings in t.id
+// themselves (std::unordered_map<std::string, int32_t> over 8 M ids costs several seconds).
+struct IdIndex {
+    std::vector<int32_t> slot;   // node index, -1 free, -2 deleted
+    uint64_t mask = 0;
+    const std::vector<std::string>& ids;
+    IdIndex(const std::vector<std::string>& id, size_t expect) : ids(id) {
+        size_t cap = 16;
+        while (cap < expect * 2 + 2) cap <<= 1;
+        slot.assign(cap, -1);
+        mask = cap - 1;
+    }
+    int64_t find_slot(std::string_view name) const {
+        for (uint64_t k = IdSet::hash(name) & mask;; k = (k + 1) & mask) {
+            if (slot[k] == -1) return -1;
+            if (slot[k] >= 0 && ids[(size_t)slot[k]] == name) return (int64_t)k;
+        }
+    }
+    void put(int32_t v) {   // index[ids[v]] = v (a later node with the same identifier takes the name over)
+        const std::string& name = ids[(size_t)v];
+        int64_t first_free = -1;
+        for (uint64_t k = IdSet::hash(name) & mask;; k = (k + 1) & mask) {
+            if (slot[k] == -1) {
+                slot[first_free >= 0 ? (uint64_t)first_free : k] = v;
+                return;
+            }
+            if (slot[k] == -2) {
+                if (first_free < 0) first_free = (int64_t)k;
+            } else if (ids[(size_t)slot[k]] == name) {
+                slot[k] = v;
+                return;
+            }
+        }
+    }
+};
+}  // namespace
+
 void uncondense_leaves(MatTree& t) {
     if (t.condensed_name.empty()) return;
-    std::unordered_map<std::string, int32_t> index;
-    index.reserve(t.id.size() * 2);
-    for (size_t v = 0; v < t.id.size(); ++v) index[t.id[v]] = (int32_t)v;
+    IoLaps lap("uncondense_leaves");
+    IdIndex index(t.id, t.id.size() + t.condensed_name.size());
+    {   // all identifiers, by the host threads (a free slot is claimed with a compare-and-swap); two nodes with one
+        // identifier — the later one owns the name — are left to one thread
+        std::atomic<int> duplicate{0};
+        parallel_ranges(t.id.size(), io_threads(), [&](int, size_t lo, size_t hi) {
+            for (size_t v = lo; v < hi; ++v) {
+                const std::string& name = t.id[v];
+                for (uint64_t k = IdSet::hash(name) & index.mask;; k = (k + 1) & index.mask) {
+                    const int32_t cur = __atomic_load_n(&index.slot[k], __ATOMIC_ACQUIRE);
+                    if (cur == -1) {
+                        int32_t expect = -1;
+                        if (__atomic_compare_exchange_n(&index.slot[k], &expect, (int32_t)v, false, __ATOMIC_ACQ_REL, __ATOMIC_ACQUIRE)) break;
+                        if (t.id[(size_t)expect] == name) {
+                            duplicate.store(1);
+                            break;
+                        }
+                    } else if (t.id[(size_t)cur] == name) {
+                        duplicate.store(1);
+                        break;
+                    }
+                }
+            }
+        });
+        if (duplicate.load()) {
+            std::fill(index.slot.begin(), index.slot.end(), -1);
+            for (size_t v = 0; v < t.id.size(); ++v) index.put((int32_t)v);
+        }
+    }
+    lap("identifier index");
     struct NewNode { int32_t parent; std::string id; float len; };
     std::vector<NewNode> added;
+    auto rename = [&](int64_t at, int32_t n, std::string id) {   // all_nodes.erase(old name); node->identifier = id; all_nodes[id] = node
+        index.slot[(size_t)at] = -2;
+        t.id[n] = std::move(id);
+        index.put(n);
+    };
     for (size_t c = 0; c < t.condensed_name.size(); ++c) {
-        auto it = index.find(t.condensed_name[c]);
-        if (it == index.end()) continue;
-        const int32_t n = it->second;
+        const int64_t at = index.find_slot(t.condensed_name[c]);
+        if (at < 0) continue;
+        const int32_t n = index.slot[(size_t)at];
         const int32_t par = t.parent[n] >= 0 ? t.parent[n] : n;
         const std::vector<std::string>& s = t.condensed_leaves[c];
         const bool has_muts = t.mut_off[n + 1] > t.mut_off[n];
         if (s.size() > 1 && has_muts) {
-            index.erase(it);
-            t.id[n] = "node_" + std::to_string(++t.n_internal_ids);
-            index[t.id[n]] = n;
+            rename(at, n, "node_" + std::to_string(++t.n_internal_ids));
             for (const std::string& leaf : s) added.push_back({n, leaf, -1.0f});
         } else if (s.size() > 1) {
-            index.erase(it);
-            t.id[n] = s[0];
-            index[t.id[n]] = n;
+            rename(at, n, s[0]);
             for (size_t k = 1; k < s.size(); ++k) added.push_back({par, s[k], t.branch_length[n]});
         } else if (s.size() == 1) {
-            index.erase(it);
-            t.id[n] = s[0];
-            index[t.id[n]] = n;
+            rename(at, n, s[0]);
         }
     }
+    lap("condensed nodes");
+    t.parent.reserve(t.parent.size() + added.size());
+    t.id.reserve(t.id.size() + added.size());
     for (NewNode& nn : added) {
         t.parent.push_back(nn.parent);
         t.id.push_back(std::move(nn.id));
@@ -620,6 +688,7 @@ void uncondense_leaves(MatTree& t) {
     }
     t.condensed_name.clear();
     t.condensed_leaves.clear();
+    lap("new leaves");
 }
 
 // ---- flattened-tree sidecar ----------------------------------------------------------------------
