@@ -1,3 +1,2 @@
 set -x
-timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('SMOKE_OK')" 2>&1 | tail -1
-timeout 200 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "tiny0 and delta" 2>&1 | tail -1
+cd profiles/microbench && g++ -O2 -std=c++17 -pthread uncondense_bench.cpp ../../wepp_b200/build/host_io.o -lz -o uncondense_bench && WEPP_TIMING=1 ./uncondense_bench 8000000 2>&1 | tail -6
