@@ -179,3 +179,21 @@ def test_product_fails_loudly_without_gpu():
     with pytest.raises(_lib.WeppError) as ei:
         Placer(0)
     assert "no CPU fallback" in str(ei.value)
+
+
+def test_group_fails_loudly_without_gpu_and_checks_its_arguments():
+    """wepp_group_*: no device, no group (and no crash); argument checks need no device at all."""
+    import torch
+    lib = _lib.load()
+    g = C.c_void_p()
+    assert lib.wepp_group_create(0, None, C.byref(g)) == -1 and b"ranks" in lib.wepp_last_error()
+    assert lib.wepp_group_create(17, None, C.byref(g)) == -1
+    assert lib.wepp_group_size(None) == 0 and lib.wepp_group_handle(None, 0) is None and lib.wepp_group_take(None, 0) is None
+    assert lib.wepp_group_place(None) == -1 and lib.wepp_group_run(None, None, None) == -1
+    lib.wepp_group_destroy(None)
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from wepp_b200.multigpu import Group
+    with pytest.raises(_lib.WeppError) as ei:
+        Group([0, 0])
+    assert "no CPU fallback" in str(ei.value)
